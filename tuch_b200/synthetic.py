@@ -1,0 +1,410 @@
+"""Deterministic synthetic stand-ins for the assets the reference loads from its
+un-shipped ``data/`` tree.
+
+Nothing here is learned data: a closed genus-0 "starfish" body (UV sphere whose
+pole axis is the arm axis, radially deformed into torso + head + 2 arms + 2 legs)
+with exactly V = rings*segs + 2 vertices and F = 2*V - 4 faces -- 84 x 82 gives the
+SMPL counts V=6890 / F=13776 -- plus SMPL-shaped blend-shape bases, joint
+regressors, skinning weights, a graph-geodesic matrix, DSC-style region pairs,
+ring-bounded body segments, an HD point regressor and an 8x69 GMM pose prior.
+
+The tensors have the shapes/dtypes of the real assets so that every kernel sees
+realistic sizes; the numbers themselves only need to (a) form a valid outward
+oriented closed mesh and (b) self-penetrate when the arms are folded inwards.
+
+Consumers: tests/, bench.py, __graft_entry__.smoke(), tests/golden/make_golden.py.
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+SMPL_PARENTS = np.array(
+    [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21],
+    dtype=np.int64)
+
+# 49 joint names / map into the 54 = 45 (24 posed + 21 picked) + 9 regressed joints.
+# Same public SPIN convention the reference reads from data.essentials.constants
+# (tuch/models/smpl.py:39-42); restated here as plain data.
+JOINT_NAMES = [
+    'OP Nose', 'OP Neck', 'OP RShoulder', 'OP RElbow', 'OP RWrist', 'OP LShoulder',
+    'OP LElbow', 'OP LWrist', 'OP MidHip', 'OP RHip', 'OP RKnee', 'OP RAnkle',
+    'OP LHip', 'OP LKnee', 'OP LAnkle', 'OP REye', 'OP LEye', 'OP REar', 'OP LEar',
+    'OP LBigToe', 'OP LSmallToe', 'OP LHeel', 'OP RBigToe', 'OP RSmallToe', 'OP RHeel',
+    'Right Ankle', 'Right Knee', 'Right Hip', 'Left Hip', 'Left Knee', 'Left Ankle',
+    'Right Wrist', 'Right Elbow', 'Right Shoulder', 'Left Shoulder', 'Left Elbow',
+    'Left Wrist', 'Neck (LSP)', 'Top of Head (LSP)', 'Pelvis (MPII)', 'Thorax (MPII)',
+    'Spine (H36M)', 'Jaw (H36M)', 'Head (H36M)', 'Nose', 'Left Eye', 'Right Eye',
+    'Left Ear', 'Right Ear']
+JOINT_MAP = {
+    'OP Nose': 24, 'OP Neck': 12, 'OP RShoulder': 17, 'OP RElbow': 19, 'OP RWrist': 21,
+    'OP LShoulder': 16, 'OP LElbow': 18, 'OP LWrist': 20, 'OP MidHip': 0, 'OP RHip': 2,
+    'OP RKnee': 5, 'OP RAnkle': 8, 'OP LHip': 1, 'OP LKnee': 4, 'OP LAnkle': 7,
+    'OP REye': 25, 'OP LEye': 26, 'OP REar': 27, 'OP LEar': 28, 'OP LBigToe': 29,
+    'OP LSmallToe': 30, 'OP LHeel': 31, 'OP RBigToe': 32, 'OP RSmallToe': 33,
+    'OP RHeel': 34, 'Right Ankle': 8, 'Right Knee': 5, 'Right Hip': 45, 'Left Hip': 46,
+    'Left Knee': 4, 'Left Ankle': 7, 'Right Wrist': 21, 'Right Elbow': 19,
+    'Right Shoulder': 17, 'Left Shoulder': 16, 'Left Elbow': 18, 'Left Wrist': 20,
+    'Neck (LSP)': 47, 'Top of Head (LSP)': 48, 'Pelvis (MPII)': 49, 'Thorax (MPII)': 50,
+    'Spine (H36M)': 51, 'Jaw (H36M)': 52, 'Head (H36M)': 53, 'Nose': 24, 'Left Eye': 26,
+    'Right Eye': 25, 'Left Ear': 28, 'Right Ear': 27}
+JOINT_IDS = {n: i for i, n in enumerate(JOINT_NAMES)}
+IGN_JOINTS = ['OP Neck', 'OP RHip', 'OP LHip', 'Right Hip', 'Left Hip']  # smplifydc.py:46
+FOCAL_LENGTH = 5000.0
+IMG_RES = 224
+
+
+def joint_map_indices():
+    """49 indices into the 54-joint set, in JOINT_NAMES order (tuch/models/smpl.py:39,42)."""
+    return np.array([JOINT_MAP[n] for n in JOINT_NAMES], dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------
+# mesh
+# ----------------------------------------------------------------------------------
+
+def _uv_sphere(rings: int, segs: int):
+    """Unit directions + faces of a UV sphere whose pole axis is +x/-x.
+
+    vertex 0 = +x pole, 1 + i*segs + j = ring i (polar angle pi*(i+1)/(rings+1)),
+    segment j; last vertex = -x pole.  Faces are counter-clockwise seen from outside.
+    """
+    th = np.pi * (np.arange(rings) + 1.0) / (rings + 1.0)
+    ph = 2.0 * np.pi * np.arange(segs) / segs
+    T, P = np.meshgrid(th, ph, indexing='ij')
+    dirs = np.stack([np.cos(T), np.sin(T) * np.cos(P), np.sin(T) * np.sin(P)], -1).reshape(-1, 3)
+    dirs = np.concatenate([[[1.0, 0, 0]], dirs, [[-1.0, 0, 0]]], 0)
+    vid = lambda i, j: 1 + i * segs + (j % segs)
+    south = 1 + rings * segs
+    faces = []
+    for j in range(segs):
+        faces.append((0, vid(0, j), vid(0, j + 1)))
+    for i in range(rings - 1):
+        for j in range(segs):
+            a, b, c, d = vid(i, j), vid(i, j + 1), vid(i + 1, j), vid(i + 1, j + 1)
+            faces.append((a, c, d))
+            faces.append((a, d, b))
+    for j in range(segs):
+        faces.append((south, vid(rings - 1, j + 1), vid(rings - 1, j)))
+    faces = np.asarray(faces, dtype=np.int64)
+    return dirs, faces
+
+
+# lobe axis (unit), length, angular sigma
+_LOBES = {
+    'larm': ((1.0, 0.10, 0.0), 0.62, 0.23),
+    'rarm': ((-1.0, 0.10, 0.0), 0.62, 0.23),
+    'head': ((0.0, 1.0, 0.0), 0.42, 0.36),
+    'lleg': ((0.28, -1.0, 0.0), 0.85, 0.24),
+    'rleg': ((-0.28, -1.0, 0.0), 0.85, 0.24),
+}
+_TORSO_R = 0.16
+
+
+def _radius(dirs):
+    r = np.full(len(dirs), _TORSO_R)
+    # torso is taller than wide/deep
+    r = r * (1.0 + 0.9 * dirs[:, 1] ** 2 - 0.25 * dirs[:, 2] ** 2)
+    for ax, length, sig in _LOBES.values():
+        ax = np.asarray(ax, float)
+        ax = ax / np.linalg.norm(ax)
+        ang = np.arccos(np.clip(dirs @ ax, -1.0, 1.0))
+        r = r + length * np.exp(-(ang / sig) ** 2)
+    return r
+
+
+def _joint_template():
+    """24 joint positions along the lobe axes (metres), SMPL kinematic order."""
+    def along(name, frac):
+        ax, length, _ = _LOBES[name]
+        ax = np.asarray(ax, float)
+        ax = ax / np.linalg.norm(ax)
+        return ax * (_TORSO_R + length) * frac
+    J = np.zeros((24, 3))
+    J[0] = (0, -0.02, 0)
+    J[1], J[2] = along('lleg', 0.16), along('rleg', 0.16)
+    J[3] = (0, 0.08, 0)
+    J[4], J[5] = along('lleg', 0.52), along('rleg', 0.52)
+    J[6] = (0, 0.17, 0)
+    J[7], J[8] = along('lleg', 0.86), along('rleg', 0.86)
+    J[9] = (0, 0.24, 0)
+    J[10], J[11] = along('lleg', 0.95), along('rleg', 0.95)
+    J[12] = along('head', 0.52)
+    J[13], J[14] = along('larm', 0.12), along('rarm', 0.12)
+    J[15] = along('head', 0.70)
+    J[16], J[17] = along('larm', 0.24), along('rarm', 0.24)
+    J[18], J[19] = along('larm', 0.56), along('rarm', 0.56)
+    J[20], J[21] = along('larm', 0.84), along('rarm', 0.84)
+    J[22], J[23] = along('larm', 0.94), along('rarm', 0.94)
+    return J
+
+
+def _seg_dist(p, a, b):
+    ab = b - a
+    t = np.clip(((p - a) @ ab) / max(ab @ ab, 1e-12), 0.0, 1.0)
+    return np.linalg.norm(p - (a + t[:, None] * ab), axis=1)
+
+
+def make_body_model(rings: int = 84, segs: int = 82, seed: int = 0, num_betas: int = 10):
+    """Synthetic SMPL-shaped body model.  Returns a dict of float32/int64 numpy arrays:
+
+    v_template[V,3], shapedirs[V,3,num_betas], posedirs[207,V*3], J_regressor[24,V],
+    lbs_weights[V,24], parents[24], faces[F,3], J_regressor_extra[9,V],
+    extra_vertex_ids[21], joint_map[49].
+    """
+    rng = np.random.default_rng(seed)
+    dirs, faces = _uv_sphere(rings, segs)
+    V = len(dirs)
+    v = dirs * _radius(dirs)[:, None]
+    v = v.astype(np.float32).astype(np.float64)
+    Jt = _joint_template()
+
+    # skinning weights: soft assignment to bones (joint -> first child, or the joint itself)
+    child = {}
+    for k in range(1, 24):
+        child.setdefault(int(SMPL_PARENTS[k]), k)
+    dist = np.zeros((V, 24))
+    for k in range(24):
+        a = Jt[k]
+        b = Jt[child[k]] if k in child else Jt[k] + (Jt[k] - Jt[SMPL_PARENTS[k]]) * 0.8
+        dist[:, k] = _seg_dist(v, a, b)
+    w = np.exp(-(dist / 0.045) ** 2) + 1e-12
+    # keep the 4 largest per vertex (SMPL weights are effectively 4-sparse)
+    idx = np.argsort(-w, axis=1)[:, 4:]
+    np.put_along_axis(w, idx, 0.0, axis=1)
+    w = w / w.sum(1, keepdims=True)
+
+    # joint regressor: convex combination of the 48 vertices nearest to each joint
+    Jreg = np.zeros((24, V))
+    for k in range(24):
+        d = np.linalg.norm(v - Jt[k], axis=1)
+        nn = np.argsort(d)[:48]
+        ww = 1.0 / (d[nn] + 0.02)
+        Jreg[k, nn] = ww / ww.sum()
+
+    # smooth, low-amplitude blend-shape bases
+    shapedirs = np.zeros((V, 3, num_betas))
+    for i in range(num_betas):
+        f = rng.uniform(1.0, 5.0, size=3)
+        ph = rng.uniform(0, 2 * np.pi, size=3)
+        amp = 0.025 / (1.0 + 0.35 * i)
+        field = np.sin(v * f + ph)                       # [V,3]
+        radial = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-6)
+        shapedirs[:, :, i] = amp * (0.7 * radial * field[:, [i % 3]] + 0.3 * field)
+    posedirs = np.zeros((207, V, 3))
+    for j in range(1, 24):
+        near = np.exp(-(np.linalg.norm(v - Jt[j], axis=1) / 0.12) ** 2)   # [V]
+        for e in range(9):
+            f = rng.uniform(2.0, 9.0, size=3)
+            ph = rng.uniform(0, 2 * np.pi, size=3)
+            posedirs[(j - 1) * 9 + e] = 0.012 * near[:, None] * np.sin(v * f + ph)
+    posedirs = posedirs.reshape(207, V * 3)
+
+    Jextra = np.zeros((9, V))
+    centres = rng.choice(V, size=9, replace=False)
+    for k, c in enumerate(centres):
+        d = np.linalg.norm(v - v[c], axis=1)
+        nn = np.argsort(d)[:32]
+        ww = rng.uniform(0.2, 1.0, size=32)
+        Jextra[k, nn] = ww / ww.sum()
+
+    extra_vertex_ids = (np.array([332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624,
+                                  6787, 2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905,
+                                  6016, 6133], dtype=np.int64) % V)
+    return dict(
+        v_template=v.astype(np.float32),
+        shapedirs=shapedirs.astype(np.float32),
+        posedirs=posedirs.astype(np.float32),
+        J_regressor=Jreg.astype(np.float32),
+        lbs_weights=w.astype(np.float32),
+        parents=SMPL_PARENTS.copy(),
+        faces=faces,
+        J_regressor_extra=Jextra.astype(np.float32),
+        extra_vertex_ids=extra_vertex_ids,
+        joint_map=joint_map_indices(),
+        rings=np.int64(rings), segs=np.int64(segs),
+    )
+
+
+# ----------------------------------------------------------------------------------
+# geodesics, regions, segments, HD regressor, prior
+# ----------------------------------------------------------------------------------
+
+def make_geodesics(v_template, faces, cache_dir: str | None = None):
+    """[V,V] float32 graph-shortest-path distances over the template edges (a stand-in for
+    smpl_neutral_geodesic_dist.npy, configs/config.py:85).  Cached on disk when cache_dir is given."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import dijkstra
+    V = len(v_template)
+    key = None
+    if cache_dir is not None:
+        import hashlib
+        h = hashlib.sha1(np.ascontiguousarray(v_template).tobytes() + np.ascontiguousarray(faces).tobytes())
+        key = os.path.join(cache_dir, 'geo_%s.npy' % h.hexdigest()[:16])
+        if os.path.exists(key):
+            return np.load(key)
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], 0)
+    e = np.unique(np.sort(e, axis=1), axis=0)
+    wgt = np.linalg.norm(v_template[e[:, 0]].astype(np.float64) - v_template[e[:, 1]], axis=1)
+    g = coo_matrix((wgt, (e[:, 0], e[:, 1])), shape=(V, V))
+    d = dijkstra(g, directed=False).astype(np.float32)
+    d = np.minimum(d, d.T)
+    if key is not None:
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = key + '.%d.tmp.npy' % os.getpid()
+        np.save(tmp, d)
+        os.replace(tmp, key)
+    return d
+
+
+def make_regions(model, n_regions: int = 24, max_pairs: int = 60, seed: int = 0):
+    """DSC-style contact signature: csig {region name: vertex-id list} and classes
+    (sorted (regionA, regionB) name pairs), cf. tuch/train/train_module.py:65-67."""
+    rng = np.random.default_rng(seed + 17)
+    w = model['lbs_weights']
+    owner = np.argmax(w, axis=1)
+    csig = {}
+    for k in range(24):
+        ids = np.where(owner == k)[0]
+        if len(ids) == 0:
+            continue
+        if len(ids) > 400:            # keep regions at the size of real DSC regions
+            ids = np.sort(rng.choice(ids, size=400, replace=False))
+        csig['region_%02d' % k] = [int(i) for i in ids]
+    names = sorted(csig.keys())[:n_regions]
+    Jt = model['J_regressor'] @ model['v_template']
+    pairs = []
+    for a in range(len(names)):
+        for b in range(a + 1, len(names)):
+            ka, kb = int(names[a][-2:]), int(names[b][-2:])
+            if SMPL_PARENTS[ka] == kb or SMPL_PARENTS[kb] == ka:
+                continue
+            pairs.append((names[a], names[b], np.linalg.norm(Jt[ka] - Jt[kb])))
+    rng.shuffle(pairs)
+    classes = [(a, b) for a, b, _ in pairs[:max_pairs]]
+    return {'classes': classes, 'csig': csig}
+
+
+def make_segments(model):
+    """Ring-bounded body segments in the format of data.essentials.segments.smpl.segm_utils
+    (tuch/utils/segmentation.py:40-46): {name: {'vidx': member vertex ids,
+    'bands': {band name: closed vertex loop (first vertex repeated at the end)}}}.
+
+    The mesh's pole axis is the arm axis, so ring ranges are arm segments; loops are ordered
+    so that the cap fan [loop[i+1], loop[i], centroid] (segmentation.py:56-66) faces outward.
+    """
+    rings, segs = int(model['rings']), int(model['segs'])
+    V = rings * segs + 2
+    ring = lambda i: [1 + i * segs + j for j in range(segs)]
+    out = {}
+
+    def loop(i, towards_plus_x):
+        r = ring(i)
+        r = r + [r[0]]
+        # ring vertices are counter-clockwise seen from +x.  Fan faces are [l[i+1], l[i], c]:
+        # with l counter-clockwise from +x the fan normal points to -x.
+        return r if not towards_plus_x else r[::-1]
+
+    q1, q2 = max(2, rings // 6), max(4, rings // 3)
+    # left arm tip: pole 0 + rings [0, q1): one band at ring q1-1 whose cap faces -x
+    out['left_hand_arm'] = {
+        'vidx': [0] + [v for i in range(q1) for v in ring(i)],
+        'bands': {'wrist': loop(q1 - 1, towards_plus_x=False)}}
+    # left upper arm: rings [q1-1, q2): two bands
+    out['left_upper_arm'] = {
+        'vidx': [v for i in range(q1 - 1, q2) for v in ring(i)],
+        'bands': {'elbow': loop(q1 - 1, towards_plus_x=True),
+                  'shoulder': loop(q2 - 1, towards_plus_x=False)}}
+    out['right_hand_arm'] = {
+        'vidx': [V - 1] + [v for i in range(rings - q1, rings) for v in ring(i)],
+        'bands': {'wrist': loop(rings - q1, towards_plus_x=True)}}
+    out['right_upper_arm'] = {
+        'vidx': [v for i in range(rings - q2, rings - q1 + 1) for v in ring(i)],
+        'bands': {'elbow': loop(rings - q1, towards_plus_x=False),
+                  'shoulder': loop(rings - q2, towards_plus_x=True)}}
+    for s in out.values():           # a .ply colour mask yields ascending ids (segmentation.py:42)
+        s['vidx'] = sorted(s['vidx'])
+    return out
+
+
+def make_hd_regressor(model, n_hd: int | None = None, seed: int = 0):
+    """Dense [N_hd, V] barycentric point regressor + faces_vert_is_sampled_from[N_hd]
+    (tuch/train/loss.py:81-88).  Points are sampled uniformly per face area."""
+    rng = np.random.default_rng(seed + 29)
+    v, f = model['v_template'].astype(np.float64), model['faces']
+    V, F = len(v), len(f)
+    if n_hd is None:
+        n_hd = int(round(2.9 * V))            # ~20 k points for V=6890
+    area = 0.5 * np.linalg.norm(np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]]), axis=1)
+    fidx = np.sort(rng.choice(F, size=n_hd, p=area / area.sum()))
+    u = rng.uniform(size=(n_hd, 2))
+    su = np.sqrt(u[:, 0])
+    bary = np.stack([1 - su, su * (1 - u[:, 1]), su * u[:, 1]], 1)
+    reg = np.zeros((n_hd, V), dtype=np.float32)
+    for c in range(3):
+        reg[np.arange(n_hd), f[fidx, c]] = bary[:, c]
+    return reg, fidx.astype(np.int64)
+
+
+def make_gmm(seed: int = 0, m: int = 8, d: int = 69):
+    """gmm_08.pkl stand-in (tuch/smplify/prior.py:55-69): means[m,d], covars[m,d,d], weights[m]."""
+    rng = np.random.default_rng(seed + 41)
+    means = rng.normal(0, 0.15, size=(m, d))
+    covs = []
+    for _ in range(m):
+        a = rng.normal(0, 1.0, size=(d, d)) / np.sqrt(d)
+        covs.append(0.05 * (a @ a.T) + 0.02 * np.eye(d))
+    wts = rng.uniform(0.5, 1.5, size=m)
+    return dict(means=means, covars=np.stack(covs), weights=wts / wts.sum())
+
+
+# ----------------------------------------------------------------------------------
+# SMPLify-DC inputs (SURVEY.md 8(d) config 2 distributions)
+# ----------------------------------------------------------------------------------
+
+def fold_arms_pose(batch: int, seed: int = 0, sigma: float = 0.3, fold: float = 1.0):
+    """[batch,72] axis-angle poses ~ N(0, sigma^2) with the arms rotated towards the torso
+    so that both the push (interior) and pull (near-contact) branches are populated."""
+    rng = np.random.default_rng(seed + 101)
+    pose = rng.normal(0, sigma, size=(batch, 72)).astype(np.float32) * 0.35
+    amt = rng.uniform(0.6, 1.25, size=(batch, 2)).astype(np.float32) * fold
+    # shoulders (16, 17) rotate about z (arms are along +-x): bring them down/in
+    pose[:, 16 * 3 + 2] += -1.15 * amt[:, 0]
+    pose[:, 17 * 3 + 2] += 1.15 * amt[:, 1]
+    # elbows (18, 19) bend back towards the torso
+    pose[:, 18 * 3 + 2] += -1.3 * amt[:, 0]
+    pose[:, 19 * 3 + 2] += 1.3 * amt[:, 1]
+    pose[:, :3] = rng.normal(0, 0.1, size=(batch, 3))
+    return pose
+
+
+def make_smplify_inputs(model, regions, batch: int, seed: int = 0, joints_fn=None):
+    """Synthetic SMPLify-DC call arguments (shapes of smplifydc.py:68-74).
+
+    joints_fn(pose[B,72], betas[B,10]) -> joints[B,49,3] is used to project a *target*
+    pose into keypoints; when None the keypoints are random but well-formed.
+    """
+    rng = np.random.default_rng(seed + 211)
+    init_pose = fold_arms_pose(batch, seed=seed, fold=0.9)
+    init_betas = rng.normal(0, 0.5, size=(batch, 10)).astype(np.float32)
+    cam_t = np.tile(np.array([[0.0, 0.0, 2 * FOCAL_LENGTH / (IMG_RES * 0.9)]], np.float32), (batch, 1))
+    cam_t = cam_t + rng.normal(0, 0.05, size=(batch, 3)).astype(np.float32)
+    center = np.full((batch, 2), IMG_RES / 2.0, np.float32)
+    kp = np.zeros((batch, 49, 3), np.float32)
+    if joints_fn is not None:
+        tgt_pose = fold_arms_pose(batch, seed=seed + 1, fold=1.1)
+        j = joints_fn(tgt_pose, init_betas)
+        p = j + cam_t[:, None, :]
+        kp[:, :, :2] = FOCAL_LENGTH * p[:, :, :2] / p[:, :, 2:3] + center[:, None, :]
+        kp[:, :, :2] += rng.normal(0, 2.0, size=(batch, 49, 2))
+    else:
+        kp[:, :, :2] = rng.uniform(40, 184, size=(batch, 49, 2))
+    kp[:, :, 2] = rng.uniform(0.5, 1.0, size=(batch, 49))
+    n_cls = len(regions['classes'])
+    gt = np.zeros((batch, n_cls), np.float32)
+    for b in range(batch):
+        k = rng.integers(1, 4)
+        gt[b, rng.choice(n_cls, size=k, replace=False)] = 1.0
+    return dict(init_pose=init_pose, init_betas=init_betas, init_cam_t=cam_t.astype(np.float32),
+                camera_center=center, keypoints_2d=kp, gt_contact=gt,
+                has_discrete_contact=np.ones(batch, bool), ignore_idxs=np.zeros(batch, bool))
