@@ -1,0 +1,61 @@
+"""ctypes loader for libtuch_b200.so (the C ABI in include/tuch_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, a
+TuchError is raised."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+
+class TuchError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    lib.tuch_last_error.restype = C.c_char_p
+    lib.tuch_last_error.argtypes = []
+    lib.tuch_abi_version.restype = i32
+    lib.tuch_launch_count.restype = C.c_longlong
+    lib.tuch_device_info.argtypes = [C.POINTER(i32)] * 3
+    lib.tuch_release_scratch.argtypes = []
+    lib.tuch_pairwise_dist.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.tuch_pairwise_dist_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.tuch_solid_angles.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.tuch_winding_numbers.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.tuch_topology_create.argtypes = [i32, i32, vp, C.POINTER(vp)]
+    lib.tuch_topology_destroy.argtypes = [vp]
+    lib.tuch_topology_destroy.restype = None
+    lib.tuch_topology_num_verts.argtypes = [vp]
+    lib.tuch_topology_num_faces.argtypes = [vp]
+    lib.tuch_topology_total_segment_verts.argtypes = [vp]
+    lib.tuch_topology_set_geodist.argtypes = [vp, vp, f32, vp]
+    lib.tuch_topology_set_geomask.argtypes = [vp, vp, vp]
+    lib.tuch_topology_set_regions.argtypes = [vp, i32, vp, vp, i32, vp, vp]
+    lib.tuch_topology_set_segments.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.tuch_contact_query.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.tuch_segment_exterior.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.tuch_region_min.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.tuch_winding_numbers_host.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.tuch_contact_query_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            raise TuchError('%s is missing: run `python -m tuch_b200.build` (or __graft_entry__.build()); '
+                            'tuch_b200 has no CPU fallback' % path)
+        _lib = C.CDLL(path)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().tuch_last_error().decode('utf-8', 'replace')
+        raise TuchError('%s failed (%d): %s' % (what or 'tuch_b200 call', rc, msg))

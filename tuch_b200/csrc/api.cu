@@ -1,0 +1,501 @@
+// C ABI (include/tuch_b200.h): status, scratch arenas, mesh topology and the contact entry points.
+#include "api_internal.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+namespace tuch {
+
+// ---------------------------------------------------------------- status
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    return 2;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// ---------------------------------------------------------------- scratch arenas
+struct Arena { void* ptr = nullptr; size_t cap = 0; };
+static std::mutex g_arena_mu;
+static std::map<std::pair<int, cudaStream_t>, Arena> g_arenas;
+
+int arena_get(cudaStream_t st, size_t bytes, void** out) {
+    int dev = 0;
+    TUCH_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    Arena& a = g_arenas[{dev, st}];
+    if (a.cap < bytes) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        TUCH_REQUIRE(cs == cudaStreamCaptureStatusNone,
+                     "scratch arena must grow (%zu -> %zu bytes) during CUDA-graph capture; run the call once "
+                     "outside the capture first", a.cap, bytes);
+        if (a.ptr != nullptr) {
+            TUCH_CUDA(cudaStreamSynchronize(st));
+            TUCH_CUDA(cudaFree(a.ptr));
+            a.ptr = nullptr; a.cap = 0;
+        }
+        const size_t want = align_up(bytes + bytes / 4, (size_t)1 << 20);
+        TUCH_CUDA(cudaMalloc(&a.ptr, want));
+        a.cap = want;
+    }
+    *out = a.ptr;
+    return 0;
+}
+
+int Scratch::commit(cudaStream_t st) {
+    void* p = nullptr;
+    if (int rc = arena_get(st, total_ > 0 ? total_ : 256, &p)) return rc;
+    base_ = (char*)p;
+    return 0;
+}
+
+}  // namespace tuch
+
+using namespace tuch;
+
+// ================================================================ status
+TUCH_EXPORT const char* tuch_last_error(void) { return g_err; }
+TUCH_EXPORT int tuch_abi_version(void) { return TUCH_B200_ABI_VERSION; }
+TUCH_EXPORT long long tuch_launch_count(void) { return g_launches.load(); }
+
+TUCH_EXPORT int tuch_device_info(int* sms, int* cc_major, int* cc_minor) {
+    int dev = 0, mj = 0, mn = 0, n = 0;
+    TUCH_CUDA(cudaGetDevice(&dev));
+    TUCH_CUDA(cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev));
+    TUCH_CUDA(cudaDeviceGetAttribute(&mn, cudaDevAttrComputeCapabilityMinor, dev));
+    TUCH_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (sms) *sms = n;
+    if (cc_major) *cc_major = mj;
+    if (cc_minor) *cc_minor = mn;
+    TUCH_REQUIRE(mj == 10, "tuch_b200 is built for sm_100a only; current device is sm_%d%d", mj, mn);
+    return 0;
+}
+
+TUCH_EXPORT int tuch_release_scratch(void) {
+    int dev = 0;
+    TUCH_CUDA(cudaGetDevice(&dev));
+    TUCH_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (auto it = g_arenas.begin(); it != g_arenas.end();) {
+        if (it->first.first == dev) {
+            if (it->second.ptr) cudaFree(it->second.ptr);
+            it = g_arenas.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    return 0;
+}
+
+// ================================================================ a1..a3
+TUCH_EXPORT int tuch_pairwise_dist(const float* x, const float* y, int bs, int nx, int ny, int squared,
+                                   float* P, void* stream) {
+    TUCH_REQUIRE(bs >= 0 && nx >= 0 && ny >= 0, "tuch_pairwise_dist: negative size");
+    if (bs == 0 || nx == 0 || ny == 0) return 0;
+    TUCH_REQUIRE(x && y && P, "tuch_pairwise_dist: null pointer");
+    return launch_pairwise_dist(x, y, bs, nx, ny, squared, P, (cudaStream_t)stream);
+}
+
+TUCH_EXPORT int tuch_pairwise_dist_backward(const float* x, const float* y, const float* P, const float* gP,
+                                            int bs, int nx, int ny, int squared, float* gx, float* gy,
+                                            void* stream) {
+    TUCH_REQUIRE(bs >= 0 && nx >= 0 && ny >= 0, "tuch_pairwise_dist_backward: negative size");
+    if (bs == 0) return 0;
+    TUCH_REQUIRE(x && y && gP && (squared || P), "tuch_pairwise_dist_backward: null pointer");
+    return launch_pairwise_dist_bwd(x, y, P, gP, bs, nx, ny, squared, gx, gy, (cudaStream_t)stream);
+}
+
+TUCH_EXPORT int tuch_solid_angles(const float* points, const float* triangles, int bs, int Q, int F,
+                                  float* out, void* stream) {
+    TUCH_REQUIRE(bs >= 0 && Q >= 0 && F >= 0, "tuch_solid_angles: negative size");
+    if (bs == 0 || Q == 0 || F == 0) return 0;
+    TUCH_REQUIRE(points && triangles && out, "tuch_solid_angles: null pointer");
+    return launch_solid_angles(points, triangles, bs, Q, F, out, (cudaStream_t)stream);
+}
+
+TUCH_EXPORT int tuch_winding_numbers(const float* points, const float* triangles, int bs, int Q, int F,
+                                     float* out, void* stream) {
+    TUCH_REQUIRE(bs >= 0 && Q >= 0 && F >= 0, "tuch_winding_numbers: negative size");
+    if (bs == 0 || Q == 0) return 0;
+    TUCH_REQUIRE(points && out, "tuch_winding_numbers: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F == 0) {                                     // empty sum (contact.py:146-147)
+        TUCH_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)bs * Q, st));
+        return 0;
+    }
+    TUCH_REQUIRE(triangles, "tuch_winding_numbers: null pointer");
+    const int Fp = padded_faces(F);
+    const int S = winding_splits(bs, Q, Fp, sm_count());
+    Scratch sc;
+    auto h_tri = sc.plan(sizeof(float4) * 3 * (size_t)bs * Fp);
+    auto h_par = sc.plan(sizeof(float) * (size_t)bs * S * Q);
+    if (int rc = sc.commit(st)) return rc;
+    float4* tri12 = sc.get<float4>(h_tri);
+    float* partial = sc.get<float>(h_par);
+    if (int rc = launch_pack_triangles(triangles, bs, F, Fp, tri12, st)) return rc;
+    WindingJob j{tri12, (long long)Fp * 3, points, (long long)Q * 3, partial, out, (long long)Q, nullptr, bs, Q, Fp, S};
+    return launch_winding(j, st);
+}
+
+// ================================================================ topology
+static void free_dev(void* p) { if (p) cudaFree(p); }
+
+template <typename T>
+static int upload(const T* host, size_t n, T** dev) {
+    *dev = nullptr;
+    if (n == 0) return 0;
+    TUCH_CUDA(cudaMalloc((void**)dev, n * sizeof(T)));
+    TUCH_CUDA(cudaMemcpy(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_create(int V, int F, const int32_t* faces_host, tuch_topology** out) {
+    TUCH_REQUIRE(out != nullptr, "tuch_topology_create: out is null");
+    *out = nullptr;
+    TUCH_REQUIRE(V > 0 && F >= 0, "tuch_topology_create: need V > 0, F >= 0 (got V=%d F=%d)", V, F);
+    TUCH_REQUIRE(F == 0 || faces_host != nullptr, "tuch_topology_create: faces is null");
+    for (size_t i = 0; i < (size_t)F * 3; ++i)
+        TUCH_REQUIRE(faces_host[i] >= 0 && faces_host[i] < V, "tuch_topology_create: face index %d out of range [0,%d)",
+                     faces_host[i], V);
+    tuch_topology* t = new tuch_topology();
+    TUCH_CUDA(cudaGetDevice(&t->device));
+    t->V = V; t->F = F;
+    t->Fp = padded_faces(F); t->Vp = padded_verts(V); t->Vq = padded_verts(V); t->W = cdiv(V, 32);
+    if (int rc = upload(faces_host, (size_t)F * 3, &t->d_faces)) { delete t; return rc; }
+    *out = t;
+    return 0;
+}
+
+static void free_regions(tuch_topology* t) {
+    free_dev(t->d_region_off); free_dev(t->d_region_ids); free_dev(t->d_pair_a); free_dev(t->d_pair_b);
+    t->d_region_off = t->d_region_ids = t->d_pair_a = t->d_pair_b = nullptr;
+    t->n_regions = t->n_pairs = 0;
+}
+static void free_segments(tuch_topology* t) {
+    free_dev(t->d_seg_vidx); free_dev(t->d_seg_faces); free_dev(t->d_slot_face); free_dev(t->d_slot_band0);
+    free_dev(t->d_loop_off); free_dev(t->d_loop_ids);
+    t->d_seg_vidx = t->d_seg_faces = t->d_slot_face = t->d_slot_band0 = t->d_loop_off = t->d_loop_ids = nullptr;
+    t->n_segments = t->n_bands = t->n_sv = t->n_slots = 0;
+    t->h_vidx_off.clear(); t->h_slot_off.clear();
+}
+
+TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
+    if (!t) return;
+    free_dev(t->d_faces); free_dev(t->d_maskT);
+    free_regions(t); free_segments(t);
+    delete t;
+}
+TUCH_EXPORT int tuch_topology_num_verts(const tuch_topology* t) { return t ? t->V : -1; }
+TUCH_EXPORT int tuch_topology_num_faces(const tuch_topology* t) { return t ? t->F : -1; }
+TUCH_EXPORT int tuch_topology_total_segment_verts(const tuch_topology* t) { return t ? t->n_sv : -1; }
+
+static int ensure_mask(tuch_topology* t) {
+    if (t->d_maskT == nullptr)
+        TUCH_CUDA(cudaMalloc((void**)&t->d_maskT, sizeof(uint32_t) * (size_t)t->W * t->Vq));
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_set_geodist(tuch_topology* t, const float* geodist, float geothres, void* stream) {
+    TUCH_REQUIRE(t && geodist, "tuch_topology_set_geodist: null pointer");
+    if (int rc = ensure_mask(t)) return rc;
+    if (int rc = launch_pack_mask(nullptr, geodist, geothres, t->V, t->Vq, t->W, t->d_maskT, (cudaStream_t)stream)) return rc;
+    t->has_mask = true;
+    return 0;
+}
+TUCH_EXPORT int tuch_topology_set_geomask(tuch_topology* t, const uint8_t* geomask, void* stream) {
+    TUCH_REQUIRE(t && geomask, "tuch_topology_set_geomask: null pointer");
+    if (int rc = ensure_mask(t)) return rc;
+    if (int rc = launch_pack_mask(geomask, nullptr, 0.f, t->V, t->Vq, t->W, t->d_maskT, (cudaStream_t)stream)) return rc;
+    t->has_mask = true;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_set_regions(tuch_topology* t, int n_regions, const int32_t* off, const int32_t* ids,
+                                          int n_pairs, const int32_t* pa, const int32_t* pb) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_set_regions: null topology");
+    TUCH_REQUIRE(n_regions >= 0 && n_pairs >= 0, "tuch_topology_set_regions: negative count");
+    TUCH_REQUIRE(n_regions == 0 || (off && ids), "tuch_topology_set_regions: null region arrays");
+    TUCH_REQUIRE(n_pairs == 0 || (pa && pb), "tuch_topology_set_regions: null pair arrays");
+    for (int r = 0; r < n_regions; ++r)
+        TUCH_REQUIRE(off[r + 1] > off[r], "tuch_topology_set_regions: region %d is empty", r);
+    const int total = n_regions ? off[n_regions] : 0;
+    for (int i = 0; i < total; ++i)
+        TUCH_REQUIRE(ids[i] >= 0 && ids[i] < t->V, "tuch_topology_set_regions: vertex id %d out of range", ids[i]);
+    for (int p = 0; p < n_pairs; ++p)
+        TUCH_REQUIRE(pa[p] >= 0 && pa[p] < n_regions && pb[p] >= 0 && pb[p] < n_regions,
+                     "tuch_topology_set_regions: pair %d names an unknown region", p);
+    free_regions(t);
+    if (int rc = upload(off, (size_t)n_regions + 1, &t->d_region_off)) return rc;
+    if (int rc = upload(ids, (size_t)total, &t->d_region_ids)) return rc;
+    if (int rc = upload(pa, (size_t)n_pairs, &t->d_pair_a)) return rc;
+    if (int rc = upload(pb, (size_t)n_pairs, &t->d_pair_b)) return rc;
+    t->n_regions = n_regions; t->n_pairs = n_pairs;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_set_segments(tuch_topology* t, int n_segments, const int32_t* vidx_off,
+                                           const int32_t* vidx, const int32_t* face_off, const int32_t* faces,
+                                           const int32_t* band_off, const int32_t* loop_off,
+                                           const int32_t* loop_ids) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_set_segments: null topology");
+    TUCH_REQUIRE(n_segments >= 0, "tuch_topology_set_segments: negative count");
+    free_segments(t);
+    if (n_segments == 0) return 0;
+    TUCH_REQUIRE(vidx_off && vidx && face_off && faces && band_off && loop_off && loop_ids,
+                 "tuch_topology_set_segments: null array");
+    const int n_sv = vidx_off[n_segments], n_sf = face_off[n_segments], n_bands = band_off[n_segments];
+    const int n_loop = loop_off[n_bands];
+    for (int i = 0; i < n_sv; ++i)
+        TUCH_REQUIRE(vidx[i] >= 0 && vidx[i] < t->V, "tuch_topology_set_segments: member vertex %d out of range", vidx[i]);
+    for (int i = 0; i < n_loop; ++i)
+        TUCH_REQUIRE(loop_ids[i] >= 0 && loop_ids[i] < t->V, "tuch_topology_set_segments: loop vertex %d out of range", loop_ids[i]);
+    for (int j = 0; j < n_bands; ++j)
+        TUCH_REQUIRE(loop_off[j + 1] > loop_off[j], "tuch_topology_set_segments: band %d has an empty loop", j);
+    std::vector<int> slot_face, slot_band0;
+    t->h_vidx_off.assign(vidx_off, vidx_off + n_segments + 1);
+    t->h_slot_off.assign(1, 0);
+    for (int s = 0; s < n_segments; ++s) {
+        const int nb = band_off[s + 1] - band_off[s];
+        for (int f = face_off[s]; f < face_off[s + 1]; ++f)
+            for (int k = 0; k < 3; ++k)
+                TUCH_REQUIRE(faces[3 * f + k] >= 0 && faces[3 * f + k] < t->V + nb,
+                             "tuch_topology_set_segments: segment %d face index %d out of range", s, faces[3 * f + k]);
+        const int nf = face_off[s + 1] - face_off[s];
+        const int nfp = padded_faces(nf);
+        for (int i = 0; i < nfp; ++i) {
+            slot_face.push_back(i < nf ? face_off[s] + i : -1);
+            slot_band0.push_back(band_off[s]);
+        }
+        t->h_slot_off.push_back((int)slot_face.size());
+    }
+    if (int rc = upload(vidx, (size_t)n_sv, &t->d_seg_vidx)) return rc;
+    if (int rc = upload(faces, (size_t)n_sf * 3, &t->d_seg_faces)) return rc;
+    if (int rc = upload(slot_face.data(), slot_face.size(), &t->d_slot_face)) return rc;
+    if (int rc = upload(slot_band0.data(), slot_band0.size(), &t->d_slot_band0)) return rc;
+    if (int rc = upload(loop_off, (size_t)n_bands + 1, &t->d_loop_off)) return rc;
+    if (int rc = upload(loop_ids, (size_t)n_loop, &t->d_loop_ids)) return rc;
+    t->n_segments = n_segments; t->n_bands = n_bands; t->n_sv = n_sv; t->n_slots = (int)slot_face.size();
+    return 0;
+}
+
+// ================================================================ fused self-contact query
+namespace tuch {
+
+// Segment pass shared by tuch_contact_query and tuch_segment_exterior.
+struct SegPlan {
+    size_t apex, tri, pts, wind;
+    std::vector<size_t> partial;
+    std::vector<int> S;
+};
+
+static void plan_segments(const tuch_topology* t, int B, Scratch& sc, SegPlan& p) {
+    p.apex = sc.plan(sizeof(float) * 3 * (size_t)B * (t->n_bands > 0 ? t->n_bands : 1));
+    p.tri = sc.plan(sizeof(float4) * 3 * (size_t)B * t->n_slots);
+    p.pts = sc.plan(sizeof(float) * 3 * (size_t)B * t->n_sv);
+    p.wind = sc.plan(sizeof(float) * (size_t)B * t->n_sv);
+    for (int s = 0; s < t->n_segments; ++s) {
+        const int Q = t->h_vidx_off[s + 1] - t->h_vidx_off[s];
+        const int Fp = t->h_slot_off[s + 1] - t->h_slot_off[s];
+        const int S = winding_splits(B, Q, Fp, sm_count());
+        p.S.push_back(S);
+        p.partial.push_back(sc.plan(sizeof(float) * (size_t)B * S * Q));
+    }
+}
+
+static int run_segments(const tuch_topology* t, const float* verts, int B, Scratch& sc, const SegPlan& p,
+                        const uint8_t* body_active, uint8_t* exterior, uint8_t* seg_ext_out, float* seg_w_out,
+                        cudaStream_t st) {
+    float* apex = sc.get<float>(p.apex);
+    float4* tri = sc.get<float4>(p.tri);
+    float* pts = sc.get<float>(p.pts);
+    float* wind = seg_w_out ? seg_w_out : sc.get<float>(p.wind);
+    if (int rc = launch_segment_apex(verts, B, t->V, t->d_loop_off, t->d_loop_ids, t->n_bands, apex, body_active, st)) return rc;
+    if (int rc = launch_segment_pack(verts, B, t->V, apex, t->n_bands, t->d_seg_faces, t->d_slot_face, t->d_slot_band0,
+                                     t->n_slots, t->d_seg_vidx, t->n_sv, tri, pts, body_active, st)) return rc;
+    for (int s = 0; s < t->n_segments; ++s) {
+        const int Q = t->h_vidx_off[s + 1] - t->h_vidx_off[s];
+        const int Fp = t->h_slot_off[s + 1] - t->h_slot_off[s];
+        WindingJob j{tri + (size_t)t->h_slot_off[s] * 3, (long long)t->n_slots * 3,
+                     pts + (size_t)t->h_vidx_off[s] * 3, (long long)t->n_sv * 3,
+                     sc.get<float>(p.partial[s]), wind + t->h_vidx_off[s], (long long)t->n_sv,
+                     body_active, B, Q, Fp, p.S[s]};
+        if (int rc = launch_winding(j, st)) return rc;
+    }
+    return launch_segment_apply(wind, t->d_seg_vidx, t->n_sv, B, t->V, exterior, seg_ext_out, body_active, st);
+}
+
+int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
+                       float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st) {
+    TUCH_REQUIRE(t != nullptr, "tuch_contact_query: null topology");
+    TUCH_REQUIRE(B >= 0, "tuch_contact_query: negative batch");
+    if (B == 0) return 0;
+    TUCH_REQUIRE(verts != nullptr, "tuch_contact_query: verts is null");
+    const bool want_w = winding != nullptr || exterior != nullptr;
+    const bool want_nn = argmin != nullptr || min_sq != nullptr;
+    TUCH_REQUIRE(!want_nn || t->has_mask,
+                 "tuch_contact_query: nearest-vertex outputs requested but the topology has no geodesic mask "
+                 "(call tuch_topology_set_geodist / tuch_topology_set_geomask)");
+    TUCH_REQUIRE(!want_w || t->F > 0, "tuch_contact_query: winding requested on a topology without faces");
+    const bool segs = exterior != nullptr && use_segments && t->n_segments > 0;
+    const int V = t->V, Fp = t->Fp, Vp = t->Vp;
+    const int S = want_w ? winding_splits(B, V, Fp, sm_count()) : 1;
+
+    Scratch sc;
+    const size_t h_tri = sc.plan(want_w ? sizeof(float4) * 3 * (size_t)B * Fp : 0);
+    const size_t h_v4 = sc.plan((want_nn && !vert4_out) ? sizeof(float4) * (size_t)B * Vp : 0);
+    const size_t h_par = sc.plan(want_w ? sizeof(float) * (size_t)B * S * V : 0);
+    const size_t h_w = sc.plan((want_w && !winding) ? sizeof(float) * (size_t)B * V : 0);
+    const size_t h_any = sc.plan(segs ? (size_t)B : 0);
+    const size_t h_am = sc.plan((want_nn && !argmin) ? sizeof(int) * (size_t)B * V : 0);
+    const size_t h_mn = sc.plan((want_nn && !min_sq) ? sizeof(float) * (size_t)B * V : 0);
+    SegPlan sp;
+    if (segs) plan_segments(t, B, sc, sp);
+    if (int rc = sc.commit(st)) return rc;
+
+    float4* tri12 = want_w ? sc.get<float4>(h_tri) : nullptr;
+    float4* vert4 = want_nn ? (vert4_out ? vert4_out : sc.get<float4>(h_v4)) : vert4_out;
+    if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, tri12, vert4, st)) return rc;
+
+    if (want_w) {
+        float* w = winding ? winding : sc.get<float>(h_w);
+        WindingJob j{tri12, (long long)Fp * 3, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V,
+                     nullptr, B, V, Fp, S};
+        if (int rc = launch_winding(j, st)) return rc;
+        if (exterior) {
+            uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;
+            if (any) TUCH_CUDA(cudaMemsetAsync(any, 0, (size_t)B, st));
+            if (int rc = launch_exterior_init(w, B, V, exterior, any, st)) return rc;
+            if (segs)
+                if (int rc = run_segments(t, verts, B, sc, sp, any, exterior, nullptr, nullptr, st)) return rc;
+        }
+    }
+    if (want_nn) {
+        int* am = argmin ? argmin : sc.get<int>(h_am);
+        float* mn = min_sq ? min_sq : sc.get<float>(h_mn);
+        if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace tuch
+
+TUCH_EXPORT int tuch_contact_query(const tuch_topology* topo, const float* verts, int B, int use_segments,
+                                   int32_t* argmin, float* min_sq, float* winding, uint8_t* exterior,
+                                   void* stream) {
+    return contact_query_impl(topo, verts, B, use_segments, argmin, min_sq, winding, exterior, nullptr,
+                              (cudaStream_t)stream);
+}
+
+TUCH_EXPORT int tuch_segment_exterior(const tuch_topology* t, const float* verts, int B, uint8_t* out,
+                                      float* winding_out, void* stream) {
+    TUCH_REQUIRE(t != nullptr, "tuch_segment_exterior: null topology");
+    TUCH_REQUIRE(B >= 0, "tuch_segment_exterior: negative batch");
+    if (B == 0 || t->n_segments == 0) return 0;
+    TUCH_REQUIRE(verts && out, "tuch_segment_exterior: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc;
+    SegPlan sp;
+    plan_segments(t, B, sc, sp);
+    if (int rc = sc.commit(st)) return rc;
+    return run_segments(t, verts, B, sc, sp, nullptr, nullptr, out, winding_out, st);
+}
+
+TUCH_EXPORT int tuch_region_min(const tuch_topology* t, const float* verts, int B, int masked,
+                                const uint8_t* active, float* min_sq, int32_t* arg_i, int32_t* arg_j,
+                                void* stream) {
+    TUCH_REQUIRE(t != nullptr, "tuch_region_min: null topology");
+    TUCH_REQUIRE(B >= 0, "tuch_region_min: negative batch");
+    if (B == 0 || t->n_pairs == 0) return 0;
+    TUCH_REQUIRE(verts && min_sq, "tuch_region_min: null pointer");
+    TUCH_REQUIRE(!masked || t->has_mask, "tuch_region_min: masked minimum requested but no geodesic mask is set");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc;
+    const size_t h_v4 = sc.plan(sizeof(float4) * (size_t)B * t->Vp);
+    const size_t h_i = sc.plan(arg_i ? 0 : sizeof(int) * (size_t)B * t->n_pairs);
+    const size_t h_j = sc.plan(arg_j ? 0 : sizeof(int) * (size_t)B * t->n_pairs);
+    if (int rc = sc.commit(st)) return rc;
+    float4* v4 = sc.get<float4>(h_v4);
+    if (int rc = launch_pack_mesh(verts, t->d_faces, B, t->V, t->F, t->Fp, t->Vp, nullptr, v4, st)) return rc;
+    return launch_region_min(v4, t->Vp, masked ? t->d_maskT : nullptr, t->Vq, t->d_region_ids, t->d_region_off,
+                             t->d_pair_a, t->d_pair_b, active, t->n_pairs, B, min_sq,
+                             arg_i ? arg_i : sc.get<int>(h_i), arg_j ? arg_j : sc.get<int>(h_j), st);
+}
+
+// ================================================================ host-buffer conveniences
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { TUCH_CUDA(cudaMalloc(&p, n ? n : 1)); return 0; }
+    template <typename T> T* as() { return (T*)p; }
+};
+}  // namespace
+
+TUCH_EXPORT int tuch_winding_numbers_host(const float* points_host, const float* triangles_host, int bs, int Q,
+                                          int F, float* out_host) {
+    TUCH_REQUIRE(bs >= 0 && Q >= 0 && F >= 0, "tuch_winding_numbers_host: negative size");
+    if (bs == 0 || Q == 0) return 0;
+    TUCH_REQUIRE(points_host && out_host && (F == 0 || triangles_host), "tuch_winding_numbers_host: null pointer");
+    DevBuf p, t, o;
+    const size_t np = sizeof(float) * 3 * (size_t)bs * Q, nt = sizeof(float) * 9 * (size_t)bs * F,
+                 no = sizeof(float) * (size_t)bs * Q;
+    if (int rc = p.alloc(np)) return rc;
+    if (int rc = t.alloc(nt)) return rc;
+    if (int rc = o.alloc(no)) return rc;
+    TUCH_CUDA(cudaMemcpyAsync(p.p, points_host, np, cudaMemcpyHostToDevice, 0));
+    if (nt) TUCH_CUDA(cudaMemcpyAsync(t.p, triangles_host, nt, cudaMemcpyHostToDevice, 0));
+    if (int rc = tuch_winding_numbers(p.as<float>(), t.as<float>(), bs, Q, F, o.as<float>(), nullptr)) return rc;
+    TUCH_CUDA(cudaMemcpyAsync(out_host, o.p, no, cudaMemcpyDeviceToHost, 0));
+    TUCH_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}
+
+TUCH_EXPORT int tuch_contact_query_host(const tuch_topology* topo, const float* verts_host, int B, int use_segments,
+                                        int32_t* argmin_host, float* min_sq_host, float* winding_host,
+                                        uint8_t* exterior_host) {
+    TUCH_REQUIRE(topo != nullptr, "tuch_contact_query_host: null topology");
+    TUCH_REQUIRE(B >= 0, "tuch_contact_query_host: negative batch");
+    if (B == 0) return 0;
+    TUCH_REQUIRE(verts_host != nullptr, "tuch_contact_query_host: verts is null");
+    const size_t n = (size_t)B * topo->V;
+    DevBuf v, am, mn, w, e;
+    if (int rc = v.alloc(n * 12)) return rc;
+    if (argmin_host) if (int rc = am.alloc(n * 4)) return rc;
+    if (min_sq_host) if (int rc = mn.alloc(n * 4)) return rc;
+    if (winding_host) if (int rc = w.alloc(n * 4)) return rc;
+    if (exterior_host) if (int rc = e.alloc(n)) return rc;
+    TUCH_CUDA(cudaMemcpyAsync(v.p, verts_host, n * 12, cudaMemcpyHostToDevice, 0));
+    if (int rc = tuch_contact_query(topo, v.as<float>(), B, use_segments, am.as<int32_t>(), mn.as<float>(),
+                                    w.as<float>(), e.as<uint8_t>(), nullptr)) return rc;
+    if (argmin_host) TUCH_CUDA(cudaMemcpyAsync(argmin_host, am.p, n * 4, cudaMemcpyDeviceToHost, 0));
+    if (min_sq_host) TUCH_CUDA(cudaMemcpyAsync(min_sq_host, mn.p, n * 4, cudaMemcpyDeviceToHost, 0));
+    if (winding_host) TUCH_CUDA(cudaMemcpyAsync(winding_host, w.p, n * 4, cudaMemcpyDeviceToHost, 0));
+    if (exterior_host) TUCH_CUDA(cudaMemcpyAsync(exterior_host, e.p, n, cudaMemcpyDeviceToHost, 0));
+    TUCH_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}

@@ -1,0 +1,59 @@
+// Internal: opaque handle layouts and the scratch bump allocator behind include/tuch_b200.h.
+#pragma once
+#include <vector>
+
+#include "../../include/tuch_b200.h"
+#include "kernels.h"
+
+struct tuch_topology {
+    int device = 0;
+    int V = 0, F = 0, Fp = 0, Vp = 0, Vq = 0, W = 0;
+    int* d_faces = nullptr;            // [F][3]
+    uint32_t* d_maskT = nullptr;       // [W][Vq] bit-packed geodesic mask
+    bool has_mask = false;
+    // DSC regions (CSR) and annotated pairs
+    int n_regions = 0, n_pairs = 0;
+    int *d_region_off = nullptr, *d_region_ids = nullptr, *d_pair_a = nullptr, *d_pair_b = nullptr;
+    // closed body segments
+    int n_segments = 0, n_bands = 0, n_sv = 0, n_slots = 0;
+    std::vector<int> h_vidx_off;       // [S+1] member-vertex ranges
+    std::vector<int> h_slot_off;       // [S+1] packed (padded) triangle ranges
+    int *d_seg_vidx = nullptr, *d_seg_faces = nullptr, *d_slot_face = nullptr, *d_slot_band0 = nullptr;
+    int *d_loop_off = nullptr, *d_loop_ids = nullptr;
+};
+
+namespace tuch {
+
+int arena_get(cudaStream_t st, size_t bytes, void** out);
+
+// Two-phase bump allocator over the per-(device, stream) arena: plan() every buffer, commit()
+// once (may grow the arena), then get<T>().
+class Scratch {
+public:
+    size_t plan(size_t bytes) {
+        const size_t off = total_;
+        total_ += align_up(bytes, 256);
+        return off;
+    }
+    int commit(cudaStream_t st);
+    template <typename T> T* get(size_t handle) const { return (T*)(base_ + handle); }
+private:
+    size_t total_ = 0;
+    char* base_ = nullptr;
+};
+
+int launch_segment_apex(const float* verts, int B, int V, const int* loop_off, const int* loop_ids,
+                        int n_bands, float* apex, const uint8_t* body_active, cudaStream_t st);
+int launch_segment_pack(const float* verts, int B, int V, const float* apex, int n_bands, const int* seg_faces,
+                        const int* slot_face, const int* slot_band0, int n_slots, const int* seg_vidx,
+                        int n_sv, float4* tri12, float* points, const uint8_t* body_active, cudaStream_t st);
+int launch_exterior_init(const float* winding, int B, int V, uint8_t* exterior, uint8_t* any_interior,
+                         cudaStream_t st);
+int launch_segment_apply(const float* seg_winding, const int* seg_vidx, int n_sv, int B, int V,
+                         uint8_t* exterior, uint8_t* seg_ext_out, const uint8_t* body_active, cudaStream_t st);
+
+// vert4_out: optional caller-owned [B][Vp] float4 buffer that receives the packed vertices
+int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
+                       float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st);
+
+}  // namespace tuch

@@ -1,0 +1,265 @@
+"""Thin torch-tensor front end of the C ABI (include/tuch_b200.h).
+
+torch is plumbing only: it owns device memory and the current stream; every computation below
+is a hand-written sm_100a kernel inside libtuch_b200.so.  All functions require CUDA tensors and
+raise TuchError otherwise -- there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, TuchError
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TuchError('%s must be a CUDA tensor: tuch_b200 has no CPU fallback' % name)
+    return t
+
+
+def _f32(t, name):
+    t = _dev(t, name).detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _i32_host(a):
+    return np.ascontiguousarray(np.asarray(a), dtype=np.int32)
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_info():
+    sm, mj, mn = C.c_int(), C.c_int(), C.c_int()
+    check(lib().tuch_device_info(C.byref(sm), C.byref(mj), C.byref(mn)), 'tuch_device_info')
+    return dict(sm_count=sm.value, cc=(mj.value, mn.value))
+
+
+def launch_count():
+    return int(lib().tuch_launch_count())
+
+
+# ------------------------------------------------------------------ a1-a3 forward kernels
+def pairwise_dist(x, y, squared=True):
+    x, y = _f32(x, 'x'), _f32(y, 'y')
+    if x.dim() != 3 or y.dim() != 3 or x.shape[2] != 3 or y.shape[2] != 3 or x.shape[0] != y.shape[0]:
+        raise TuchError('pairwise_dist expects x[bs,Nx,3], y[bs,Ny,3]; got %s, %s' % (tuple(x.shape), tuple(y.shape)))
+    bs, nx, ny = x.shape[0], x.shape[1], y.shape[1]
+    P = torch.empty(bs, nx, ny, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib().tuch_pairwise_dist(_ptr(x), _ptr(y), bs, nx, ny, int(bool(squared)), _ptr(P), _stream()),
+              'tuch_pairwise_dist')
+    return P
+
+
+def pairwise_dist_backward(x, y, P, gP, squared=True):
+    x, y, P, gP = _f32(x, 'x'), _f32(y, 'y'), _f32(P, 'P'), _f32(gP, 'gP')
+    bs, nx, ny = x.shape[0], x.shape[1], y.shape[1]
+    gx, gy = torch.empty_like(x), torch.empty_like(y)
+    with torch.cuda.device(x.device):
+        check(lib().tuch_pairwise_dist_backward(_ptr(x), _ptr(y), _ptr(P), _ptr(gP), bs, nx, ny,
+                                                int(bool(squared)), _ptr(gx), _ptr(gy), _stream()),
+              'tuch_pairwise_dist_backward')
+    return gx, gy
+
+
+def solid_angles(points, triangles):
+    p, t = _f32(points, 'points'), _f32(triangles, 'triangles')
+    if p.dim() != 3 or t.dim() != 4 or p.shape[2] != 3 or tuple(t.shape[2:]) != (3, 3) or p.shape[0] != t.shape[0]:
+        raise TuchError('solid_angles expects points[B,Q,3], triangles[B,F,3,3]; got %s, %s'
+                        % (tuple(p.shape), tuple(t.shape)))
+    B, Q, F = p.shape[0], p.shape[1], t.shape[1]
+    out = torch.empty(B, Q, F, device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        check(lib().tuch_solid_angles(_ptr(p), _ptr(t), B, Q, F, _ptr(out), _stream()), 'tuch_solid_angles')
+    return out
+
+
+def winding_numbers(points, triangles):
+    p, t = _f32(points, 'points'), _f32(triangles, 'triangles')
+    if p.dim() != 3 or t.dim() != 4 or p.shape[2] != 3 or tuple(t.shape[2:]) != (3, 3) or p.shape[0] != t.shape[0]:
+        raise TuchError('winding_numbers expects points[B,Q,3], triangles[B,F,3,3]; got %s, %s'
+                        % (tuple(p.shape), tuple(t.shape)))
+    B, Q, F = p.shape[0], p.shape[1], t.shape[1]
+    out = torch.empty(B, Q, device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        check(lib().tuch_winding_numbers(_ptr(p), _ptr(t), B, Q, F, _ptr(out), _stream()), 'tuch_winding_numbers')
+    return out
+
+
+# ------------------------------------------------------------------ topology handle
+class Topology:
+    """Device-resident constants of one mesh topology (faces, geodesic mask, DSC regions, body
+    segments) -- the arguments the reference threads through every call as face_tensor / geomask /
+    cdict / segments (smplifydc.py:58-66, losses.py:34-51)."""
+
+    def __init__(self, faces, num_verts, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise TuchError('Topology needs a CUDA device: tuch_b200 has no CPU fallback')
+        f = faces.detach().cpu().numpy() if isinstance(faces, torch.Tensor) else np.asarray(faces)
+        f = _i32_host(f.reshape(-1, 3))
+        self.V, self.F = int(num_verts), int(len(f))
+        self.faces_np = f
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_create(self.V, self.F, _hp(f), C.byref(self._h)), 'tuch_topology_create')
+        self.has_mask = False
+        self.region_names = []
+        self.classes = []
+        self.segment_names = []
+        self.segment_vidx = []
+        self.n_seg_verts = 0
+
+    def __del__(self):
+        try:
+            h = getattr(self, '_h', None)
+            if h is not None and h.value:
+                lib().tuch_topology_destroy(h)
+                self._h = None
+        except Exception:       # interpreter shutdown: modules may already be torn down
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # geomask = geodist > geothres (smplifydc.py:65)
+    def set_geodist(self, geodist, geothres):
+        g = _f32(geodist.to(self.device) if isinstance(geodist, torch.Tensor) else
+                 torch.as_tensor(np.asarray(geodist), device=self.device), 'geodist')
+        if tuple(g.shape) != (self.V, self.V):
+            raise TuchError('geodist must be [%d,%d], got %s' % (self.V, self.V, tuple(g.shape)))
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_set_geodist(self._h, _ptr(g), float(geothres), _stream()),
+                  'tuch_topology_set_geodist')
+            torch.cuda.current_stream().synchronize()
+        self.has_mask = True
+
+    def set_geomask(self, geomask):
+        m = geomask if isinstance(geomask, torch.Tensor) else torch.as_tensor(np.asarray(geomask))
+        m = _dev(m.to(self.device), 'geomask').to(torch.uint8).contiguous()
+        if tuple(m.shape) != (self.V, self.V):
+            raise TuchError('geomask must be [%d,%d], got %s' % (self.V, self.V, tuple(m.shape)))
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_set_geomask(self._h, _ptr(m), _stream()), 'tuch_topology_set_geomask')
+            torch.cuda.current_stream().synchronize()
+        self.has_mask = True
+
+    def set_regions(self, cdict):
+        """cdict = {'classes': sequence of (regionA, regionB), 'csig': {region: vertex ids}}
+        (losses.py:110-113, train_module.py:65-67)."""
+        names = []
+        for ra, rb in cdict['classes']:
+            for r in (ra, rb):
+                if r not in names:
+                    names.append(r)
+        off, ids = [0], []
+        for n in names:
+            v = [int(i) for i in cdict['csig'][n]]
+            ids += v
+            off.append(len(ids))
+        idx = {n: i for i, n in enumerate(names)}
+        pa = _i32_host([idx[a] for a, _ in cdict['classes']])
+        pb = _i32_host([idx[b] for _, b in cdict['classes']])
+        off, ids = _i32_host(off), _i32_host(ids)
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_set_regions(self._h, len(names), _hp(off), _hp(ids), len(pa), _hp(pa), _hp(pb)),
+                  'tuch_topology_set_regions')
+        self.region_names = names
+        self.classes = [tuple(c) for c in cdict['classes']]
+
+    def set_segments(self, segments):
+        """segments: iterable of (name, vidx, closed_faces[n,3], band loops) in BatchBodySegment order
+        (segmentation.py:113-115); closed_faces index V + k for the k-th band centroid."""
+        v_off, v_ids, f_off, f_ids, b_off, l_off, l_ids = [0], [], [0], [], [0], [0], []
+        names, vidx_list = [], []
+        for name, vidx, cfaces, loops in segments:
+            names.append(name)
+            vidx = [int(i) for i in vidx]
+            vidx_list.append(np.asarray(vidx, dtype=np.int64))
+            v_ids += vidx
+            v_off.append(len(v_ids))
+            cf = np.asarray(cfaces, dtype=np.int64).reshape(-1, 3)
+            f_ids += [int(i) for i in cf.reshape(-1)]
+            f_off.append(len(f_ids) // 3)
+            for lp in loops:
+                l_ids += [int(i) for i in lp]
+                l_off.append(len(l_ids))
+            b_off.append(len(l_off) - 1)
+        arrs = [_i32_host(a) for a in (v_off, v_ids, f_off, f_ids, b_off, l_off, l_ids)]
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_set_segments(self._h, len(names), *[_hp(a) for a in arrs]),
+                  'tuch_topology_set_segments')
+        self.segment_names = names
+        self.segment_vidx = vidx_list
+        self.n_seg_verts = int(v_off[-1])
+
+    # ------------------------------------------------------------------ queries
+    def _verts(self, verts):
+        v = _f32(verts, 'verts')
+        if v.dim() != 3 or v.shape[1] != self.V or v.shape[2] != 3:
+            raise TuchError('verts must be [B,%d,3], got %s' % (self.V, tuple(v.shape)))
+        if v.device != self.device:
+            raise TuchError('verts live on %s but the topology on %s' % (v.device, self.device))
+        return v
+
+    def contact_query(self, verts, use_segments=True, want_nearest=True, want_winding=True):
+        """Fused losses.py:76-93 for the whole batch -> dict(argmin int32[B,V], min_sq[B,V],
+        winding[B,V], exterior bool[B,V])."""
+        v = self._verts(verts)
+        B = v.shape[0]
+        out = {}
+        am = mn = w = ext = None
+        if want_nearest:
+            am = torch.empty(B, self.V, device=v.device, dtype=torch.int32)
+            mn = torch.empty(B, self.V, device=v.device, dtype=torch.float32)
+        if want_winding:
+            w = torch.empty(B, self.V, device=v.device, dtype=torch.float32)
+            ext = torch.empty(B, self.V, device=v.device, dtype=torch.uint8)
+        with torch.cuda.device(v.device):
+            check(lib().tuch_contact_query(self._h, _ptr(v), B, int(bool(use_segments)), _ptr(am), _ptr(mn),
+                                           _ptr(w), _ptr(ext), _stream()), 'tuch_contact_query')
+        out.update(argmin=am, min_sq=mn, winding=w, exterior=None if ext is None else ext.bool())
+        return out
+
+    def segment_exterior(self, verts):
+        """BatchBodySegment.batch_has_self_isec for a batch: list (segment order) of bool [B, n_s]."""
+        v = self._verts(verts)
+        B = v.shape[0]
+        flags = torch.empty(B, self.n_seg_verts, device=v.device, dtype=torch.uint8)
+        wind = torch.empty(B, self.n_seg_verts, device=v.device, dtype=torch.float32)
+        with torch.cuda.device(v.device):
+            check(lib().tuch_segment_exterior(self._h, _ptr(v), B, _ptr(flags), _ptr(wind), _stream()),
+                  'tuch_segment_exterior')
+        sizes = [len(x) for x in self.segment_vidx]
+        return [f.bool() for f in torch.split(flags, sizes, dim=1)], list(torch.split(wind, sizes, dim=1))
+
+    def region_min(self, verts, masked=True, active=None):
+        """-> (min_sq[B,n_pairs], arg_i, arg_j) over the annotated region pairs."""
+        v = self._verts(verts)
+        B, P = v.shape[0], len(self.classes)
+        mn = torch.zeros(B, P, device=v.device, dtype=torch.float32)
+        ai = torch.full((B, P), -1, device=v.device, dtype=torch.int32)
+        aj = torch.full((B, P), -1, device=v.device, dtype=torch.int32)
+        act = None
+        if active is not None:
+            act = _dev(active, 'active').to(torch.uint8).contiguous()
+            if tuple(act.shape) != (B, P):
+                raise TuchError('active must be [%d,%d], got %s' % (B, P, tuple(act.shape)))
+        with torch.cuda.device(v.device):
+            check(lib().tuch_region_min(self._h, _ptr(v), B, int(bool(masked)), _ptr(act), _ptr(mn), _ptr(ai),
+                                        _ptr(aj), _stream()), 'tuch_region_min')
+        return mn, ai, aj
