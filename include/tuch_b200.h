@@ -120,6 +120,40 @@ int tuch_topology_total_segment_verts(const tuch_topology* topo);
 int tuch_region_min(const tuch_topology* topo, const float* verts, int B, int masked,
                     const uint8_t* active, float* min_sq, int32_t* arg_i, int32_t* arg_j, void* stream);
 
+/* ------------------------------------------------------------------ a11  SMPL body model
+ * tuch/models/smpl.py:34-56 over smplx==0.1.13 `SMPL.forward` / `lbs.lbs` (third-party, not in
+ * the reference tree): shape blend, joint regression, Rodrigues, pose blend, 24-joint kinematic
+ * chain, skinning, 21 vertex-picked joints, n_extra_reg regressed joints, remap to n_out joints.
+ * All model arrays are HOST pointers, copied at creation:
+ *   v_template[V,3] shapedirs[V,3,L] posedirs[207,3V] J_regressor[24,V] lbs_weights[V,24]
+ *   parents[24] extra_vertex_ids[n_extra_verts] J_regressor_extra[n_extra_reg,V] joint_map[n_out]
+ * (joint_map indexes the concatenation [24 posed | picked vertices | regressed extras]). */
+typedef struct tuch_smpl tuch_smpl;
+
+int tuch_smpl_create(int V, int num_betas, const float* v_template_host, const float* shapedirs_host,
+                     const float* posedirs_host, const float* J_regressor_host,
+                     const float* lbs_weights_host, const int32_t* parents_host, int n_extra_verts,
+                     const int32_t* extra_vertex_ids_host, int n_extra_reg,
+                     const float* J_regressor_extra_host, int n_out, const int32_t* joint_map_host,
+                     tuch_smpl** out);
+void tuch_smpl_destroy(tuch_smpl* smpl);
+int tuch_smpl_num_verts(const tuch_smpl* smpl);
+int tuch_smpl_num_joints(const tuch_smpl* smpl);
+/* floats of caller-owned device workspace a forward/backward pair at batch B needs; forward fills
+ * it with the intermediates backward reads (rotations, chain transforms, posed template). */
+size_t tuch_smpl_workspace_floats(const tuch_smpl* smpl, int B);
+
+/* betas[B,L]; pose = axis-angle [B,72] (pose_is_rotmat == 0; smplx batch_rodrigues form) or
+ * rotation matrices [B,24,3,3] (pose_is_rotmat != 0, the `pose2rot=False` call of train_module.py:202).
+ * -> vertices[B,V,3], joints[B,n_out,3] (joints may be NULL). */
+int tuch_smpl_forward(const tuch_smpl* smpl, const float* betas, const float* pose, int pose_is_rotmat,
+                      int B, float* workspace, float* vertices, float* joints, void* stream);
+/* vector-Jacobian product of tuch_smpl_forward: g_vertices[B,V,3] and/or g_joints[B,n_out,3]
+ * (either may be NULL) -> g_pose ([B,72] or [B,24,3,3]) and g_betas[B,L] (either may be NULL). */
+int tuch_smpl_backward(const tuch_smpl* smpl, const float* pose, int pose_is_rotmat, int B,
+                       float* workspace, const float* g_vertices, const float* g_joints,
+                       float* g_pose, float* g_betas, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer conveniences
  * Same as the calls above with HOST buffers; copies in/out on an internal stream and
  * synchronises.  Used by non-torch callers and by the end-to-end benchmark leg. */

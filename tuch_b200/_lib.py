@@ -39,6 +39,15 @@ def _declare(lib):
     lib.tuch_contact_query.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.tuch_segment_exterior.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.tuch_region_min.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.tuch_smpl_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, vp, C.POINTER(vp)]
+    lib.tuch_smpl_destroy.argtypes = [vp]
+    lib.tuch_smpl_destroy.restype = None
+    lib.tuch_smpl_num_verts.argtypes = [vp]
+    lib.tuch_smpl_num_joints.argtypes = [vp]
+    lib.tuch_smpl_workspace_floats.argtypes = [vp, i32]
+    lib.tuch_smpl_workspace_floats.restype = C.c_size_t
+    lib.tuch_smpl_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.tuch_smpl_backward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.tuch_winding_numbers_host.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.tuch_contact_query_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libtuch_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '--use_fast_math', '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden']
+              '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden']
 
 
 def sources():

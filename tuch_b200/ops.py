@@ -263,3 +263,76 @@ class Topology:
             check(lib().tuch_region_min(self._h, _ptr(v), B, int(bool(masked)), _ptr(act), _ptr(mn), _ptr(ai),
                                         _ptr(aj), _stream()), 'tuch_region_min')
         return mn, ai, aj
+
+
+# ------------------------------------------------------------------ SMPL body model handle
+class SmplHandle:
+    """Device-resident SMPL model (tuch_smpl): constants uploaded once, forward / backward kernels."""
+
+    def __init__(self, arrays, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise TuchError('SmplHandle needs a CUDA device: tuch_b200 has no CPU fallback')
+        f32 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+        vt = f32(arrays['v_template'])
+        self.V = int(vt.shape[0])
+        sd = f32(arrays['shapedirs'])
+        self.L = int(sd.shape[-1])
+        pd = f32(arrays['posedirs']).reshape(207, self.V * 3)
+        jr = f32(arrays['J_regressor'])
+        lw = f32(arrays['lbs_weights'])
+        par = _i32_host(arrays['parents'])
+        xv = _i32_host(arrays['extra_vertex_ids'])
+        xr = f32(arrays['J_regressor_extra']).reshape(-1, self.V)
+        jm = _i32_host(arrays['joint_map'])
+        self.NO = int(len(jm))
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().tuch_smpl_create(self.V, self.L, _hp(vt), _hp(sd), _hp(pd), _hp(jr), _hp(lw), _hp(par),
+                                         len(xv), _hp(xv), xr.shape[0], _hp(xr), len(jm), _hp(jm),
+                                         C.byref(self._h)), 'tuch_smpl_create')
+
+    def __del__(self):
+        try:
+            h = getattr(self, '_h', None)
+            if h is not None and h.value:
+                lib().tuch_smpl_destroy(h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace(self, B):
+        n = int(lib().tuch_smpl_workspace_floats(self._h, int(B)))
+        return torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+
+    def forward(self, betas, pose, is_rotmat, workspace=None):
+        """betas[B,L], pose [B,72] | [B,24,3,3] -> (vertices[B,V,3], joints[B,NO,3], workspace)."""
+        betas, pose = _f32(betas, 'betas'), _f32(pose, 'pose')
+        B = betas.shape[0]
+        if betas.shape[1] != self.L:
+            raise TuchError('betas must be [B,%d], got %s' % (self.L, tuple(betas.shape)))
+        if pose.numel() != B * (216 if is_rotmat else 72):
+            raise TuchError('pose has %d elements for batch %d (is_rotmat=%s)' % (pose.numel(), B, is_rotmat))
+        ws = workspace if workspace is not None else self.workspace(B)
+        verts = torch.empty(B, self.V, 3, device=betas.device, dtype=torch.float32)
+        joints = torch.empty(B, self.NO, 3, device=betas.device, dtype=torch.float32)
+        with torch.cuda.device(betas.device):
+            check(lib().tuch_smpl_forward(self._h, _ptr(betas), _ptr(pose), int(bool(is_rotmat)), B, _ptr(ws),
+                                          _ptr(verts), _ptr(joints), _stream()), 'tuch_smpl_forward')
+        return verts, joints, ws
+
+    def backward(self, pose, is_rotmat, workspace, g_verts, g_joints, need_pose=True, need_betas=True):
+        pose = _f32(pose, 'pose')
+        B = pose.shape[0]
+        gv = _f32(g_verts, 'g_verts') if g_verts is not None else None
+        gj = _f32(g_joints, 'g_joints') if g_joints is not None else None
+        g_pose = torch.empty(B, 216 if is_rotmat else 72, device=pose.device, dtype=torch.float32) if need_pose else None
+        g_betas = torch.empty(B, self.L, device=pose.device, dtype=torch.float32) if need_betas else None
+        with torch.cuda.device(pose.device):
+            check(lib().tuch_smpl_backward(self._h, _ptr(pose), int(bool(is_rotmat)), B, _ptr(workspace), _ptr(gv),
+                                           _ptr(gj), _ptr(g_pose), _ptr(g_betas), _stream()), 'tuch_smpl_backward')
+        return g_pose, g_betas
