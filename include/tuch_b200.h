@@ -36,6 +36,13 @@ int tuch_abi_version(void);
 int tuch_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
 long long tuch_launch_count(void);
+/* Optional per-kernel device timing for benchmarks: while enabled, the dominant kernels
+ * ("winding_kernel", "winding_kernel_segments", "nearest_kernel") are bracketed by CUDA events on
+ * their launch stream.  tuch_kernel_timing_read synchronises on the recorded events and returns the
+ * accumulated device time and launch count since the last reset. */
+int tuch_kernel_timing_enable(int on);
+int tuch_kernel_timing_reset(void);
+int tuch_kernel_timing_read(const char* name, double* total_ms, long long* launches);
 /* releases every scratch arena of the current device (synchronises the device) */
 int tuch_release_scratch(void);
 
@@ -153,6 +160,70 @@ int tuch_smpl_forward(const tuch_smpl* smpl, const float* betas, const float* po
 int tuch_smpl_backward(const tuch_smpl* smpl, const float* pose, int pose_is_rotmat, int B,
                        float* workspace, const float* g_vertices, const float* g_joints,
                        float* g_pose, float* g_betas, void* stream);
+
+/* ------------------------------------------------------------------ a7/a8  reprojection + GMoF
+ * tuch/utils/geometry.py:83-111 (perspective_projection, identity rotation as at losses.py:56-59)
+ * + tuch/smplify/losses.py:25-32,60-61: loss[b,j] = conf^2 * sum_xy gmof(f (p/p_z)_xy + c_xy - target_xy),
+ * p = joints[b,j] + cam_t[b].  Forward value and analytic gradient in one launch:
+ *   g_joints[B,J,3], g_cam_t[B,3] = d(sum_bj g_loss[b,j] loss[b,j])/d(.)   (g_loss NULL = ones).
+ * cam_t_est != NULL adds camera_fitting_loss's depth term (losses.py:146):
+ *   depth_loss[b] = depth_loss_weight^2 (cam_t_z - cam_t_est_z)^2, its gradient goes into g_cam_t.
+ * Any output may be NULL. */
+int tuch_reprojection_loss(const float* joints, const float* cam_t, const float* center,
+                           const float* joints_2d, const float* conf, int B, int J, float focal_length,
+                           float sigma, const float* cam_t_est, float depth_loss_weight, const float* g_loss,
+                           float* loss, float* depth_loss, float* g_joints, float* g_cam_t, void* stream);
+
+/* ------------------------------------------------------------------ a9  MaxMixturePrior
+ * tuch/smplify/prior.py:36-132 (use_merged=True): HOST arrays means[M,D], precisions[M,D,D],
+ * nll_weights[M] (prior.py:80-96), copied. */
+typedef struct tuch_prior tuch_prior;
+int tuch_prior_create(int M, int D, const float* means_host, const float* precisions_host,
+                      const float* nll_weights_host, tuch_prior** out);
+void tuch_prior_destroy(tuch_prior* prior);
+
+/* value[b] = ppw^2 * min_m[0.5 (th-mu_m)^T P_m (th-mu_m) - log nll_w_m]      prior.py:117-132
+ *          + apw^2 * sum exp(+-th[52,55,9,12])^2                              losses.py:155-162
+ *          + spw^2 * |betas[b]|^2                                             losses.py:149,192
+ * pose[B,D] (body pose, D = 69), betas[B,L] (may be NULL when spw == 0).  Outputs (each may be NULL):
+ * value[B], prior_value[B] (unweighted mixture term), component[B] (arg min), g_pose[B,D], g_betas[B,L]. */
+int tuch_pose_terms(const tuch_prior* prior, const float* pose, const float* betas, int B, int D, int L,
+                    float pose_prior_weight, float angle_prior_weight, float shape_prior_weight,
+                    float* value, float* prior_value, int32_t* component, float* g_pose, float* g_betas,
+                    void* stream);
+
+/* ------------------------------------------------------------------ push / pull contact terms
+ * d_i = |p_i - p_argmin[i]|; interior points (exterior == 0) pay tanh(d/0.04)^2, exterior points pay
+ * 0.005 tanh(d/0.005)^2 -- only where d < euclthres (TUCH_PULL_THRESHOLD, losses.py:96-105) or
+ * everywhere (TUCH_PULL_ALL, loss.py:306-312).  TUCH_REDUCE_SUM adds the terms (losses.py:105,
+ * loss.py:315), TUCH_REDUCE_MEAN averages push and pull separately (eft/loss.py:158-166).
+ * points[B,N,3], argmin int32 [B,N], exterior uint8 [B,N]; body_active uint8 [B] (NULL = all;
+ * inactive bodies get loss 0 and no gradient: ignore_idxs / valid_fit), counts int32 [B] (NULL = N;
+ * valid points per body for the data-dependent HD selection).  loss[B]; parts[B,4] = (sum push, sum
+ * pull, #push, #pull); g_points[B,N,3] is ACCUMULATED into: += weight * g_loss[b] * d loss[b]/d points. */
+#define TUCH_PULL_THRESHOLD 0
+#define TUCH_PULL_ALL 1
+#define TUCH_REDUCE_SUM 0
+#define TUCH_REDUCE_MEAN 1
+int tuch_contact_loss(const float* points, const int32_t* argmin, const uint8_t* exterior,
+                      const uint8_t* body_active, const int32_t* counts, int B, int N, float euclthres,
+                      int pull_mode, int reduce_mode, float weight, const float* g_loss, float* loss,
+                      float* parts, float* g_points, void* stream);
+
+/* region-to-region term (losses.py:108-117): r2r[b] = sum over the pairs tuch_region_min reported
+ * (arg_i >= 0) of min_sq[b,p]; g_verts[B,V,3] += weight * g_loss[b] * d r2r[b]/d verts through the
+ * attaining entry of the expansion-form distance matrix (contact.py:42).  +inf minima (fully masked
+ * pair) propagate to r2r but carry no gradient, as in the reference. */
+int tuch_region_sum(const float* verts, int B, int V, int n_pairs, const float* min_sq, const int32_t* arg_i,
+                    const int32_t* arg_j, const uint8_t* body_active, float weight, const float* g_loss,
+                    float* r2r, float* g_verts, void* stream);
+
+/* ------------------------------------------------------------------ a13  torch.optim.Adam
+ * One step of Adam (no weight decay, no amsgrad) as configured at smplifydc.py:117,150,197.
+ * step_dev is a DEVICE int32 holding the number of steps taken so far; the call uses step+1 for the
+ * bias corrections and then increments it (so a captured CUDA graph can be replayed). */
+int tuch_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                   int32_t* step_dev, double lr, double beta1, double beta2, double eps, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer conveniences
  * Same as the calls above with HOST buffers; copies in/out on an internal stream and

@@ -22,6 +22,9 @@ def _declare(lib):
     lib.tuch_launch_count.restype = C.c_longlong
     lib.tuch_device_info.argtypes = [C.POINTER(i32)] * 3
     lib.tuch_release_scratch.argtypes = []
+    lib.tuch_kernel_timing_enable.argtypes = [i32]
+    lib.tuch_kernel_timing_reset.argtypes = []
+    lib.tuch_kernel_timing_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib.tuch_pairwise_dist.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.tuch_pairwise_dist_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.tuch_solid_angles.argtypes = [vp, vp, i32, i32, i32, vp, vp]
@@ -48,6 +51,14 @@ def _declare(lib):
     lib.tuch_smpl_workspace_floats.restype = C.c_size_t
     lib.tuch_smpl_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.tuch_smpl_backward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.tuch_reprojection_loss.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, vp, f32, vp, vp, vp, vp, vp, vp]
+    lib.tuch_prior_create.argtypes = [i32, i32, vp, vp, vp, C.POINTER(vp)]
+    lib.tuch_prior_destroy.argtypes = [vp]
+    lib.tuch_prior_destroy.restype = None
+    lib.tuch_pose_terms.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp]
+    lib.tuch_contact_loss.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, vp, vp, vp]
+    lib.tuch_region_sum.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp]
+    lib.tuch_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
     lib.tuch_winding_numbers_host.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.tuch_contact_query_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
 

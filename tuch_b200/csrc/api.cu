@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 
 namespace tuch {
 
@@ -36,6 +37,33 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// ---------------------------------------------------------------- per-kernel timing
+struct TimedPair { cudaEvent_t a, b; };
+struct TimedKernel { std::string name; std::vector<TimedPair> pending; double total_ms = 0.0; long long count = 0; };
+static std::mutex g_timing_mu;
+static bool g_timing_on = false;
+static std::vector<TimedKernel> g_timed;
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t st) : st_(st) {
+    if (!g_timing_on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    int k = -1;
+    for (size_t i = 0; i < g_timed.size(); ++i) if (g_timed[i].name == name) { k = (int)i; break; }
+    if (k < 0) { g_timed.push_back(TimedKernel{name}); k = (int)g_timed.size() - 1; }
+    TimedPair p{};
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+    cudaEventRecord(p.a, st);
+    g_timed[k].pending.push_back(p);
+    slot_ = k;
+}
+KernelTimer::~KernelTimer() {
+    if (slot_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    cudaEventRecord(g_timed[slot_].pending.back().b, st_);
 }
 
 // ---------------------------------------------------------------- scratch arenas
@@ -108,6 +136,42 @@ TUCH_EXPORT int tuch_release_scratch(void) {
         } else {
             ++it;
         }
+    }
+    return 0;
+}
+
+TUCH_EXPORT int tuch_kernel_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing_on = on != 0;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_kernel_timing_reset(void) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (auto& k : g_timed) {
+        for (auto& p : k.pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        k.pending.clear(); k.total_ms = 0.0; k.count = 0;
+    }
+    return 0;
+}
+
+TUCH_EXPORT int tuch_kernel_timing_read(const char* name, double* total_ms, long long* launches) {
+    TUCH_REQUIRE(name != nullptr, "tuch_kernel_timing_read: name is null");
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (total_ms) *total_ms = 0.0;
+    if (launches) *launches = 0;
+    for (auto& k : g_timed) {
+        if (k.name != name) continue;
+        for (auto& p : k.pending) {
+            TUCH_CUDA(cudaEventSynchronize(p.b));
+            float ms = 0.f;
+            TUCH_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+            k.total_ms += ms; k.count += 1;
+            cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+        }
+        k.pending.clear();
+        if (total_ms) *total_ms = k.total_ms;
+        if (launches) *launches = k.count;
     }
     return 0;
 }

@@ -421,8 +421,11 @@ int launch_winding(const WindingJob& j, cudaStream_t st) {
     const int n_tiles = j.Fp / WN_TILE_F;
     const int per = cdiv(n_tiles, j.S);
     dim3 grid(cdiv(j.Q, WN_THREADS * WN_QPT), j.S, j.B);
-    winding_kernel<<<grid, WN_THREADS, 0, st>>>(j.tri12, j.points, j.partial, j.Q, j.Fp, per, j.tri_stride,
-                                                j.point_stride, (long long)j.S * j.Q, j.body_active);
+    {
+        KernelTimer timer(j.body_active == nullptr && j.Q >= 1024 ? "winding_kernel" : "winding_kernel_segments", st);
+        winding_kernel<<<grid, WN_THREADS, 0, st>>>(j.tri12, j.points, j.partial, j.Q, j.Fp, per, j.tri_stride,
+                                                    j.point_stride, (long long)j.S * j.Q, j.body_active);
+    }
     TUCH_LAUNCH_CHECK(); count_launch();
     dim3 g2(cdiv(j.Q, 256), j.B);
     winding_finalize_kernel<<<g2, 256, 0, st>>>(j.partial, j.Q, j.S, (long long)j.S * j.Q, j.out_stride,
@@ -434,6 +437,7 @@ int launch_winding(const WindingJob& j, cudaStream_t st) {
 int launch_nearest(const float4* vert4, const uint32_t* maskT, int B, int V, int Vp, int Vq,
                    int* argmin, float* minval, cudaStream_t st) {
     dim3 grid(cdiv(V, NN_THREADS), B);
+    KernelTimer timer("nearest_kernel", st);
     nearest_kernel<<<grid, NN_THREADS, 0, st>>>(vert4, maskT, V, Vp, Vq, argmin, minval);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;

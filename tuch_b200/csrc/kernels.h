@@ -49,4 +49,16 @@ int launch_region_min(const float4* vert4, int Vp, const uint32_t* maskT, int Vq
 int sm_count();
 void count_launch();
 
+// Optional per-kernel device timing (tuch_kernel_timing_*): when enabled, a KernelTimer brackets a
+// launch with two CUDA events on the launch stream; the pairs are resolved when the totals are read.
+// Nothing is recorded while the stream is being captured into a CUDA graph.
+class KernelTimer {
+public:
+    KernelTimer(const char* name, cudaStream_t st);
+    ~KernelTimer();
+private:
+    int slot_ = -1;
+    cudaStream_t st_;
+};
+
 }  // namespace tuch

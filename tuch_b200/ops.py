@@ -51,6 +51,21 @@ def launch_count():
     return int(lib().tuch_launch_count())
 
 
+def kernel_timing(enable=None, reset=False):
+    """Per-kernel CUDA-event timing inside the library (bench.py's roofline leg)."""
+    if reset:
+        check(lib().tuch_kernel_timing_reset(), 'tuch_kernel_timing_reset')
+    if enable is not None:
+        check(lib().tuch_kernel_timing_enable(int(bool(enable))), 'tuch_kernel_timing_enable')
+
+
+def kernel_time(name):
+    """-> (total device ms, launches) of a timed kernel since the last reset."""
+    ms, n = C.c_double(), C.c_longlong()
+    check(lib().tuch_kernel_timing_read(name.encode(), C.byref(ms), C.byref(n)), 'tuch_kernel_timing_read')
+    return ms.value, n.value
+
+
 # ------------------------------------------------------------------ a1-a3 forward kernels
 def pairwise_dist(x, y, squared=True):
     x, y = _f32(x, 'x'), _f32(y, 'y')
@@ -336,3 +351,142 @@ class SmplHandle:
             check(lib().tuch_smpl_backward(self._h, _ptr(pose), int(bool(is_rotmat)), B, _ptr(workspace), _ptr(gv),
                                            _ptr(gj), _ptr(g_pose), _ptr(g_betas), _stream()), 'tuch_smpl_backward')
         return g_pose, g_betas
+
+
+# ------------------------------------------------------------------ SMPLify-DC objective terms
+PULL_THRESHOLD, PULL_ALL = 0, 1
+REDUCE_SUM, REDUCE_MEAN = 0, 1
+
+
+def reprojection_loss(joints, cam_t, center, joints_2d, conf, focal_length, sigma=100.0, cam_t_est=None,
+                      depth_loss_weight=0.0, g_loss=None, want_grad=True):
+    """losses.py:56-61 (+ the depth term of :146 when cam_t_est is given) -> dict(loss[B,J],
+    depth[B] | None, g_joints[B,J,3] | None, g_cam_t[B,3] | None)."""
+    joints, cam_t, center = _f32(joints, 'joints'), _f32(cam_t, 'cam_t'), _f32(center, 'center')
+    joints_2d, conf = _f32(joints_2d, 'joints_2d'), _f32(conf, 'conf')
+    B, J = joints.shape[0], joints.shape[1]
+    if (tuple(joints.shape) != (B, J, 3) or tuple(cam_t.shape) != (B, 3) or tuple(center.shape) != (B, 2)
+            or tuple(joints_2d.shape) != (B, J, 2) or tuple(conf.shape) != (B, J)):
+        raise TuchError('reprojection_loss: inconsistent shapes %s %s %s %s %s' % (
+            tuple(joints.shape), tuple(cam_t.shape), tuple(center.shape), tuple(joints_2d.shape), tuple(conf.shape)))
+    est = _f32(cam_t_est, 'cam_t_est') if cam_t_est is not None else None
+    gl = _f32(g_loss, 'g_loss') if g_loss is not None else None
+    loss = torch.empty(B, J, device=joints.device, dtype=torch.float32)
+    depth = torch.empty(B, device=joints.device, dtype=torch.float32) if est is not None else None
+    gj = torch.empty(B, J, 3, device=joints.device, dtype=torch.float32) if want_grad else None
+    gc = torch.empty(B, 3, device=joints.device, dtype=torch.float32) if want_grad else None
+    with torch.cuda.device(joints.device):
+        check(lib().tuch_reprojection_loss(_ptr(joints), _ptr(cam_t), _ptr(center), _ptr(joints_2d), _ptr(conf), B, J,
+                                           float(focal_length), float(sigma), _ptr(est), float(depth_loss_weight),
+                                           _ptr(gl), _ptr(loss), _ptr(depth), _ptr(gj), _ptr(gc), _stream()),
+              'tuch_reprojection_loss')
+    return dict(loss=loss, depth=depth, g_joints=gj, g_cam_t=gc)
+
+
+class PriorHandle:
+    """Device-resident max-mixture pose prior (prior.py:80-96 buffers)."""
+
+    def __init__(self, means, precisions, nll_weights, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise TuchError('PriorHandle needs a CUDA device: tuch_b200 has no CPU fallback')
+        f32 = lambda a: np.ascontiguousarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a),
+                                             dtype=np.float32)
+        mu, pr, w = f32(means), f32(precisions), f32(nll_weights).reshape(-1)
+        self.M, self.D = int(mu.shape[0]), int(mu.shape[1])
+        if tuple(pr.shape) != (self.M, self.D, self.D) or len(w) != self.M:
+            raise TuchError('prior arrays have inconsistent shapes %s %s %s' % (mu.shape, pr.shape, w.shape))
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().tuch_prior_create(self.M, self.D, _hp(mu), _hp(pr), _hp(w), C.byref(self._h)), 'tuch_prior_create')
+
+    def __del__(self):
+        try:
+            h = getattr(self, '_h', None)
+            if h is not None and h.value:
+                lib().tuch_prior_destroy(h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+def pose_terms(prior, pose, betas=None, pose_prior_weight=1.0, angle_prior_weight=0.0, shape_prior_weight=0.0,
+               want_grad=True):
+    """prior.py:117-132 + losses.py:155-162 + the shape regulariser -> dict(value[B], prior[B],
+    component[B], g_pose[B,D] | None, g_betas[B,L] | None).  Weights are the UNSQUARED ones."""
+    pose = _f32(pose, 'pose')
+    B, D = pose.shape
+    be = _f32(betas, 'betas') if betas is not None else None
+    L = be.shape[1] if be is not None else 0
+    value = torch.empty(B, device=pose.device, dtype=torch.float32)
+    pv = torch.empty(B, device=pose.device, dtype=torch.float32)
+    comp = torch.empty(B, device=pose.device, dtype=torch.int32)
+    gp = torch.empty(B, D, device=pose.device, dtype=torch.float32) if want_grad else None
+    gb = torch.empty(B, L, device=pose.device, dtype=torch.float32) if (want_grad and be is not None) else None
+    with torch.cuda.device(pose.device):
+        check(lib().tuch_pose_terms(prior.handle if prior is not None else None, _ptr(pose), _ptr(be), B, D, L,
+                                    float(pose_prior_weight), float(angle_prior_weight), float(shape_prior_weight),
+                                    _ptr(value), _ptr(pv), _ptr(comp), _ptr(gp), _ptr(gb), _stream()), 'tuch_pose_terms')
+    return dict(value=value, prior=pv, component=comp, g_pose=gp, g_betas=gb)
+
+
+def contact_loss(points, argmin, exterior, euclthres, pull_mode=PULL_THRESHOLD, reduce_mode=REDUCE_SUM,
+                 body_active=None, counts=None, weight=1.0, g_loss=None, g_points=None, want_parts=False):
+    """Push/pull terms (losses.py:96-105 | loss.py:299-315 | eft/loss.py:158-166) -> (loss[B], parts | None).
+    When g_points[B,N,3] is given, weight * g_loss[b] * d loss[b]/d points is ACCUMULATED into it."""
+    p = _f32(points, 'points')
+    B, N = p.shape[0], p.shape[1]
+    am = _dev(argmin, 'argmin')
+    if am.dtype != torch.int32:
+        am = am.to(torch.int32)
+    am = am.contiguous()
+    ex = _dev(exterior, 'exterior').to(torch.uint8).contiguous()
+    if tuple(am.shape) != (B, N) or tuple(ex.shape) != (B, N):
+        raise TuchError('contact_loss: argmin / exterior must be [%d,%d]' % (B, N))
+    act = _dev(body_active, 'body_active').to(torch.uint8).contiguous() if body_active is not None else None
+    cnt = _dev(counts, 'counts').to(torch.int32).contiguous() if counts is not None else None
+    gl = _f32(g_loss, 'g_loss') if g_loss is not None else None
+    if g_points is not None and (g_points.dtype != torch.float32 or not g_points.is_contiguous()
+                                 or tuple(g_points.shape) != (B, N, 3)):
+        raise TuchError('contact_loss: g_points must be a contiguous fp32 [%d,%d,3] tensor' % (B, N))
+    loss = torch.empty(B, device=p.device, dtype=torch.float32)
+    parts = torch.empty(B, 4, device=p.device, dtype=torch.float32) if want_parts else None
+    with torch.cuda.device(p.device):
+        check(lib().tuch_contact_loss(_ptr(p), _ptr(am), _ptr(ex), _ptr(act), _ptr(cnt), B, N, float(euclthres),
+                                      int(pull_mode), int(reduce_mode), float(weight), _ptr(gl), _ptr(loss),
+                                      _ptr(parts), _ptr(g_points), _stream()), 'tuch_contact_loss')
+    return loss, parts
+
+
+def region_sum(verts, min_sq, arg_i, arg_j, body_active=None, weight=1.0, g_loss=None, g_verts=None):
+    """r2r[b] = sum of the reported region minima (losses.py:116-117); optionally accumulates the
+    gradient through the attaining vertex pairs into g_verts."""
+    v = _f32(verts, 'verts')
+    B, V = v.shape[0], v.shape[1]
+    P = min_sq.shape[1]
+    act = _dev(body_active, 'body_active').to(torch.uint8).contiguous() if body_active is not None else None
+    gl = _f32(g_loss, 'g_loss') if g_loss is not None else None
+    r2r = torch.empty(B, device=v.device, dtype=torch.float32)
+    with torch.cuda.device(v.device):
+        check(lib().tuch_region_sum(_ptr(v), B, V, P, _ptr(min_sq), _ptr(arg_i), _ptr(arg_j), _ptr(act), float(weight),
+                                    _ptr(gl), _ptr(r2r), _ptr(g_verts), _stream()), 'tuch_region_sum')
+    return r2r
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place torch.optim.Adam step on a contiguous fp32 CUDA tensor; step_dev is an int32 CUDA
+    scalar holding the steps taken so far (incremented by the call)."""
+    for t, n in ((param, 'param'), (grad, 'grad'), (exp_avg, 'exp_avg'), (exp_avg_sq, 'exp_avg_sq')):
+        _dev(t, n)
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
+            raise TuchError('adam_step: %s must be a contiguous fp32 tensor of %d elements' % (n, param.numel()))
+    if step_dev.dtype != torch.int32 or not step_dev.is_cuda:
+        raise TuchError('adam_step: step_dev must be an int32 CUDA tensor')
+    with torch.cuda.device(param.device):
+        check(lib().tuch_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
+                                   _ptr(step_dev), float(lr), float(beta1), float(beta2), float(eps), _stream()),
+              'tuch_adam_step')

@@ -1,0 +1,196 @@
+"""Host-side mirror of tuch/smplify/smplifydc.py: SMPLifyDC.__init__ (:30-66), __call__ (:68-236),
+get_fitting_loss (:238-276) -- same constructor / call arguments and the same 7-tuple return.
+
+Per iteration the reference runs ~80 ATen launches per body inside a Python loop over the batch plus
+torch.optim.Adam's per-parameter loop; here one iteration is: fused LBS forward (3 launches), the
+fused contact query (winding + segment whitelist + masked nearest vertex), the objective kernels
+(value + analytic gradient), the fused LBS backward and one Adam kernel per parameter tensor, all
+batched over the bodies and enqueued on the current stream without host synchronisation.
+
+Where the reference reads config.SMPL_MODEL_DIR / config.PRIOR_FOLDER / constants.JOINT_IDS from its
+un-shipped data tree, the same objects can be handed in directly (`smpl=`, `pose_prior=`,
+`ign_joints=`).
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from ..models.smpl import SMPL
+from .losses import camera_fitting_loss, body_fitting_loss, contact_fitting_loss, topology_for
+from .prior import MaxMixturePrior
+
+IGNORED_JOINT_NAMES = ['OP Neck', 'OP RHip', 'OP LHip', 'Right Hip', 'Left Hip']
+
+
+class _Adam:
+    """torch.optim.Adam(params, lr, betas) semantics over the fused Adam kernel (tuch_adam_step);
+    the step counter lives on the device."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.params = params
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.state = [(torch.zeros_like(p), torch.zeros_like(p),
+                       torch.zeros((), dtype=torch.int32, device=p.device)) for p in params]
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def step(self):
+        with torch.no_grad():
+            for p, (m, v, t) in zip(self.params, self.state):
+                if p.grad is None:
+                    continue
+                ops.adam_step(p, p.grad.contiguous(), m, v, t, self.lr, self.betas[0], self.betas[1], self.eps)
+
+
+class SMPLifyDC():
+    """SMPLify-DC optimisation follows the SMPLify routine, but takes discrete contact annotations
+    into account."""
+
+    def __init__(self,
+                 step_size=1e-2,
+                 batch_size=66,
+                 num_iters=100,
+                 focal_length=5000,
+                 geodistssmpl=None,
+                 geothres=0.0,
+                 euclthres=0.0,
+                 device=torch.device('cuda'),
+                 smpl=None, pose_prior=None, ign_joints=None):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise ops.TuchError('SMPLifyDC needs a CUDA device: tuch_b200 has no CPU fallback')
+        self.focal_length = focal_length
+        self.step_size = step_size
+        self.num_iters = num_iters
+        if ign_joints is None or pose_prior is None or smpl is None:
+            try:                                           # the reference's own sources (smplifydc.py:46-56)
+                from configs import config
+                from data.essentials import constants
+            except Exception as e:
+                raise ops.TuchError('SMPLifyDC: smpl= / pose_prior= / ign_joints= not given and the reference '
+                                    'data tree (configs.config, data.essentials.constants) is not importable: %s' % (e,))
+            if ign_joints is None:
+                ign_joints = [constants.JOINT_IDS[i] for i in IGNORED_JOINT_NAMES]
+            if pose_prior is None:
+                pose_prior = MaxMixturePrior(prior_folder=config.PRIOR_FOLDER, num_gaussians=8, dtype=torch.float32)
+            if smpl is None:
+                smpl = SMPL(config.SMPL_MODEL_DIR, batch_size=batch_size, create_transl=False)
+        self.ign_joints = [int(i) for i in ign_joints]
+        self.pose_prior = pose_prior.to(self.device)
+        self.smpl = smpl.to(self.device)
+        self.face_tensor = torch.tensor(self.smpl.faces.astype(np.int64), dtype=torch.long, device=self.device) \
+            .unsqueeze_(0).repeat([batch_size, 1, 1])
+        self.geodistssmpl = geodistssmpl
+        self.geothres = geothres
+        self.geomask = self.geodistssmpl > self.geothres
+        self.euclthres = euclthres
+
+    # ------------------------------------------------------------------ helpers
+    def _forward(self, global_orient, body_pose, betas, **kw):
+        return self.smpl(global_orient=global_orient, body_pose=body_pose, betas=betas, **kw)
+
+    def __call__(self, init_pose, init_betas, init_cam_t,
+                 camera_center, keypoints_2d, use_contact=False,
+                 contactlist=[], gt_contact=None,
+                 ignore_idxs=None, has_discrete_contact=None,
+                 has_gt_keypoints=None, contact_loss_weight=1,
+                 contact_loss_return='sum', segments=None):
+        """Perform body fitting.  Returns (vertices, joints, pose, betas, camera_translation,
+        reprojection_loss, optiverts) exactly as smplifydc.py:234."""
+        camera_translation = init_cam_t.clone()
+        joints_2d = keypoints_2d[:, :, :2].contiguous()
+        joints_conf = keypoints_2d[:, :, -1].clone()
+        body_pose = init_pose[:, 3:].detach().clone()
+        global_orient = init_pose[:, :3].detach().clone()
+        betas = init_betas.detach().clone()
+
+        # ---- stage 1: camera translation + (shape | global orientation), pose fixed (:100-134)
+        camera_translation.requires_grad_(True)
+        if use_contact:
+            betas.requires_grad_(True)
+            stage1 = [betas, camera_translation]
+        else:
+            global_orient.requires_grad_(True)
+            stage1 = [global_orient, camera_translation]
+        opt = _Adam(stage1, lr=self.step_size, betas=(0.9, 0.999))
+        spw = 1.0 if use_contact else 0.0
+        for _ in range(self.num_iters):
+            out = self._forward(global_orient, body_pose, betas)
+            loss = camera_fitting_loss(out, camera_translation, init_cam_t, camera_center, joints_2d, joints_conf,
+                                       focal_length=self.focal_length, shape_prior_weight=spw)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        # ---- stage 2 (:136-210)
+        optiverts = []
+        joints_conf[:, self.ign_joints] = 0.0
+        if use_contact:
+            loop1_pose, loop1_orient = body_pose.clone(), global_orient.clone()
+            camera_translation.requires_grad_(False)
+            betas.requires_grad_(False)
+            body_pose.requires_grad_(True)
+            global_orient.requires_grad_(True)
+            opt = _Adam([body_pose, global_orient], lr=self.step_size)
+            topo = topology_for(self.geomask, self.face_tensor, self.smpl.get_num_verts(), contactlist, segments)
+            for _ in range(self.num_iters):
+                out = self._forward(global_orient, body_pose, betas)
+                optiverts.append(out.vertices)
+                loss = contact_fitting_loss(body_pose, global_orient, loop1_pose, loop1_orient, betas, out.joints,
+                                            topo, self.euclthres, camera_translation, camera_center,
+                                            joints_2d, joints_conf, self.pose_prior,
+                                            cdict=contactlist, gt_contact=gt_contact, ignore_idxs=ignore_idxs,
+                                            has_discrete_contact=has_discrete_contact, verts=out.vertices,
+                                            face_tensor=self.face_tensor, focal_length=self.focal_length,
+                                            contact_loss_weight=contact_loss_weight, output=contact_loss_return,
+                                            segments=segments)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        else:
+            body_pose.requires_grad_(True)
+            betas.requires_grad_(True)
+            global_orient.requires_grad_(True)
+            camera_translation.requires_grad_(False)
+            opt = _Adam([body_pose, betas, global_orient], lr=self.step_size, betas=(0.9, 0.999))
+            for _ in range(self.num_iters):
+                out = self._forward(global_orient, body_pose, betas)
+                optiverts.append(out.vertices)
+                loss = body_fitting_loss(body_pose, betas, out.joints, camera_translation, camera_center,
+                                         joints_2d, joints_conf, self.pose_prior, focal_length=self.focal_length)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        if len(optiverts) == 0:
+            optiverts = None
+
+        # ---- final reprojection score and full skin (:215-229)
+        with torch.no_grad():
+            out = self._forward(global_orient, body_pose, betas, return_full_pose=True)
+            if has_gt_keypoints is not None:
+                joints_conf[has_gt_keypoints, :25] = 0
+            reprojection_loss = body_fitting_loss(body_pose, betas, out.joints, camera_translation, camera_center,
+                                                  joints_2d, joints_conf, self.pose_prior,
+                                                  focal_length=self.focal_length, output='reprojection')
+        vertices = out.vertices.detach()
+        joints = out.joints.detach()
+        pose = torch.cat([global_orient, body_pose], dim=-1).detach()
+        betas = betas.detach()
+        return vertices, joints, pose, betas, camera_translation, reprojection_loss, optiverts
+
+    def get_fitting_loss(self, pose, betas, cam_t, camera_center, keypoints_2d, has_gt_keypoints=None):
+        """Reprojection loss [B,49] of given body and camera parameters (smplifydc.py:238-276).  As in
+        the reference, the confidences of the ignored joints are zeroed IN the caller's keypoints_2d."""
+        joints_2d = keypoints_2d[:, :, :2]
+        joints_conf = keypoints_2d[:, :, -1]
+        joints_conf[:, self.ign_joints] = 0.
+        if has_gt_keypoints is not None:
+            joints_conf = joints_conf.clone()
+            joints_conf[has_gt_keypoints, :25] = 0
+        body_pose, global_orient = pose[:, 3:], pose[:, :3]
+        with torch.no_grad():
+            out = self._forward(global_orient, body_pose, betas, return_full_pose=True)
+            return body_fitting_loss(body_pose, betas, out.joints, cam_t, camera_center, joints_2d, joints_conf,
+                                     self.pose_prior, focal_length=self.focal_length, output='reprojection')
