@@ -225,6 +225,30 @@ int tuch_region_sum(const float* verts, int B, int V, int n_pairs, const float* 
 int tuch_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                    int32_t* step_dev, double lr, double beta1, double beta2, double eps, void* stream);
 
+/* ------------------------------------------------------------------ a12  RegressorLoss.contact_loss
+ * tuch/train/loss.py:240-317.  The HD-point regressor (loss.py:81-83 loads it as a dense [N_hd, V]
+ * matrix) is handed over in CSR form (HOST arrays, copied) together with faces_vert_is_sampled_from
+ * (loss.py:84-88). */
+int tuch_topology_set_hd(tuch_topology* topo, int n_hd, const int32_t* row_offsets_host,
+                         const int32_t* cols_host, const float* vals_host, const int32_t* hd_face_host);
+int tuch_topology_num_hd(const tuch_topology* topo);
+
+/* loss[b] for every body with valid[b] != 0 (valid NULL = all; others get 0):
+ *   exterior / nearest geodesically-far vertex of the mesh vertices, segment whitelist always on (:251-270)
+ *   use_hd != 0: HD points on faces touching a vertex that is in contact (min_sq < euclthres^2) or interior
+ *     (:278-281), regressed from the vertices (:285), masked nearest HD point through the proxy vertices
+ *     (:288-291), inside test of the 1 mm normal-offset points against the mesh (:295-297),
+ *     loss[b] = sum 0.005 tanh(d/0.005)^2 [exterior] + sum tanh(d/0.04)^2 [interior]   (:299-315)
+ *   use_hd == 0: the same terms on the mesh vertices (:303).
+ * g_verts[B,V,3] (may be NULL) is ACCUMULATED into: += weight * g_loss[b] * d loss[b] / d verts.
+ * Optional debug outputs: counts_out[B] selected HD points per body, sel_out[B,N_hd] their indices
+ * (first counts entries), hd_argmin_out / hd_exterior_out [B,N_hd] in selection order.
+ * The caller forms contact_loss[valid_fit].mean() (:317). */
+int tuch_regressor_contact_loss(const tuch_topology* topo, const float* verts, int B, const uint8_t* valid,
+                                float euclthres, int use_hd, float weight, const float* g_loss, float* loss,
+                                float* g_verts, int32_t* counts_out, int32_t* sel_out, int32_t* hd_argmin_out,
+                                uint8_t* hd_exterior_out, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer conveniences
  * Same as the calls above with HOST buffers; copies in/out on an internal stream and
  * synchronises.  Used by non-torch callers and by the end-to-end benchmark leg. */

@@ -1,0 +1,130 @@
+"""GPU parity of RegressorLoss (tuch_b200/train/loss.py over tuch_regressor_contact_loss) against the
+golden vectors recorded from the reference's tuch/train/loss.py and against the CPU oracle."""
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+Opt = namedtuple('Opt', ['contact_loss_weight', 'openpose_train_weight', 'gt_train_weight', 'shape_loss_weight',
+                         'keypoint_loss_weight', 'pose_loss_weight', 'beta_loss_weight'])
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def make_criterion(assets, use_hd, geothres=0.3, B=3):
+    from tuch_b200.train.loss import RegressorLoss
+    from tuch_b200.utils.segmentation import BatchBodySegment
+    m = assets['model']
+    faces = torch.tensor(m['faces'], device=DEV)
+    face_tensor = faces[None].repeat(B, 1, 1)
+    segments = BatchBodySegment(list(assets['segs'].keys()), faces, segment_data=assets['segs'])
+    return RegressorLoss(Opt(1.0, 0.0, 1.0, 0.0, 5.0, 1.0, 0.001), DEV, len(m['v_template']), face_tensor,
+                         torch.tensor(assets['geo'], device=DEV), geothres=geothres, euclthres=0.02,
+                         face_tensor=face_tensor, use_hd=use_hd, hd_regressor=assets.get('hd_reg'),
+                         hd_faces=assets.get('hd_fidx'), segments=segments)
+
+
+@pytest.mark.parametrize('tag,use_hd', [('hd', True), ('nohd', False)])
+def test_contact_loss_matches_reference_golden(small_assets, tag, use_hd):
+    r = golden('regressor_contact_loss.npz')
+    crit = make_criterion(small_assets, use_hd)
+    pv = torch.tensor(r['verts'], device=DEV, requires_grad=True)
+    val = crit.contact_loss(pv, torch.tensor(r['valid'], device=DEV))
+    val.backward()
+    ref = float(r[tag + '/loss'])
+    assert abs(val.item() - ref) < 1e-4 * abs(ref), (val.item(), ref)
+    assert rel(pv.grad, r[tag + '/g_verts']) < 2e-4
+
+
+def test_hd_selection_matches_oracle(small_assets):
+    """selection, HD nearest point and HD inside flags against the oracle's per-body restatement."""
+    from oracle import regressor as oreg, segments as oseg
+    a = small_assets
+    r = golden('regressor_contact_loss.npz')
+    crit = make_criterion(a, True)
+    verts = torch.tensor(r['verts'], device=DEV)
+    valid = torch.tensor([True, True, True], device=DEV)
+    loss, dbg = crit._topo.regressor_contact_loss(verts, valid=valid, euclthres=0.02, use_hd=True, debug=True)
+    segs = oseg.build_segments(a['segs'], a['model']['faces'])
+    _, aux = oreg.regressor_contact_loss(torch.tensor(r['verts']), [True] * 3, a['model']['faces'], a['geo'] > 0.3,
+                                         0.02, segs, a['hd_reg'], a['hd_fidx'], use_hd=True, return_aux=True)
+    assert sum(int(x['sel_hd'].sum()) for x in aux.values()) > 0
+    for b in range(3):
+        sel = np.where(aux[b]['sel_hd'])[0]
+        n = int(dbg['counts'][b])
+        assert n == len(sel)
+        assert np.array_equal(dbg['sel'][b, :n].cpu().numpy(), sel)
+        if n:
+            assert np.array_equal(dbg['hd_argmin'][b, :n].cpu().numpy(), aux[b]['hd_argmin'])
+            assert np.array_equal(dbg['hd_exterior'][b, :n].cpu().numpy().astype(bool), aux[b]['hd_exterior'])
+
+
+def test_forward_loss_dict_and_invalid_bodies(small_assets):
+    a = small_assets
+    r = golden('regressor_contact_loss.npz')
+    crit = make_criterion(a, True)
+    B = 3
+    g = torch.Generator().manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(DEV)
+    pv = torch.tensor(r['verts'], device=DEV, requires_grad=True)
+    valid = torch.tensor([True, False, True], device=DEV)
+    kp = torch.cat([rnd(B, 49, 2), torch.rand(B, 49, 1, generator=g).to(DEV)], -1)
+    j3 = torch.cat([rnd(B, 24, 3), torch.ones(B, 24, 1, device=DEV)], -1)
+    pose = rnd(B, 72) * 0.2
+    from tuch_b200.utils.geometry import batch_rodrigues
+    rot = batch_rodrigues(pose.view(-1, 3)).view(B, 24, 3, 3) + 0.01 * rnd(B, 24, 3, 3)
+    total, d = crit(rot, rnd(B, 10), pose, rnd(B, 10), rnd(B, 49, 2), kp, rnd(B, 49, 3), j3,
+                    torch.tensor([1, 0, 1], device=DEV), pv, torch.tensor(r['verts'], device=DEV) + 0.01,
+                    rnd(B, 3), valid, valid)
+    assert set(d) == {'loss_shape', 'loss_keypoints', 'loss_keypoints_3d', 'loss_regr_pose', 'loss_regr_betas',
+                      'loss_cam', 'loss_contact'}
+    assert abs(d['loss_contact'].item() - float(r['hd/loss'])) < 1e-4 * abs(float(r['hd/loss']))
+    assert abs(d['loss_shape'].item() - 0.01) < 1e-5
+    total.backward()
+    assert torch.isfinite(pv.grad).all() and pv.grad[1].abs().max() == 0        # invalid body gets no gradient
+    assert hasattr(crit, 'segments') and crit.segments.names == list(a['segs'].keys())
+
+
+def test_contact_loss_full_size(full_assets):
+    """SMPL-sized mesh with a 20k-point HD model: oracle parity on 2 bodies (value + gradient)."""
+    from oracle import regressor as oreg, segments as oseg
+    from tuch_b200 import synthetic as syn
+    from test_contact_gpu import posed_verts
+    a = dict(full_assets)
+    a['hd_reg'], a['hd_fidx'] = syn.make_hd_regressor(a['model'], n_hd=20000)
+    crit = make_criterion(a, True, B=2)
+    verts = posed_verts(a, 2, seed=21)
+    pv = torch.tensor(verts, device=DEV, requires_grad=True)
+    val = crit.contact_loss(pv, torch.tensor([True, True], device=DEV))
+    val.backward()
+    segs = oseg.build_segments(a['segs'], a['model']['faces'])
+    p32 = torch.tensor(verts, requires_grad=True)
+    ref, aux = oreg.regressor_contact_loss(p32, [True, True], a['model']['faces'], a['geo'] > 0.3, 0.02, segs,
+                                           a['hd_reg'], a['hd_fidx'], use_hd=True, return_aux=True)
+    ref.backward()
+    assert ref.item() > 0
+    # 20k HD points are dense enough for fp32 near-ties in the nearest-point search: the selection must
+    # be identical, the nearest point / inside flag may differ on a handful of points, and the loss and
+    # its gradient must agree up to those
+    _, dbg = crit._topo.regressor_contact_loss(pv.detach(), valid=torch.tensor([True, True], device=DEV),
+                                               euclthres=0.02, use_hd=True, debug=True)
+    for b in range(2):
+        sel = np.where(aux[b]['sel_hd'])[0]
+        n = int(dbg['counts'][b])
+        assert n == len(sel) and n > 100
+        assert np.array_equal(dbg['sel'][b, :n].cpu().numpy(), sel)
+        assert (dbg['hd_argmin'][b, :n].cpu().numpy() != aux[b]['hd_argmin']).mean() < 0.01
+        assert (dbg['hd_exterior'][b, :n].cpu().numpy().astype(bool) != aux[b]['hd_exterior']).mean() < 0.005
+    assert abs(val.item() - ref.item()) < 2e-3 * abs(ref.item()), (val.item(), ref.item())
+    g, gr = pv.grad.cpu().double().flatten(), p32.grad.double().flatten()
+    assert float((g * gr).sum() / (g.norm() * gr.norm())) > 0.9995
+    assert rel(pv.grad, p32.grad.numpy()) < 5e-2

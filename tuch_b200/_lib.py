@@ -59,6 +59,9 @@ def _declare(lib):
     lib.tuch_contact_loss.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, vp, vp, vp]
     lib.tuch_region_sum.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp]
     lib.tuch_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
+    lib.tuch_topology_set_hd.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.tuch_topology_num_hd.argtypes = [vp]
+    lib.tuch_regressor_contact_loss.argtypes = [vp, vp, i32, vp, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tuch_winding_numbers_host.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.tuch_contact_query_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
 

@@ -69,13 +69,13 @@ KernelTimer::~KernelTimer() {
 // ---------------------------------------------------------------- scratch arenas
 struct Arena { void* ptr = nullptr; size_t cap = 0; };
 static std::mutex g_arena_mu;
-static std::map<std::pair<int, cudaStream_t>, Arena> g_arenas;
+static std::map<std::pair<std::pair<int, int>, cudaStream_t>, Arena> g_arenas;
 
-int arena_get(cudaStream_t st, size_t bytes, void** out) {
+int arena_get(cudaStream_t st, size_t bytes, void** out, int slot) {
     int dev = 0;
     TUCH_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_arena_mu);
-    Arena& a = g_arenas[{dev, st}];
+    Arena& a = g_arenas[{{dev, slot}, st}];
     if (a.cap < bytes) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
@@ -95,9 +95,9 @@ int arena_get(cudaStream_t st, size_t bytes, void** out) {
     return 0;
 }
 
-int Scratch::commit(cudaStream_t st) {
+int Scratch::commit_slot(cudaStream_t st, int slot) {
     void* p = nullptr;
-    if (int rc = arena_get(st, total_ > 0 ? total_ : 256, &p)) return rc;
+    if (int rc = arena_get(st, total_ > 0 ? total_ : 256, &p, slot)) return rc;
     base_ = (char*)p;
     return 0;
 }
@@ -130,7 +130,7 @@ TUCH_EXPORT int tuch_release_scratch(void) {
     TUCH_CUDA(cudaDeviceSynchronize());
     std::lock_guard<std::mutex> lk(g_arena_mu);
     for (auto it = g_arenas.begin(); it != g_arenas.end();) {
-        if (it->first.first == dev) {
+        if (it->first.first.first == dev) {
             if (it->second.ptr) cudaFree(it->second.ptr);
             it = g_arenas.erase(it);
         } else {
@@ -271,6 +271,7 @@ static void free_segments(tuch_topology* t) {
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT);
+    free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
 }

@@ -20,11 +20,16 @@ struct tuch_topology {
     std::vector<int> h_slot_off;       // [S+1] packed (padded) triangle ranges
     int *d_seg_vidx = nullptr, *d_seg_faces = nullptr, *d_slot_face = nullptr, *d_slot_band0 = nullptr;
     int *d_loop_off = nullptr, *d_loop_ids = nullptr;
+    // HD-point regressor (CSR rows) and the source face of every HD point (loss.py:81-89)
+    int n_hd = 0;
+    int *d_hd_row_off = nullptr, *d_hd_cols = nullptr, *d_hd_face = nullptr;
+    float* d_hd_vals = nullptr;
 };
 
 namespace tuch {
 
-int arena_get(cudaStream_t st, size_t bytes, void** out);
+// slot 0 is the arena of the leaf entry points; slot 1 belongs to entry points that call them
+int arena_get(cudaStream_t st, size_t bytes, void** out, int slot = 0);
 
 // Two-phase bump allocator over the per-(device, stream) arena: plan() every buffer, commit()
 // once (may grow the arena), then get<T>().
@@ -35,7 +40,8 @@ public:
         total_ += align_up(bytes, 256);
         return off;
     }
-    int commit(cudaStream_t st);
+    int commit(cudaStream_t st) { return commit_slot(st, 0); }
+    int commit_slot(cudaStream_t st, int slot);
     template <typename T> T* get(size_t handle) const { return (T*)(base_ + handle); }
 private:
     size_t total_ = 0;

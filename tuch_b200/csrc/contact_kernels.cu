@@ -69,12 +69,18 @@ __global__ void pack_triangles_kernel(const float* __restrict__ tris, int F, int
 __global__ void __launch_bounds__(WN_THREADS)
 winding_kernel(const float4* __restrict__ tri12, const float* __restrict__ points,
                float* __restrict__ partial, int Q, int Fp, int tiles_per_split, long long tri_stride,
-               long long point_stride, long long partial_stride, const uint8_t* __restrict__ body_active) {
+               long long point_stride, long long partial_stride, const uint8_t* __restrict__ body_active,
+               const int* __restrict__ q_counts) {
     __shared__ __align__(128) float4 s_tri[WN_STAGES][WN_TILE_F * 3];
     __shared__ __align__(8) uint64_t s_bar[WN_STAGES];
 
     const int b = blockIdx.z;
     if (body_active != nullptr && !body_active[b]) return;     // uniform per CTA
+    const int q_stride = Q;                                    // layout of `partial` is [S][Q]
+    if (q_counts != nullptr) {                                 // data-dependent query count (HD selection)
+        Q = min(Q, q_counts[b]);
+        if ((int)blockIdx.x * (WN_THREADS * WN_QPT) >= Q) return;
+    }
     const int split = blockIdx.y;
     const int n_tiles_total = Fp / WN_TILE_F;
     const int tile0 = split * tiles_per_split;
@@ -121,7 +127,7 @@ winding_kernel(const float4* __restrict__ tri12, const float* __restrict__ point
         }
     }
 
-    float* out = partial + (size_t)b * partial_stride + (size_t)split * Q;
+    float* out = partial + (size_t)b * partial_stride + (size_t)split * q_stride;
 #pragma unroll
     for (int k = 0; k < WN_QPT; ++k) {
         const int q = q0 + k * WN_THREADS;
@@ -132,11 +138,15 @@ winding_kernel(const float4* __restrict__ tri12, const float* __restrict__ point
 // sums the F-split partials in a fixed order and applies 2 / (4 pi)   (contact.py:109,146-147)
 __global__ void winding_finalize_kernel(const float* __restrict__ partial, int Q, int S,
                                         long long partial_stride, long long out_stride,
-                                        float* __restrict__ winding, const uint8_t* __restrict__ body_active) {
+                                        float* __restrict__ winding, const uint8_t* __restrict__ body_active,
+                                        const int* __restrict__ q_counts) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
-    if (body_active != nullptr && !body_active[b]) { winding[(size_t)b * out_stride + q] = 0.f; return; }
+    if ((body_active != nullptr && !body_active[b]) || (q_counts != nullptr && q >= q_counts[b])) {
+        winding[(size_t)b * out_stride + q] = 0.f;
+        return;
+    }
     const float* p = partial + (size_t)b * partial_stride + q;
     float acc = 0.f;
     for (int s = 0; s < S; ++s) acc += p[(size_t)s * Q];
@@ -424,12 +434,12 @@ int launch_winding(const WindingJob& j, cudaStream_t st) {
     {
         KernelTimer timer(j.body_active == nullptr && j.Q >= 1024 ? "winding_kernel" : "winding_kernel_segments", st);
         winding_kernel<<<grid, WN_THREADS, 0, st>>>(j.tri12, j.points, j.partial, j.Q, j.Fp, per, j.tri_stride,
-                                                    j.point_stride, (long long)j.S * j.Q, j.body_active);
+                                                    j.point_stride, (long long)j.S * j.Q, j.body_active, j.q_counts);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     dim3 g2(cdiv(j.Q, 256), j.B);
     winding_finalize_kernel<<<g2, 256, 0, st>>>(j.partial, j.Q, j.S, (long long)j.S * j.Q, j.out_stride,
-                                                j.winding, j.body_active);
+                                                j.winding, j.body_active, j.q_counts);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

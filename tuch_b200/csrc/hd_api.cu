@@ -1,0 +1,111 @@
+// C ABI of the regressor contact loss (include/tuch_b200.h, section a12): tuch/train/loss.py:240-317.
+#include "hd_internal.h"
+#include "objective_internal.h"
+
+using namespace tuch;
+
+TUCH_EXPORT int tuch_topology_set_hd(tuch_topology* t, int n_hd, const int32_t* row_offsets_host,
+                                     const int32_t* cols_host, const float* vals_host, const int32_t* hd_face_host) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_set_hd: null topology");
+    TUCH_REQUIRE(n_hd >= 0, "tuch_topology_set_hd: negative count");
+    auto freep = [](void* p) { if (p) cudaFree(p); };
+    freep(t->d_hd_row_off); freep(t->d_hd_cols); freep(t->d_hd_vals); freep(t->d_hd_face);
+    t->d_hd_row_off = t->d_hd_cols = t->d_hd_face = nullptr; t->d_hd_vals = nullptr; t->n_hd = 0;
+    if (n_hd == 0) return 0;
+    TUCH_REQUIRE(row_offsets_host && cols_host && vals_host && hd_face_host, "tuch_topology_set_hd: null array");
+    TUCH_REQUIRE(row_offsets_host[0] == 0, "tuch_topology_set_hd: row_offsets[0] must be 0");
+    for (int k = 0; k < n_hd; ++k) {
+        TUCH_REQUIRE(row_offsets_host[k + 1] >= row_offsets_host[k], "tuch_topology_set_hd: row offsets must not decrease");
+        TUCH_REQUIRE(hd_face_host[k] >= 0 && hd_face_host[k] < t->F, "tuch_topology_set_hd: source face %d out of range", hd_face_host[k]);
+    }
+    const int nnz = row_offsets_host[n_hd];
+    for (int e = 0; e < nnz; ++e)
+        TUCH_REQUIRE(cols_host[e] >= 0 && cols_host[e] < t->V, "tuch_topology_set_hd: column %d out of range", cols_host[e]);
+    auto up = [](const void* h, size_t bytes, void** d) -> int {
+        TUCH_CUDA(cudaMalloc(d, bytes ? bytes : 4));
+        if (bytes) TUCH_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (int rc = up(row_offsets_host, sizeof(int) * ((size_t)n_hd + 1), (void**)&t->d_hd_row_off)) return rc;
+    if (int rc = up(cols_host, sizeof(int) * (size_t)nnz, (void**)&t->d_hd_cols)) return rc;
+    if (int rc = up(vals_host, sizeof(float) * (size_t)nnz, (void**)&t->d_hd_vals)) return rc;
+    if (int rc = up(hd_face_host, sizeof(int) * (size_t)n_hd, (void**)&t->d_hd_face)) return rc;
+    t->n_hd = n_hd;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_num_hd(const tuch_topology* t) { return t ? t->n_hd : -1; }
+
+TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float* verts, int B, const uint8_t* valid,
+                                            float euclthres, int use_hd, float weight, const float* g_loss,
+                                            float* loss, float* g_verts, int32_t* counts_out, int32_t* sel_out,
+                                            int32_t* hd_argmin_out, uint8_t* hd_exterior_out, void* stream) {
+    TUCH_REQUIRE(t != nullptr, "tuch_regressor_contact_loss: null topology");
+    TUCH_REQUIRE(B >= 0, "tuch_regressor_contact_loss: negative batch");
+    if (B == 0) return 0;
+    TUCH_REQUIRE(verts && loss, "tuch_regressor_contact_loss: null pointer");
+    TUCH_REQUIRE(t->has_mask && t->F > 0, "tuch_regressor_contact_loss: the topology needs faces and a geodesic mask");
+    TUCH_REQUIRE(!use_hd || t->n_hd > 0, "tuch_regressor_contact_loss: use_hd requested but no HD regressor is set "
+                                         "(tuch_topology_set_hd)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = t->V, N = use_hd ? t->n_hd : 0;
+    const size_t BV = (size_t)B * V, BN = (size_t)B * N;
+
+    // the caller-visible scratch of this entry point lives in its own arena slot: contact_query_impl
+    // commits the shared per-stream arena, so everything that must survive it is planned FIRST there
+    // through `reserve` (see contact_query_impl)
+    Scratch sc;
+    const size_t h_am = sc.plan(sizeof(int) * BV), h_mn = sc.plan(sizeof(float) * BV), h_ex = sc.plan(BV);
+    const size_t h_idx = sc.plan(sizeof(int) * BN), h_cnt = sc.plan(sizeof(int) * (size_t)B);
+    const size_t h_hd4 = sc.plan(sizeof(float4) * BN), h_hd = sc.plan(sizeof(float) * 3 * BN);
+    const size_t h_off = sc.plan(sizeof(float) * 3 * BN), h_px = sc.plan(sizeof(int) * BN);
+    const size_t h_ham = sc.plan(sizeof(int) * BN), h_hw = sc.plan(sizeof(float) * BN), h_hex = sc.plan(BN);
+    const size_t h_ghd = sc.plan(sizeof(float) * 3 * BN);
+    const int Fp = t->Fp;
+    const int S = use_hd ? winding_splits(B, N, Fp, sm_count()) : 1;
+    const size_t h_tri = sc.plan(use_hd ? sizeof(float4) * 3 * (size_t)B * Fp : 0);
+    const size_t h_par = sc.plan(use_hd ? sizeof(float) * (size_t)B * S * N : 0);
+    if (int rc = sc.commit_slot(st, 1)) return rc;
+    int* am = sc.get<int>(h_am);
+    float* mn = sc.get<float>(h_mn);
+    uint8_t* ex = sc.get<uint8_t>(h_ex);
+
+    // loss.py:251-270 -- exterior flags (winding + segment whitelist) and the masked nearest vertex
+    if (int rc = contact_query_impl(t, verts, B, 1, am, mn, nullptr, ex, nullptr, st)) return rc;
+
+    if (!use_hd) {                                                    // loss.py:303-315
+        return launch_contact_loss(verts, am, ex, valid, nullptr, B, V, 0.f, PULL_ALL, REDUCE_SUM, weight, g_loss,
+                                   loss, nullptr, g_verts, st);
+    }
+    int* idx = sel_out ? sel_out : sc.get<int>(h_idx);
+    int* cnt = counts_out ? counts_out : sc.get<int>(h_cnt);
+    float4* hd4 = sc.get<float4>(h_hd4);
+    float* hd = sc.get<float>(h_hd);
+    float* off = sc.get<float>(h_off);
+    int* proxy = sc.get<int>(h_px);
+    int* ham = hd_argmin_out ? hd_argmin_out : sc.get<int>(h_ham);
+    float* hw = sc.get<float>(h_hw);
+    uint8_t* hex = hd_exterior_out ? hd_exterior_out : sc.get<uint8_t>(h_hex);
+    if (int rc = launch_hd_select(mn, ex, valid, t->d_faces, B, V, N, t->d_hd_face, euclthres * euclthres, idx, cnt, st)) return rc;
+    if (int rc = launch_hd_gather(verts, B, V, N, idx, cnt, t->d_hd_row_off, t->d_hd_cols, t->d_hd_vals, t->d_hd_face,
+                                  t->d_faces, hd4, hd, off, proxy, st)) return rc;
+    if (int rc = launch_hd_nearest(hd4, proxy, cnt, B, N, t->d_maskT, t->Vq, ham, st)) return rc;
+    // loss.py:297 -- inside test of the offset HD points against the full mesh
+    float4* tri12 = sc.get<float4>(h_tri);
+    if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, t->Vp, tri12, nullptr, st)) return rc;
+    WindingJob j{tri12, (long long)Fp * 3, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Fp, S};
+    j.q_counts = cnt;
+    if (int rc = launch_winding(j, st)) return rc;
+    if (int rc = launch_exterior_init(hw, B, N, hex, nullptr, st)) return rc;
+    // loss.py:299-315
+    float* g_hd = nullptr;
+    if (g_verts != nullptr) {
+        g_hd = sc.get<float>(h_ghd);
+        TUCH_CUDA(cudaMemsetAsync(g_hd, 0, sizeof(float) * 3 * BN, st));
+    }
+    if (int rc = launch_contact_loss(hd, ham, hex, valid, cnt, B, N, 0.f, PULL_ALL, REDUCE_SUM, weight, g_loss, loss,
+                                     nullptr, g_hd, st)) return rc;
+    if (g_verts != nullptr)
+        if (int rc = launch_hd_scatter(g_hd, B, V, N, idx, cnt, t->d_hd_row_off, t->d_hd_cols, t->d_hd_vals, g_verts, st)) return rc;
+    return 0;
+}

@@ -30,6 +30,7 @@ struct WindingJob {
     float* winding; long long out_stride;          // floats per body
     const uint8_t* body_active;                    // optional [B]: 0 = skip body (output 0)
     int B, Q, Fp, S;
+    const int* q_counts = nullptr;                 // optional [B]: only the first q_counts[b] queries are valid
 };
 int launch_winding(const WindingJob& job, cudaStream_t st);
 int launch_nearest(const float4* vert4, const uint32_t* maskT, int B, int V, int Vp, int Vq,

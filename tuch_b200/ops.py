@@ -137,6 +137,7 @@ class Topology:
         self.segment_names = []
         self.segment_vidx = []
         self.n_seg_verts = 0
+        self.n_hd = 0
 
     def __del__(self):
         try:
@@ -221,6 +222,57 @@ class Topology:
         self.segment_names = names
         self.segment_vidx = vidx_list
         self.n_seg_verts = int(v_off[-1])
+
+    def set_hd(self, regressor, faces_vert_is_sampled_from):
+        """HD-point model of the regressor loss (loss.py:81-89): `regressor` is the dense [N_hd, V] matrix
+        the reference loads (numpy / torch / scipy.sparse); only its non-zeros are kept (CSR)."""
+        if hasattr(regressor, 'tocsr'):
+            csr = regressor.tocsr()
+            off, cols, vals = csr.indptr, csr.indices, csr.data
+            n = csr.shape[0]
+        else:
+            R = regressor.detach().cpu().numpy() if isinstance(regressor, torch.Tensor) else np.asarray(regressor)
+            if R.ndim != 2 or R.shape[1] != self.V:
+                raise TuchError('HD regressor must be [N_hd,%d], got %s' % (self.V, R.shape))
+            n = R.shape[0]
+            r, c = np.nonzero(R)
+            off = np.zeros(n + 1, np.int64)
+            np.add.at(off, r + 1, 1)
+            off = np.cumsum(off)
+            cols, vals = c, R[r, c]
+        hf = faces_vert_is_sampled_from
+        hf = hf.detach().cpu().numpy() if isinstance(hf, torch.Tensor) else np.asarray(hf)
+        if len(hf) != n:
+            raise TuchError('faces_vert_is_sampled_from has %d entries for %d HD points' % (len(hf), n))
+        off, cols, hf = _i32_host(off), _i32_host(cols), _i32_host(hf)
+        vals = np.ascontiguousarray(vals, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_set_hd(self._h, int(n), _hp(off), _hp(cols), _hp(vals), _hp(hf)),
+                  'tuch_topology_set_hd')
+        self.n_hd = int(n)
+
+    def regressor_contact_loss(self, verts, valid=None, euclthres=0.02, use_hd=True, weight=1.0, g_loss=None,
+                               g_verts=None, debug=False):
+        """loss.py:240-315 for the whole batch -> loss[B] (0 for invalid bodies); see tuch_regressor_contact_loss."""
+        v = self._verts(verts)
+        B = v.shape[0]
+        val = _dev(valid, 'valid').to(torch.uint8).contiguous() if valid is not None else None
+        gl = _f32(g_loss, 'g_loss') if g_loss is not None else None
+        loss = torch.zeros(B, device=v.device, dtype=torch.float32)
+        N = getattr(self, 'n_hd', 0) if use_hd else 0
+        dbg = {}
+        if debug and use_hd:
+            dbg = dict(counts=torch.zeros(B, device=v.device, dtype=torch.int32),
+                       sel=torch.zeros(B, N, device=v.device, dtype=torch.int32),
+                       hd_argmin=torch.zeros(B, N, device=v.device, dtype=torch.int32),
+                       hd_exterior=torch.zeros(B, N, device=v.device, dtype=torch.uint8))
+        with torch.cuda.device(v.device):
+            check(lib().tuch_regressor_contact_loss(self._h, _ptr(v), B, _ptr(val), float(euclthres), int(bool(use_hd)),
+                                                    float(weight), _ptr(gl), _ptr(loss), _ptr(g_verts),
+                                                    _ptr(dbg.get('counts')), _ptr(dbg.get('sel')),
+                                                    _ptr(dbg.get('hd_argmin')), _ptr(dbg.get('hd_exterior')), _stream()),
+                  'tuch_regressor_contact_loss')
+        return (loss, dbg) if debug else loss
 
     # ------------------------------------------------------------------ queries
     def _verts(self, verts):

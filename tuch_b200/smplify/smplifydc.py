@@ -44,6 +44,39 @@ class _Adam:
                 ops.adam_step(p, p.grad.contiguous(), m, v, t, self.lr, self.betas[0], self.betas[1], self.eps)
 
 
+class ContactFit:
+    """One stage-2 optimisation in flight; see SMPLifyDC.begin_contact_fit."""
+
+    def __init__(self, owner, body_pose, global_orient, betas, camera_translation, camera_center, joints_2d,
+                 joints_conf, contactlist, gt_contact, ignore_idxs, has_discrete_contact, contact_loss_weight,
+                 contact_loss_return, segments):
+        self.owner = owner
+        self.body_pose, self.global_orient, self.betas = body_pose, global_orient, betas
+        self.loop1_pose, self.loop1_orient = body_pose.detach().clone(), global_orient.detach().clone()
+        body_pose.requires_grad_(True)
+        global_orient.requires_grad_(True)
+        self.opt = _Adam([body_pose, global_orient], lr=owner.step_size)
+        self.topo = topology_for(owner.geomask, owner.face_tensor, owner.smpl.get_num_verts(), contactlist, segments)
+        self.args = dict(camera_t=camera_translation, camera_center=camera_center, joints_2d=joints_2d,
+                         joints_conf=joints_conf, pose_prior=owner.pose_prior, cdict=contactlist,
+                         gt_contact=gt_contact, ignore_idxs=ignore_idxs, has_discrete_contact=has_discrete_contact,
+                         face_tensor=owner.face_tensor, focal_length=owner.focal_length,
+                         contact_loss_weight=contact_loss_weight, output=contact_loss_return, segments=segments)
+        self.vertices = None
+        self.loss = None
+
+    def step(self):
+        out = self.owner._forward(self.global_orient, self.body_pose, self.betas)
+        self.vertices = out.vertices
+        self.loss = contact_fitting_loss(self.body_pose, self.global_orient, self.loop1_pose, self.loop1_orient,
+                                         self.betas, out.joints, self.topo, self.owner.euclthres,
+                                         verts=out.vertices, **self.args)
+        self.opt.zero_grad()
+        self.loss.backward()
+        self.opt.step()
+        return self.loss
+
+
 class SMPLifyDC():
     """SMPLify-DC optimisation follows the SMPLify routine, but takes discrete contact annotations
     into account."""
@@ -91,6 +124,16 @@ class SMPLifyDC():
     def _forward(self, global_orient, body_pose, betas, **kw):
         return self.smpl(global_orient=global_orient, body_pose=body_pose, betas=betas, **kw)
 
+    def begin_contact_fit(self, body_pose, global_orient, betas, camera_translation, camera_center, joints_2d,
+                          joints_conf, contactlist, gt_contact, ignore_idxs, has_discrete_contact,
+                          contact_loss_weight=1, contact_loss_return='sum', segments=None):
+        """Stage-2 contact optimisation state (smplifydc.py:139-183): body_pose / global_orient become the
+        optimised leaves (updated in place), everything else is held fixed.  ContactFit.step() runs one
+        iteration: SMPL forward -> contact_fitting_loss -> backward -> Adam."""
+        return ContactFit(self, body_pose, global_orient, betas, camera_translation, camera_center, joints_2d,
+                          joints_conf, contactlist, gt_contact, ignore_idxs, has_discrete_contact,
+                          contact_loss_weight, contact_loss_return, segments)
+
     def __call__(self, init_pose, init_betas, init_cam_t,
                  camera_center, keypoints_2d, use_contact=False,
                  contactlist=[], gt_contact=None,
@@ -128,27 +171,14 @@ class SMPLifyDC():
         optiverts = []
         joints_conf[:, self.ign_joints] = 0.0
         if use_contact:
-            loop1_pose, loop1_orient = body_pose.clone(), global_orient.clone()
             camera_translation.requires_grad_(False)
             betas.requires_grad_(False)
-            body_pose.requires_grad_(True)
-            global_orient.requires_grad_(True)
-            opt = _Adam([body_pose, global_orient], lr=self.step_size)
-            topo = topology_for(self.geomask, self.face_tensor, self.smpl.get_num_verts(), contactlist, segments)
+            fit = self.begin_contact_fit(body_pose, global_orient, betas, camera_translation, camera_center,
+                                         joints_2d, joints_conf, contactlist, gt_contact, ignore_idxs,
+                                         has_discrete_contact, contact_loss_weight, contact_loss_return, segments)
             for _ in range(self.num_iters):
-                out = self._forward(global_orient, body_pose, betas)
-                optiverts.append(out.vertices)
-                loss = contact_fitting_loss(body_pose, global_orient, loop1_pose, loop1_orient, betas, out.joints,
-                                            topo, self.euclthres, camera_translation, camera_center,
-                                            joints_2d, joints_conf, self.pose_prior,
-                                            cdict=contactlist, gt_contact=gt_contact, ignore_idxs=ignore_idxs,
-                                            has_discrete_contact=has_discrete_contact, verts=out.vertices,
-                                            face_tensor=self.face_tensor, focal_length=self.focal_length,
-                                            contact_loss_weight=contact_loss_weight, output=contact_loss_return,
-                                            segments=segments)
-                opt.zero_grad()
-                loss.backward()
-                opt.step()
+                fit.step()
+                optiverts.append(fit.vertices)
         else:
             body_pose.requires_grad_(True)
             betas.requires_grad_(True)
