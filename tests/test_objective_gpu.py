@@ -236,3 +236,40 @@ def test_smplify_dc_matches_reference_golden(ctx, tag, use_contact, eu):
                               kp2, has_gt_keypoints=t(np.array([True, False, False])))
     assert rel(fl, s[tag + '/get_fitting_loss']) < 1e-4
     assert np.array_equal(kp2.cpu().numpy(), s[tag + '/kp_after'])      # in-place side effect of the reference
+
+
+def test_contact_from_verts_mirror_matches_reference_golden(ctx):
+    from tuch_b200.train.train_module import contact_from_verts
+    c = golden('contact_from_verts.npz')
+    val = contact_from_verts(t(c['verts']), ctx['a']['regions'])
+    assert val.shape == c['value'].shape
+    assert np.abs(val.cpu().numpy() - c['value']).max() < 2e-6
+
+
+def test_eft_contact_loss_against_oracle(ctx):
+    """tuch/eft/loss.py:129-181 (means instead of sums, no euclthres gate, 100 * (c + 0.5 r2r))."""
+    from oracle import losses as ol, segments as oseg
+    from tuch_b200.eft.loss import contact_loss
+    a, g = ctx['a'], ctx['g']
+    verts_np = g['thres02_seg/verts']
+    geomask_np = a['geo'] > float(g['geothres'])
+    segs = oseg.build_segments(a['segs'], a['model']['faces'])
+    v64 = torch.tensor(verts_np, dtype=torch.float64, requires_grad=True)
+    total = v64.new_zeros(())
+    for b in range(3):
+        ext, am, mn, wn = ol.contact_query(v64[b].detach().float(), a['model']['faces'], geomask_np, segs,
+                                           always_segments=True)
+        d = torch.norm(v64[b] - v64[b][torch.as_tensor(am, dtype=torch.long)], dim=1)
+        e = torch.as_tensor(ext)
+        c = (torch.tanh(d[~e] / 0.04) ** 2).mean() if (~e).any() else 0.0
+        c = c + ((0.005 * torch.tanh(d[e] / 0.005) ** 2).mean() if e.any() else 0.0)
+        active = np.where(g['gt_contact'][b] == 1)[0]
+        r = ol.r2r_term(v64[b], geomask_np, a['regions'], active) if len(active) else 0.0
+        total = total + 100 * (c + 0.5 * r)
+    total.backward()
+    v = t(verts_np).requires_grad_(True)
+    face_tensor = ctx['faces'][None].repeat(3, 1, 1)
+    got = contact_loss(t(g['gt_contact']), v, ctx['geomask'], face_tensor, a['regions'], ctx['segments'])
+    got.backward()
+    assert abs(got.item() - total.item()) < 1e-4 * abs(total.item())
+    assert rel(v.grad, v64.grad.numpy()) < 2e-4
