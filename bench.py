@@ -221,7 +221,20 @@ def run_ours(args):
                     nearest_kernel_avg_ms=near_ms / max(near_n, 1), segment_winding_ms_per_step=seg_ms / args.steps,
                     note='fused kernel keeps the V x F solid-angle tensor on chip: it is bound by fp32 issue slots '
                          '(ncu: ~84% issue-active), not by HBM; see DESIGN.md and profiles/')
+    # the binding roof: warp-instruction issue slots (148 SMs x 4 schedulers x clock), at the issued
+    # instructions per (query, triangle) pair that ncu reports for this kernel build
+    ipp, sm_hz = None, (clocks or {}).get('sm_mhz') if clocks else None
     traffic_file = os.path.join(ROOT, 'profiles', 'winding_traffic.json')
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            ipp = json.load(f).get('warp_instr_per_32_pairs')
+    roofline_compute = None
+    if ipp and sm_hz and wind_n:
+        peak_pairs = 148 * 4 * sm_hz * 1e6 * 32.0 / ipp
+        roofline_compute = dict(bound='fp32-issue', kernel='winding_kernel', achieved=pairs / (wind_avg_ms * 1e-3),
+                                peak=peak_pairs, unit='pair-evals/s', frac=pairs / (wind_avg_ms * 1e-3) / peak_pairs,
+                                warp_instr_per_32_pairs=ipp, sm_mhz=sm_hz,
+                                note='peak = 148 SM x 4 issue slots x SM clock x 32 lanes / issued instr per pair (ncu)')
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             tf = json.load(f)
@@ -247,6 +260,8 @@ def run_ours(args):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              ms_per_step=e2e_ms),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline)
+        if roofline_compute is not None:
+            line['roofline_compute'] = roofline_compute
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
