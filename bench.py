@@ -345,6 +345,9 @@ def run_reference(args):
 
 
 def main():
+    if '--impl' in sys.argv and 'reference' in sys.argv:
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host core
+        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -77,6 +77,15 @@ typedef struct tuch_topology tuch_topology;
 int tuch_topology_create(int V, int F, const int32_t* faces_host, tuch_topology** out);
 void tuch_topology_destroy(tuch_topology* topo);
 int tuch_topology_num_verts(const tuch_topology* topo);
+/* The faces are cut once, on the host, into triangle strips laid out as a vertex stream in
+ * self-contained tiles of 256 elements (each element closes one triangle with its two predecessors;
+ * flag bit 0 = closes a face, bit 31 = corner order is an odd permutation of the face): the winding
+ * kernel then pays one new corner per triangle instead of three.  stats: stream length (elements per
+ * body, >= F) and number of strips.  tuch_strip_stream_host runs the same builder without a device
+ * (vid_out / flag_out may be NULL to query the length only). */
+int tuch_topology_strip_stats(const tuch_topology* topo, int* stream_len, int* n_strips);
+int tuch_strip_stream_host(const int32_t* faces_host, int F, int32_t* vid_out, uint32_t* flag_out, int capacity,
+                           int* stream_len, int* n_strips);
 int tuch_topology_num_faces(const tuch_topology* topo);
 
 /* geomask[r][c] = geodist[r][c] > geothres, from a DEVICE float [V,V] matrix ... */

@@ -1,7 +1,5 @@
-# One GPU-box visit: smoke, bench (ours + reference arm), ncu launch list of the bench command.
+# One GPU-box visit: tests, smoke, bench (ours + reference arm).  Usage: bash scripts/gpu_round.sh [tests|notests]
 set -x
+if [ "${1:-tests}" = "tests" ]; then python -m pytest tests -m gpu -x -q 2>&1 | tail -15; fi
 python __graft_entry__.py smoke 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -3 gpurun_out/ncu_bench.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3500 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err

@@ -1,6 +1,8 @@
 // C ABI (include/tuch_b200.h): status, scratch arenas, mesh topology and the contact entry points.
 #include "api_internal.h"
+#include "strips.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -251,6 +253,15 @@ TUCH_EXPORT int tuch_topology_create(int V, int F, const int32_t* faces_host, tu
     t->V = V; t->F = F;
     t->Fp = padded_faces(F); t->Vp = padded_verts(V); t->Vq = padded_verts(V); t->W = cdiv(V, 32);
     if (int rc = upload(faces_host, (size_t)F * 3, &t->d_faces)) { delete t; return rc; }
+    if (F > 0) {
+        std::vector<int> vid;
+        std::vector<uint32_t> flag;
+        int rc = build_strip_stream(faces_host, F, WS_TILE, vid, flag, &t->n_strips);
+        if (!rc) rc = upload(vid.data(), vid.size(), &t->d_strip_vid);
+        if (!rc) rc = upload(flag.data(), flag.size(), &t->d_strip_flag);
+        if (rc) { tuch_topology_destroy(t); return rc; }
+        t->Lp = (int)vid.size();
+    }
     *out = t;
     return 0;
 }
@@ -270,11 +281,33 @@ static void free_segments(tuch_topology* t) {
 
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
-    free_dev(t->d_faces); free_dev(t->d_maskT);
+    free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_flag);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
 }
+TUCH_EXPORT int tuch_topology_strip_stats(const tuch_topology* t, int* stream_len, int* n_strips) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_strip_stats: null topology");
+    if (stream_len) *stream_len = t->Lp;
+    if (n_strips) *n_strips = t->n_strips;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_strip_stream_host(const int32_t* faces_host, int F, int32_t* vid_out, uint32_t* flag_out,
+                                       int capacity, int* stream_len, int* n_strips) {
+    TUCH_REQUIRE(faces_host != nullptr && F > 0, "tuch_strip_stream_host: need faces");
+    std::vector<int> vid;
+    std::vector<uint32_t> flag;
+    if (int rc = build_strip_stream(faces_host, F, WS_TILE, vid, flag, n_strips)) return rc;
+    if (stream_len) *stream_len = (int)vid.size();
+    if (vid_out != nullptr && flag_out != nullptr) {
+        TUCH_REQUIRE(capacity >= (int)vid.size(), "tuch_strip_stream_host: capacity %d < stream length %zu", capacity, vid.size());
+        std::copy(vid.begin(), vid.end(), vid_out);
+        std::copy(flag.begin(), flag.end(), flag_out);
+    }
+    return 0;
+}
+
 TUCH_EXPORT int tuch_topology_num_verts(const tuch_topology* t) { return t ? t->V : -1; }
 TUCH_EXPORT int tuch_topology_num_faces(const tuch_topology* t) { return t ? t->F : -1; }
 TUCH_EXPORT int tuch_topology_total_segment_verts(const tuch_topology* t) { return t ? t->n_sv : -1; }
@@ -427,11 +460,11 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                  "(call tuch_topology_set_geodist / tuch_topology_set_geomask)");
     TUCH_REQUIRE(!want_w || t->F > 0, "tuch_contact_query: winding requested on a topology without faces");
     const bool segs = exterior != nullptr && use_segments && t->n_segments > 0;
-    const int V = t->V, Fp = t->Fp, Vp = t->Vp;
-    const int S = want_w ? winding_splits(B, V, Fp, sm_count()) : 1;
+    const int V = t->V, Fp = t->Fp, Vp = t->Vp, Lp = t->Lp;
+    const int S = want_w ? strip_splits(B, V, Lp, sm_count()) : 1;
 
     Scratch sc;
-    const size_t h_tri = sc.plan(want_w ? sizeof(float4) * 3 * (size_t)B * Fp : 0);
+    const size_t h_tri = sc.plan(want_w ? sizeof(float4) * (size_t)B * Lp : 0);
     const size_t h_v4 = sc.plan((want_nn && !vert4_out) ? sizeof(float4) * (size_t)B * Vp : 0);
     const size_t h_par = sc.plan(want_w ? sizeof(float) * (size_t)B * S * V : 0);
     const size_t h_w = sc.plan((want_w && !winding) ? sizeof(float) * (size_t)B * V : 0);
@@ -442,15 +475,16 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     if (segs) plan_segments(t, B, sc, sp);
     if (int rc = sc.commit(st)) return rc;
 
-    float4* tri12 = want_w ? sc.get<float4>(h_tri) : nullptr;
+    float4* strip4 = want_w ? sc.get<float4>(h_tri) : nullptr;
     float4* vert4 = want_nn ? (vert4_out ? vert4_out : sc.get<float4>(h_v4)) : vert4_out;
-    if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, tri12, vert4, st)) return rc;
+    if (vert4 != nullptr)
+        if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, nullptr, vert4, st)) return rc;
 
     if (want_w) {
         float* w = winding ? winding : sc.get<float>(h_w);
-        WindingJob j{tri12, (long long)Fp * 3, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V,
-                     nullptr, B, V, Fp, S};
-        if (int rc = launch_winding(j, st)) return rc;
+        if (int rc = launch_pack_strips(verts, B, V, t->d_strip_vid, t->d_strip_flag, Lp, strip4, st)) return rc;
+        StripJob j{strip4, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V, nullptr, B, V, Lp, S};
+        if (int rc = launch_winding_strips(j, st)) return rc;
         if (exterior) {
             uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;
             if (any) TUCH_CUDA(cudaMemsetAsync(any, 0, (size_t)B, st));

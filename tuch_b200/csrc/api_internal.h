@@ -9,6 +9,10 @@ struct tuch_topology {
     int device = 0;
     int V = 0, F = 0, Fp = 0, Vp = 0, Vq = 0, W = 0;
     int* d_faces = nullptr;            // [F][3]
+    // triangle-strip stream of the faces (strips.cu): vertex id / flag per element, Lp elements
+    int Lp = 0, n_strips = 0;
+    int* d_strip_vid = nullptr;
+    uint32_t* d_strip_flag = nullptr;
     uint32_t* d_maskT = nullptr;       // [W][Vq] bit-packed geodesic mask
     bool has_mask = false;
     // DSC regions (CSR) and annotated pairs

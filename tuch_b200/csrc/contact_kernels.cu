@@ -437,9 +437,14 @@ int launch_winding(const WindingJob& j, cudaStream_t st) {
                                                     j.point_stride, (long long)j.S * j.Q, j.body_active, j.q_counts);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
-    dim3 g2(cdiv(j.Q, 256), j.B);
-    winding_finalize_kernel<<<g2, 256, 0, st>>>(j.partial, j.Q, j.S, (long long)j.S * j.Q, j.out_stride,
-                                                j.winding, j.body_active, j.q_counts);
+    return launch_winding_finalize(j.partial, j.B, j.Q, j.S, j.out_stride, j.winding, j.body_active, j.q_counts, st);
+}
+
+int launch_winding_finalize(const float* partial, int B, int Q, int S, long long out_stride, float* winding,
+                            const uint8_t* body_active, const int* q_counts, cudaStream_t st) {
+    dim3 g2(cdiv(Q, 256), B);
+    winding_finalize_kernel<<<g2, 256, 0, st>>>(partial, Q, S, (long long)S * Q, out_stride, winding, body_active,
+                                                q_counts);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

@@ -1,6 +1,7 @@
 // C ABI of the regressor contact loss (include/tuch_b200.h, section a12): tuch/train/loss.py:240-317.
 #include "hd_internal.h"
 #include "objective_internal.h"
+#include "strips.h"
 
 using namespace tuch;
 
@@ -61,9 +62,9 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     const size_t h_off = sc.plan(sizeof(float) * 3 * BN), h_px = sc.plan(sizeof(int) * BN);
     const size_t h_ham = sc.plan(sizeof(int) * BN), h_hw = sc.plan(sizeof(float) * BN), h_hex = sc.plan(BN);
     const size_t h_ghd = sc.plan(sizeof(float) * 3 * BN);
-    const int Fp = t->Fp;
-    const int S = use_hd ? winding_splits(B, N, Fp, sm_count()) : 1;
-    const size_t h_tri = sc.plan(use_hd ? sizeof(float4) * 3 * (size_t)B * Fp : 0);
+    const int Lp = t->Lp;
+    const int S = use_hd ? strip_splits(B, N, Lp, sm_count()) : 1;
+    const size_t h_tri = sc.plan(use_hd ? sizeof(float4) * (size_t)B * Lp : 0);
     const size_t h_par = sc.plan(use_hd ? sizeof(float) * (size_t)B * S * N : 0);
     if (int rc = sc.commit_slot(st, 1)) return rc;
     int* am = sc.get<int>(h_am);
@@ -91,11 +92,11 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
                                   t->d_faces, hd4, hd, off, proxy, st)) return rc;
     if (int rc = launch_hd_nearest(hd4, proxy, cnt, B, N, t->d_maskT, t->Vq, ham, st)) return rc;
     // loss.py:297 -- inside test of the offset HD points against the full mesh
-    float4* tri12 = sc.get<float4>(h_tri);
-    if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, t->Vp, tri12, nullptr, st)) return rc;
-    WindingJob j{tri12, (long long)Fp * 3, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Fp, S};
+    float4* strip4 = sc.get<float4>(h_tri);
+    if (int rc = launch_pack_strips(verts, B, V, t->d_strip_vid, t->d_strip_flag, Lp, strip4, st)) return rc;
+    StripJob j{strip4, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Lp, S};
     j.q_counts = cnt;
-    if (int rc = launch_winding(j, st)) return rc;
+    if (int rc = launch_winding_strips(j, st)) return rc;
     if (int rc = launch_exterior_init(hw, B, N, hex, nullptr, st)) return rc;
     // loss.py:299-315
     float* g_hd = nullptr;

@@ -33,6 +33,8 @@ struct WindingJob {
     const int* q_counts = nullptr;                 // optional [B]: only the first q_counts[b] queries are valid
 };
 int launch_winding(const WindingJob& job, cudaStream_t st);
+int launch_winding_finalize(const float* partial, int B, int Q, int S, long long out_stride, float* winding,
+                            const uint8_t* body_active, const int* q_counts, cudaStream_t st);
 int launch_nearest(const float4* vert4, const uint32_t* maskT, int B, int V, int Vp, int Vq,
                    int* argmin, float* minval, cudaStream_t st);
 int launch_pack_mask(const uint8_t* mask, const float* dist, float thres, int V, int Vq, int W,

@@ -66,6 +66,19 @@ def kernel_time(name):
     return ms.value, n.value
 
 
+def strip_stream(faces):
+    """Host-only: the triangle-strip vertex stream the library builds for a face list ->
+    (vid int32 [L], flag uint32 [L], n_strips).  See tuch_strip_stream_host."""
+    f = _i32_host(np.asarray(faces).reshape(-1, 3))
+    L, n = C.c_int(), C.c_int()
+    check(lib().tuch_strip_stream_host(_hp(f), len(f), None, None, 0, C.byref(L), C.byref(n)), 'tuch_strip_stream_host')
+    vid = np.empty(L.value, np.int32)
+    flag = np.empty(L.value, np.uint32)
+    check(lib().tuch_strip_stream_host(_hp(f), len(f), _hp(vid), _hp(flag), L.value, C.byref(L), C.byref(n)),
+          'tuch_strip_stream_host')
+    return vid, flag, n.value
+
+
 # ------------------------------------------------------------------ a1-a3 forward kernels
 def pairwise_dist(x, y, squared=True):
     x, y = _f32(x, 'x'), _f32(y, 'y')
