@@ -254,11 +254,11 @@ TUCH_EXPORT int tuch_topology_create(int V, int F, const int32_t* faces_host, tu
     t->Fp = padded_faces(F); t->Vp = padded_verts(V); t->Vq = padded_verts(V); t->W = cdiv(V, 32);
     if (int rc = upload(faces_host, (size_t)F * 3, &t->d_faces)) { delete t; return rc; }
     if (F > 0) {
-        std::vector<int> vid;
+        std::vector<int> vid, fid;
         std::vector<uint32_t> flag;
-        int rc = build_strip_stream(faces_host, F, WS_TILE, vid, flag, &t->n_strips);
+        int rc = build_strip_stream(faces_host, F, WS_TILE, vid, flag, fid, &t->n_strips);
         if (!rc) rc = upload(vid.data(), vid.size(), &t->d_strip_vid);
-        if (!rc) rc = upload(flag.data(), flag.size(), &t->d_strip_flag);
+        if (!rc) rc = upload(fid.data(), fid.size(), &t->d_strip_fid);
         if (rc) { tuch_topology_destroy(t); return rc; }
         t->Lp = (int)vid.size();
     }
@@ -281,7 +281,7 @@ static void free_segments(tuch_topology* t) {
 
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
-    free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_flag);
+    free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -296,9 +296,9 @@ TUCH_EXPORT int tuch_topology_strip_stats(const tuch_topology* t, int* stream_le
 TUCH_EXPORT int tuch_strip_stream_host(const int32_t* faces_host, int F, int32_t* vid_out, uint32_t* flag_out,
                                        int capacity, int* stream_len, int* n_strips) {
     TUCH_REQUIRE(faces_host != nullptr && F > 0, "tuch_strip_stream_host: need faces");
-    std::vector<int> vid;
+    std::vector<int> vid, fid;
     std::vector<uint32_t> flag;
-    if (int rc = build_strip_stream(faces_host, F, WS_TILE, vid, flag, n_strips)) return rc;
+    if (int rc = build_strip_stream(faces_host, F, WS_TILE, vid, flag, fid, n_strips)) return rc;
     if (stream_len) *stream_len = (int)vid.size();
     if (vid_out != nullptr && flag_out != nullptr) {
         TUCH_REQUIRE(capacity >= (int)vid.size(), "tuch_strip_stream_host: capacity %d < stream length %zu", capacity, vid.size());
@@ -464,7 +464,8 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     const int S = want_w ? strip_splits(B, V, Lp, sm_count()) : 1;
 
     Scratch sc;
-    const size_t h_tri = sc.plan(want_w ? sizeof(float4) * (size_t)B * Lp : 0);
+    const size_t h_tri = sc.plan(want_w ? sizeof(float4) * 2 * (size_t)B * Lp : 0);
+    const size_t h_info = sc.plan(want_w ? sizeof(float4) * (size_t)B * (Lp / WS_TILE) : 0);
     const size_t h_v4 = sc.plan((want_nn && !vert4_out) ? sizeof(float4) * (size_t)B * Vp : 0);
     const size_t h_par = sc.plan(want_w ? sizeof(float) * (size_t)B * S * V : 0);
     const size_t h_w = sc.plan((want_w && !winding) ? sizeof(float) * (size_t)B * V : 0);
@@ -482,8 +483,9 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
 
     if (want_w) {
         float* w = winding ? winding : sc.get<float>(h_w);
-        if (int rc = launch_pack_strips(verts, B, V, t->d_strip_vid, t->d_strip_flag, Lp, strip4, st)) return rc;
-        StripJob j{strip4, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V, nullptr, B, V, Lp, S};
+        float4* info = sc.get<float4>(h_info);
+        if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
+        StripJob j{strip4, info, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V, nullptr, B, V, Lp, S};
         if (int rc = launch_winding_strips(j, st)) return rc;
         if (exterior) {
             uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;

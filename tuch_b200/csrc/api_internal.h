@@ -11,8 +11,7 @@ struct tuch_topology {
     int* d_faces = nullptr;            // [F][3]
     // triangle-strip stream of the faces (strips.cu): vertex id / flag per element, Lp elements
     int Lp = 0, n_strips = 0;
-    int* d_strip_vid = nullptr;
-    uint32_t* d_strip_flag = nullptr;
+    int *d_strip_vid = nullptr, *d_strip_fid = nullptr;
     uint32_t* d_maskT = nullptr;       // [W][Vq] bit-packed geodesic mask
     bool has_mask = false;
     // DSC regions (CSR) and annotated pairs

@@ -64,7 +64,8 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     const size_t h_ghd = sc.plan(sizeof(float) * 3 * BN);
     const int Lp = t->Lp;
     const int S = use_hd ? strip_splits(B, N, Lp, sm_count()) : 1;
-    const size_t h_tri = sc.plan(use_hd ? sizeof(float4) * (size_t)B * Lp : 0);
+    const size_t h_tri = sc.plan(use_hd ? sizeof(float4) * 2 * (size_t)B * Lp : 0);
+    const size_t h_info = sc.plan(use_hd ? sizeof(float4) * (size_t)B * (Lp / WS_TILE) : 0);
     const size_t h_par = sc.plan(use_hd ? sizeof(float) * (size_t)B * S * N : 0);
     if (int rc = sc.commit_slot(st, 1)) return rc;
     int* am = sc.get<int>(h_am);
@@ -93,8 +94,9 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     if (int rc = launch_hd_nearest(hd4, proxy, cnt, B, N, t->d_maskT, t->Vq, ham, st)) return rc;
     // loss.py:297 -- inside test of the offset HD points against the full mesh
     float4* strip4 = sc.get<float4>(h_tri);
-    if (int rc = launch_pack_strips(verts, B, V, t->d_strip_vid, t->d_strip_flag, Lp, strip4, st)) return rc;
-    StripJob j{strip4, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Lp, S};
+    float4* info = sc.get<float4>(h_info);
+    if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
+    StripJob j{strip4, info, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Lp, S};
     j.q_counts = cnt;
     if (int rc = launch_winding_strips(j, st)) return rc;
     if (int rc = launch_exterior_init(hw, B, N, hex, nullptr, st)) return rc;
