@@ -42,7 +42,7 @@ def peaks():
 
 def make_assets(batch, seed):
     from tuch_b200 import synthetic as syn
-    model = syn.make_body_model(84, 82, seed=0)                                   # V = 6890, F = 13776
+    model = syn.make_lattice_body_model(seed=0)                                   # V = 6890, F = 13776
     geo = syn.make_geodesics(model['v_template'], model['faces'],
                              cache_dir=os.environ.get('TUCH_B200_CACHE', '/tmp/tuch_b200_cache'))
     regions = syn.make_regions(model)

@@ -7,7 +7,7 @@ from tuch_b200 import ops, synthetic as syn
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = torch.device('cuda:0')
 print(ops.device_info())
-m = syn.make_body_model()
+m = syn.make_lattice_body_model() if os.environ.get('BODY', 'lattice') == 'lattice' else syn.make_body_model()
 V = len(m['v_template'])
 topo = ops.Topology(m['faces'], V, dev)
 t0 = time.time()

@@ -37,13 +37,23 @@ def small_assets():
     return dict(model=model, geo=geo, regions=regions, segs=segs, hd_reg=hd_reg, hd_fidx=hd_fidx, gmm=gmm)
 
 
+def _full(model):
+    from tuch_b200 import synthetic as syn
+    geo = syn.make_geodesics(model['v_template'], model['faces'], cache_dir=CACHE)
+    return dict(model=model, geo=geo, regions=syn.make_regions(model), segs=syn.make_segments(model), gmm=syn.make_gmm())
+
+
 @pytest.fixture(scope='session')
 def full_assets():
-    """SMPL-sized synthetic assets (V=6890, F=13776); the geodesic matrix is cached under CACHE."""
+    """SMPL-sized synthetic assets (V=6890, F=13776) with SMPL-like triangle statistics (lattice body);
+    the geodesic matrix is cached under CACHE."""
     from tuch_b200 import synthetic as syn
-    model = syn.make_body_model(84, 82, seed=0)
-    geo = syn.make_geodesics(model['v_template'], model['faces'], cache_dir=CACHE)
-    regions = syn.make_regions(model)
-    segs = syn.make_segments(model)
-    gmm = syn.make_gmm()
-    return dict(model=model, geo=geo, regions=regions, segs=segs, gmm=gmm)
+    return _full(syn.make_lattice_body_model(seed=0))
+
+
+@pytest.fixture(scope='session')
+def full_assets_uv():
+    """Same counts on the UV 'starfish' tessellation (long sliver triangles): the stress case for
+    anything that clusters or bounds triangles spatially."""
+    from tuch_b200 import synthetic as syn
+    return _full(syn.make_body_model(84, 82, seed=0))

@@ -154,10 +154,16 @@ def make_body_model(rings: int = 84, segs: int = 82, seed: int = 0, num_betas: i
     """
     rng = np.random.default_rng(seed)
     dirs, faces = _uv_sphere(rings, segs)
-    V = len(dirs)
     v = dirs * _radius(dirs)[:, None]
     v = v.astype(np.float32).astype(np.float64)
-    Jt = _joint_template()
+    out = _dress_mesh(v, faces, _joint_template(), rng, num_betas)
+    out.update(rings=np.int64(rings), segs=np.int64(segs))
+    return out
+
+
+def _dress_mesh(v, faces, Jt, rng, num_betas):
+    """SMPL-shaped tensors (skinning weights, regressors, blend-shape bases) for a template mesh."""
+    V = len(v)
 
     # skinning weights: soft assignment to bones (joint -> first child, or the joint itself)
     child = {}
@@ -222,8 +228,136 @@ def make_body_model(rings: int = 84, segs: int = 82, seed: int = 0, num_betas: i
         J_regressor_extra=Jextra.astype(np.float32),
         extra_vertex_ids=extra_vertex_ids,
         joint_map=joint_map_indices(),
-        rings=np.int64(rings), segs=np.int64(segs),
     )
+
+
+# ----------------------------------------------------------------------------------
+# lattice body: SMPL-like tessellation statistics (near-uniform, near-isotropic triangles)
+# ----------------------------------------------------------------------------------
+# The UV "starfish" above has the SMPL vertex/face counts but not SMPL's triangle statistics: its limbs
+# are covered by a few long slivers.  Kernels whose cost depends on the spatial extent of triangle
+# clusters (far-field winding numbers, bounding-box pruning) need a body whose triangles look like
+# SMPL's.  This one is the boundary surface of a humanoid built from boxes on an integer lattice --
+# 6,888 unit quads = exactly V = 6,890 / F = 13,776 -- rounded by Taubin smoothing.
+_LATTICE_BOXES = dict(              # half-open lattice ranges (x0, x1, y0, y1, z0, z1); +x = left, +y = up
+    torso=(-9, 9, 0, 34, -5, 6), neck=(-3, 3, 34, 36, -3, 3), head=(-5, 5, 36, 48, -5, 6),
+    larm=(9, 43, 28, 33, -2, 3), rarm=(-43, -9, 28, 33, -2, 3),
+    lleg=(1, 9, -41, 0, -3, 4), rleg=(-9, -1, -41, 0, -3, 4))
+_LATTICE_PITCH = 0.019              # metres per lattice step: 1.69 m tall, 1.63 m arm span
+_LATTICE_WRIST, _LATTICE_SHOULDER = 30, 14     # |x| of the arm segment planes
+
+
+def _lattice_surface():
+    """Lattice corner coordinates [V,3] (int) and outward-oriented quads [Q,4] of the box union."""
+    bx = list(_LATTICE_BOXES.values())
+    lo = np.array([min(b[0] for b in bx), min(b[2] for b in bx), min(b[4] for b in bx)]) - 1
+    hi = np.array([max(b[1] for b in bx), max(b[3] for b in bx), max(b[5] for b in bx)]) + 1
+    occ = np.zeros(hi - lo, bool)
+    for (x0, x1, y0, y1, z0, z1) in bx:
+        occ[x0 - lo[0]:x1 - lo[0], y0 - lo[1]:y1 - lo[1], z0 - lo[2]:z1 - lo[2]] = True
+    vid, verts, quads = {}, [], []
+
+    def v(p):
+        p = (int(p[0]), int(p[1]), int(p[2]))
+        if p not in vid:
+            vid[p] = len(verts)
+            verts.append(p)
+        return vid[p]
+    for idx in np.argwhere(occ):
+        for a in range(3):
+            for sgn in (-1, 1):
+                n = idx.copy()
+                n[a] += sgn
+                if occ[tuple(n)]:
+                    continue
+                o = idx + lo
+                o[a] += 1 if sgn > 0 else 0
+                e1 = np.zeros(3, int); e1[(a + 1) % 3] = 1
+                e2 = np.zeros(3, int); e2[(a + 2) % 3] = 1          # e1 x e2 = +axis a
+                c = [o, o + e1, o + e1 + e2, o + e2] if sgn > 0 else [o, o + e2, o + e1 + e2, o + e1]
+                quads.append([v(q) for q in c])
+    return np.asarray(verts, np.int64), np.asarray(quads, np.int64)
+
+
+def _lattice_joints():
+    P = _LATTICE_PITCH
+    arm_y, mid_z = 30.5, 0.5
+    J = np.zeros((24, 3))
+    J[0] = (0, 2, mid_z)
+    J[1], J[2] = (5, -2, mid_z), (-5, -2, mid_z)
+    J[3] = (0, 9, mid_z)
+    J[4], J[5] = (5, -21, mid_z), (-5, -21, mid_z)
+    J[6] = (0, 16, mid_z)
+    J[7], J[8] = (5, -37, mid_z), (-5, -37, mid_z)
+    J[9] = (0, 23, mid_z)
+    J[10], J[11] = (5, -40, 2.5), (-5, -40, 2.5)
+    J[12] = (0, 34, mid_z)
+    J[13], J[14] = (4, arm_y, mid_z), (-4, arm_y, mid_z)
+    J[15] = (0, 40, mid_z)
+    J[16], J[17] = (10, arm_y, mid_z), (-10, arm_y, mid_z)
+    J[18], J[19] = (25, arm_y, mid_z), (-25, arm_y, mid_z)
+    J[20], J[21] = (38, arm_y, mid_z), (-38, arm_y, mid_z)
+    J[22], J[23] = (41.5, arm_y, mid_z), (-41.5, arm_y, mid_z)
+    return J * P
+
+
+def make_lattice_body_model(seed: int = 0, num_betas: int = 10, smooth_iters: int = 12):
+    """SMPL-sized synthetic body (V=6890, F=13776) with SMPL-like triangle statistics; same keys as
+    make_body_model plus lattice_xyz[V,3] (integer lattice coordinates, used by make_segments).
+    Vertex ids are a seeded random permutation, so nothing can lean on index locality."""
+    rng = np.random.default_rng(seed)
+    lat, quads = _lattice_surface()
+    V = len(lat)
+    perm = rng.permutation(V)                        # new id of lattice vertex i
+    inv = np.argsort(perm)
+    lat = lat[inv]
+    quads = perm[quads]
+    # alternate the quad diagonal with lattice parity (no preferred direction)
+    par = (lat[quads[:, 0]].sum(1) % 2) == 0
+    f_a = np.concatenate([quads[par][:, [0, 1, 2]], quads[par][:, [0, 2, 3]]], 0)
+    f_b = np.concatenate([quads[~par][:, [0, 1, 3]], quads[~par][:, [1, 2, 3]]], 0)
+    faces = np.concatenate([f_a, f_b], 0)
+    faces = faces[np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))]
+    # Taubin smoothing over the quad edges rounds the boxes without shrinking the limbs
+    e = np.concatenate([quads[:, [0, 1]], quads[:, [1, 2]], quads[:, [2, 3]], quads[:, [3, 0]]], 0)
+    e = np.unique(np.sort(e, axis=1), axis=0)
+    deg = np.bincount(e.ravel(), minlength=V).astype(np.float64)
+    v = lat.astype(np.float64) * _LATTICE_PITCH
+
+    def lap(x):
+        acc = np.zeros_like(x)
+        for ax in range(3):
+            acc[:, ax] = np.bincount(e[:, 0], x[e[:, 1], ax], V) + np.bincount(e[:, 1], x[e[:, 0], ax], V)
+        return acc / deg[:, None] - x
+    for _ in range(smooth_iters):
+        v = v + 0.5 * lap(v)
+        v = v - 0.53 * lap(v)
+    v = v.astype(np.float32).astype(np.float64)
+    out = _dress_mesh(v, faces, _lattice_joints(), rng, num_betas)
+    out['lattice_xyz'] = lat
+    return out
+
+
+def _lattice_segments(lat):
+    """Arm segments of the lattice body, bounded by the lattice planes |x| = wrist / shoulder."""
+    def ring(x):
+        ids = np.where((lat[:, 0] == x) & (lat[:, 1] >= 28) & (lat[:, 1] <= 33) & (lat[:, 2] >= -2) & (lat[:, 2] <= 3))[0]
+        ang = np.arctan2(lat[ids, 2] - 0.5, lat[ids, 1] - 30.5)
+        r = [int(i) for i in ids[np.argsort(ang)]]                 # counter-clockwise seen from +x
+        return r + [r[0]]
+
+    def arm(lo, hi):
+        return [int(i) for i in np.where((lat[:, 0] >= lo) & (lat[:, 0] <= hi) & (lat[:, 1] >= 28) & (lat[:, 1] <= 33)
+                                         & (lat[:, 2] >= -2) & (lat[:, 2] <= 3))[0]]
+    w, sh, tip = _LATTICE_WRIST, _LATTICE_SHOULDER, 43
+    # cap fans are [l[i+1], l[i], c] (segmentation.py:56-66): a loop that is counter-clockwise seen
+    # from +x gives a cap facing -x
+    return {
+        'left_hand_arm': {'vidx': arm(w, tip), 'bands': {'wrist': ring(w)}},
+        'left_upper_arm': {'vidx': arm(sh, w), 'bands': {'elbow': ring(w)[::-1], 'shoulder': ring(sh)}},
+        'right_hand_arm': {'vidx': arm(-tip, -w), 'bands': {'wrist': ring(-w)[::-1]}},
+        'right_upper_arm': {'vidx': arm(-w, -sh), 'bands': {'elbow': ring(-w), 'shoulder': ring(-sh)[::-1]}},
+    }
 
 
 # ----------------------------------------------------------------------------------
@@ -293,6 +427,11 @@ def make_segments(model):
     The mesh's pole axis is the arm axis, so ring ranges are arm segments; loops are ordered
     so that the cap fan [loop[i+1], loop[i], centroid] (segmentation.py:56-66) faces outward.
     """
+    if 'lattice_xyz' in model:
+        out = _lattice_segments(np.asarray(model['lattice_xyz']))
+        for s in out.values():
+            s['vidx'] = sorted(s['vidx'])
+        return out
     rings, segs = int(model['rings']), int(model['segs'])
     V = rings * segs + 2
     ring = lambda i: [1 + i * segs + j for j in range(segs)]
