@@ -109,9 +109,33 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
                                const int32_t* band_offsets_host, const int32_t* loop_offsets_host,
                                const int32_t* loop_ids_host);
 
+/* Winding-number evaluation inside tuch_contact_query.  Callers of the reference only consume the
+ * flag `winding_numbers(...) <= 0.99` (losses.py:82, loss.py:262), so the default mode evaluates the
+ * sum hierarchically: the faces are clustered once per topology (leaves of <= 32 faces, super-clusters
+ * of <= 8 leaves); per body, clusters farther than 2 radii from a query contribute through a
+ * second-order multipole expansion of the solid-angle integrand (max abs error measured 3.8e-3 on the winding
+ * number), nearer leaves are summed exactly, and every query whose value falls within 0.03 of the 0.99
+ * threshold is re-evaluated exactly over all faces -- the exterior flags are those of the exact sum.
+ * TUCH_WINDING_EXACT sums all F solid angles for every query (values within 2e-5 of the reference).
+ * The hierarchy is built from the template given to tuch_topology_set_template (HOST [V,3]) or, when
+ * none was given, from the first body a query sees (one blocking device->host copy, outside graph
+ * capture only). */
+#define TUCH_WINDING_EXACT 0
+#define TUCH_WINDING_FAST 1
+int tuch_topology_set_template(tuch_topology* topo, const float* verts_host);
+int tuch_topology_set_winding_mode(tuch_topology* topo, int mode);
+int tuch_topology_cluster_stats(const tuch_topology* topo, int* n_leaves, int* n_supers);
+/* the hierarchy builder without a device: leaf_face_out[n_leaves][32] (face id or -1),
+ * super_off_out[n_supers + 1] (leaf ranges), qperm_out[V] (vertex ids in cluster order); output
+ * pointers may be NULL to query the counts only. */
+int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float* verts_host,
+                           int32_t* leaf_face_out, int leaf_capacity, int32_t* super_off_out,
+                           int super_capacity, int32_t* qperm_out, int* n_leaves, int* n_supers);
+
 /* ------------------------------------------------------------------ fused self-contact query
  * Replaces, for every body of the batch, losses.py:76-93 / loss.py:256-270:
- *   winding[b,v]  = winding_numbers(verts[b], verts[b][faces])           (contact.py:112)
+ *   winding[b,v]  = winding_numbers(verts[b], verts[b][faces])           (contact.py:112; see the
+ *                   winding mode above: approximate away from the threshold in TUCH_WINDING_FAST)
  *   exterior[b,v] = winding <= 0.99, then set to 1 where v is inside its own closed segment
  *                   (losses.py:82-89; segment pass only if use_segments != 0; when
  *                   segments_only_if_interior != 0 a body without interior vertices skips it,

@@ -26,7 +26,30 @@ def timeit(fn, n=5):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
 
+# posed bodies with self-penetration (LBS of the CPU oracle), tiled to the batch
+from oracle import lbs as olbs
+tm = olbs.to_torch_model(m)
+nb = min(B, 16)
+pose = torch.tensor(syn.fold_arms_pose(nb, seed=7))
+betas = torch.tensor(np.random.default_rng(7).normal(0, 0.5, size=(nb, 10)).astype(np.float32))
+pv = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev)
+verts = pv.repeat((B + nb - 1) // nb, 1, 1)[:B].contiguous()
+topo.set_template(m['v_template'])
+print('clusters', topo.cluster_stats())
+ops.kernel_timing(enable=True, reset=True)
+topo.set_winding_mode(topo.WINDING_EXACT)
 tw = timeit(lambda: topo.contact_query(verts, use_segments=False, want_nearest=False))
+w_exact = topo.contact_query(verts, use_segments=False, want_nearest=False)
+topo.set_winding_mode(topo.WINDING_FAST)
+tf = timeit(lambda: topo.contact_query(verts, use_segments=False, want_nearest=False))
+w_fast = topo.contact_query(verts, use_segments=False, want_nearest=False)
+err = (w_exact['winding'] - w_fast['winding']).abs()
+away = (w_exact['winding'] - 0.99).abs() > 1e-4
+print('fast winding %.3f ms (exact %.3f ms): max err %.2e, flag mismatches %d, interior %d, near-threshold %d' % (
+    tf, tw, float(err.max()), int((w_exact['exterior'] != w_fast['exterior'])[away].sum()), int((~w_exact['exterior']).sum()),
+    int(((w_fast['winding'] - 0.99).abs() < 0.02).sum())))
+for k in ('winding_kernel', 'winding_refine_kernel', 'nearest_kernel'):
+    print(' ', k, ops.kernel_time(k))
 tn = timeit(lambda: topo.contact_query(verts, use_segments=False, want_winding=False))
 pairs = B * V * 13776
 print('B=%d winding %.3f ms (%.1f Gpairs/s)  nearest %.3f ms (%.1f Gpairs/s)' % (B, tw, pairs / tw / 1e6, tn, B * V * V / tn / 1e6))

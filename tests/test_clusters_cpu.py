@@ -1,0 +1,92 @@
+"""Host-only checks of the face-cluster hierarchy behind the hierarchical winding kernel
+(tuch_b200/csrc/clusters.cu), and of the far-field expansion it evaluates, restated in numpy and held
+against the oracle's exact solid angles."""
+import numpy as np
+
+
+def tree_for(model):
+    from tuch_b200 import ops
+    return ops.cluster_tree(model['faces'], model['v_template'])
+
+
+def check_tree(model):
+    faces = model['faces']
+    F, V = len(faces), len(model['v_template'])
+    t = tree_for(model)
+    leaf, sup, qp = t['leaf_face'], t['super_off'], t['qperm']
+    ids = leaf[leaf >= 0]
+    assert len(ids) == F and np.array_equal(np.sort(ids), np.arange(F))            # a partition of the faces
+    assert np.array_equal(np.sort(qp), np.arange(V))                               # a permutation of the vertices
+    assert sup[0] == 0 and sup[-1] == len(leaf) and np.all(np.diff(sup) >= 1) and np.all(np.diff(sup) <= 24)
+    for row in leaf:                                                               # padding only at the end
+        n = int((row >= 0).sum())
+        assert n >= 1 and np.all(row[:n] >= 0) and np.all(row[n:] < 0)
+    return t
+
+
+def test_tree_small_and_full():
+    from tuch_b200 import synthetic as syn
+    check_tree(syn.make_body_model(10, 12, seed=0))
+    t = check_tree(syn.make_lattice_body_model(seed=0))
+    # near-minimal leaf count: the far field costs one evaluation per leaf
+    assert len(t['leaf_face']) <= 1.15 * (13776 // 32 + 1)
+    check_tree(syn.make_body_model(84, 82, seed=0))
+
+
+def test_tree_disconnected_and_tiny():
+    from tuch_b200 import ops
+    # two separate tetrahedra and a lone triangle
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    verts = np.concatenate([v, v + 5, v[:3] + 9])
+    tet = np.array([[0, 2, 1], [0, 1, 3], [1, 2, 3], [0, 3, 2]])
+    faces = np.concatenate([tet, tet + 4, [[8, 9, 10]]])
+    t = ops.cluster_tree(faces, verts)
+    assert sorted(t['leaf_face'][t['leaf_face'] >= 0].tolist()) == list(range(9))
+    comps = [set(r[r >= 0].tolist()) for r in t['leaf_face']]
+    assert {0, 1, 2, 3} in comps and {4, 5, 6, 7} in comps and {8} in comps        # components are never mixed
+
+
+def test_far_field_expansion_matches_exact_solid_angles():
+    """The node record of cluster_pack_kernel, restated in fp64: centre, radius, M0, tr M1, sym M1, u and
+    the cubic form.  Beyond 2 radii (WC_BETA) its error against the exact cluster solid angles is a few 1e-3
+    of a winding number in total."""
+    import torch
+    from oracle import clib, lbs as olbs
+    from tuch_b200 import synthetic as syn
+    model = syn.make_lattice_body_model(seed=0)
+    faces = model['faces']
+    t = tree_for(model)
+    tm = olbs.to_torch_model(model)
+    pose = torch.tensor(syn.fold_arms_pose(1, seed=5))
+    v = olbs.smpl_forward(tm, torch.zeros(1, 10), pose[:, 3:], pose[:, :3])[0][0].numpy().astype(np.float64)
+    tri = v[faces]
+    A, B, C = tri[:, 0], tri[:, 1], tri[:, 2]
+    av = 0.5 * np.cross(B - A, C - A)
+    area = np.linalg.norm(av, axis=1)
+    rng = np.random.default_rng(0)
+    q = v[rng.choice(len(v), 400, replace=False)]
+    sa = clib.solid_angles(q, tri, dtype=np.float64)                               # [Q,F], = 2 atan2(...)
+    total_err = np.zeros(len(q))
+    signed_err = np.zeros(len(q))
+    for row in t['leaf_face']:
+        fs = row[row >= 0]
+        p = ((A[fs] + B[fs] + C[fs]) / 3 * area[fs, None]).sum(0) / area[fs].sum()
+        R = np.sqrt(((tri[fs].reshape(-1, 3) - p) ** 2).sum(1).max())
+        c = (A[fs] + B[fs] + C[fs]) / 3 - p
+        mids = np.stack([(A[fs] + B[fs]) / 2, (B[fs] + C[fs]) / 2, (C[fs] + A[fs]) / 2], 1) - p
+        S = np.einsum('tmj,tmk->tjk', mids, mids) / 3
+        M0 = av[fs].sum(0)
+        M1 = np.einsum('ti,tj->ij', av[fs], c)
+        M2 = np.einsum('ti,tjk->ijk', av[fs], S)
+        u = 2 * np.einsum('iik->k', M2) + np.einsum('kjj->k', M2)
+        r = p[None] - q
+        d = np.linalg.norm(r, axis=1)
+        omega = (r @ M0 + np.trace(M1)) / d ** 3 - (3 * np.einsum('qi,ij,qj->q', r, M1, r) + 1.5 * r @ u) / d ** 5 \
+            + 7.5 * np.einsum('ijk,qi,qj,qk->q', M2, r, r, r) / d ** 7
+        far = d > 2.0 * R
+        total_err += np.where(far, np.abs(omega - sa[:, fs].sum(1)), 0.0) / (4 * np.pi)
+        signed_err += np.where(far, omega - sa[:, fs].sum(1), 0.0) / (4 * np.pi)
+    # even if every leaf's error had the same sign the total stays below a third of the 0.03 re-evaluation
+    # margin (WC_MARGIN); the actual error is a few 1e-3
+    assert total_err.max() < 1e-2, total_err.max()
+    assert np.abs(signed_err).max() < 4e-3, np.abs(signed_err).max()

@@ -27,11 +27,16 @@ def posed_verts(assets, batch, seed, dtype=np.float32):
     return olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].numpy().astype(dtype)
 
 
-def make_topology(assets, dev, geothres=0.3, segments=True, regions=True):
+def make_topology(assets, dev, geothres=0.3, segments=True, regions=True, exact=True, template=True):
+    """exact=True pins the winding numbers to the all-faces sum (value parity); exact=False is the
+    product default (hierarchical far field + exact re-evaluation near the 0.99 threshold)."""
     from tuch_b200 import ops
     from tuch_b200.utils.segmentation import BatchBodySegment
     m = assets['model']
     topo = ops.Topology(m['faces'], len(m['v_template']), dev)
+    topo.set_winding_mode(topo.WINDING_EXACT if exact else topo.WINDING_FAST)
+    if not exact and template:
+        topo.set_template(m['v_template'])
     topo.set_geodist(torch.tensor(assets['geo'], device=dev), geothres)
     if regions:
         topo.set_regions(assets['regions'])
@@ -102,10 +107,17 @@ def check_query(assets, dev, batch, seed, use_segments):
     topo = make_topology(assets, dev)
     verts = posed_verts(assets, batch, seed)
     out = topo.contact_query(torch.tensor(verts, device=dev), use_segments=use_segments)
+    fast = make_topology(assets, dev, exact=False).contact_query(torch.tensor(verts, device=dev), use_segments=use_segments)
     faces = assets['model']['faces']
     geomask = assets['geo'] > 0.3
     segs = oseg.build_segments(assets['segs'], faces)
     n_interior = 0
+    # hierarchical mode: same nearest vertices, winding numbers within the far-field error, flags
+    # identical away from the threshold
+    assert torch.equal(fast['argmin'], out['argmin']) and torch.equal(fast['min_sq'], out['min_sq'])
+    assert (fast['winding'] - out['winding']).abs().max() < 5e-3
+    away = (out['winding'] - 0.99).abs() > 1e-4
+    assert torch.equal(fast['exterior'][away], out['exterior'][away])
     for b in range(batch):
         v = verts[b]
         w64 = clib.winding_numbers(v, v[faces], dtype=np.float64)
@@ -228,3 +240,57 @@ def test_contact_query_full_size(dev, full_assets):
     # the template (unposed, no self-contact) has no interior vertex
     t = torch.tensor(full_assets['model']['v_template'], device=verts.device)[None]
     assert bool(topo.contact_query(t, use_segments=False)['exterior'].all())
+
+
+def _fast_vs_exact(assets, dev, batch, seed, template):
+    ex = make_topology(assets, dev, segments=False, regions=False)
+    fa = make_topology(assets, dev, segments=False, regions=False, exact=False, template=template)
+    verts = torch.tensor(posed_verts(assets, batch, seed), device=dev)
+    a = ex.contact_query(verts, use_segments=False, want_nearest=False)
+    b = fa.contact_query(verts, use_segments=False, want_nearest=False)
+    stats = fa.cluster_stats()
+    assert stats['leaves'] >= len(assets['model']['faces']) // 32 and stats['supers'] >= 1
+    err = (a['winding'] - b['winding']).abs()
+    assert float(err.max()) < 5e-3, float(err.max())
+    # every query the far field could misclassify was re-evaluated exactly
+    band = (b['winding'] - 0.99).abs() < 0.03
+    if bool(band.any()):
+        assert float(err[band].max()) < 2e-5
+    away = (a['winding'] - 0.99).abs() > 1e-4
+    assert torch.equal(a['exterior'][away], b['exterior'][away])
+    assert int((~a['exterior']).sum()) > 0
+    # deterministic, and invariant to the batch composition
+    b2 = fa.contact_query(verts, use_segments=False, want_nearest=False)
+    assert torch.equal(b['winding'], b2['winding'])
+    c = fa.contact_query(verts[1:3].contiguous(), use_segments=False, want_nearest=False)
+    assert (c['winding'] - b['winding'][1:3]).abs().max() < 5e-6
+    return float(err.max())
+
+
+def test_hierarchical_winding_full_size(dev, full_assets, full_assets_uv):
+    """Far-field winding numbers (clusters.cu) against the all-faces sum at SMPL size, on the SMPL-like
+    lattice body and on the sliver-triangle UV body, with the hierarchy built from the template and
+    lazily from the first posed body."""
+    _fast_vs_exact(full_assets, dev, batch=6, seed=21, template=True)
+    _fast_vs_exact(full_assets, dev, batch=3, seed=22, template=False)
+    _fast_vs_exact(full_assets_uv, dev, batch=4, seed=23, template=True)
+
+
+def test_hierarchical_winding_touching_contact(dev, full_assets):
+    """SMPLify-DC converges to touching contact, where vertices sit right at the 0.99 threshold: sweep
+    the arm fold so that vertices cross the torso surface in small steps and compare the flags with the
+    all-faces sum."""
+    from oracle import lbs as olbs
+    from tuch_b200 import synthetic as syn
+    ex = make_topology(full_assets, dev, segments=False, regions=False)
+    fa = make_topology(full_assets, dev, segments=False, regions=False, exact=False)
+    tm = olbs.to_torch_model(full_assets['model'])
+    folds = np.linspace(0.55, 1.0, 12)
+    pose = torch.tensor(np.concatenate([syn.fold_arms_pose(1, seed=24, fold=float(f)) for f in folds]))
+    verts = olbs.smpl_forward(tm, torch.zeros(len(folds), 10), pose[:, 3:], pose[:, :3])[0].to(dev).contiguous()
+    a = ex.contact_query(verts, use_segments=False, want_nearest=False)
+    b = fa.contact_query(verts, use_segments=False, want_nearest=False)
+    away = (a['winding'] - 0.99).abs() > 1e-4
+    assert torch.equal(a['exterior'][away], b['exterior'][away])
+    n_int = (~a['exterior']).sum(1)
+    assert int(n_int.min()) != int(n_int.max())          # the sweep really crosses the surface

@@ -1,12 +1,14 @@
 // C ABI (include/tuch_b200.h): status, scratch arenas, mesh topology and the contact entry points.
 #include "api_internal.h"
 #include "strips.h"
+#include "clusters.h"
 
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <string>
@@ -282,6 +284,7 @@ static void free_segments(tuch_topology* t) {
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
+    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_qperm);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -305,6 +308,66 @@ TUCH_EXPORT int tuch_strip_stream_host(const int32_t* faces_host, int F, int32_t
         std::copy(vid.begin(), vid.end(), vid_out);
         std::copy(flag.begin(), flag.end(), flag_out);
     }
+    return 0;
+}
+
+static int install_clusters(tuch_topology* t, const float* verts_host) {
+    std::vector<int> faces((size_t)t->F * 3);
+    TUCH_CUDA(cudaMemcpy(faces.data(), t->d_faces, faces.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    ClusterTree tree;
+    if (int rc = build_cluster_tree(faces.data(), t->F, t->V, verts_host, tree)) return rc;
+    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_qperm);
+    t->d_leaf_face = t->d_super_off = t->d_qperm = nullptr;
+    t->has_clusters = false;
+    if (int rc = upload(tree.leaf_face.data(), tree.leaf_face.size(), &t->d_leaf_face)) return rc;
+    if (int rc = upload(tree.super_off.data(), tree.super_off.size(), &t->d_super_off)) return rc;
+    if (int rc = upload(tree.qperm.data(), tree.qperm.size(), &t->d_qperm)) return rc;
+    t->K = tree.K; t->NS = tree.NS;
+    t->has_clusters = true;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_set_template(tuch_topology* t, const float* verts_host) {
+    TUCH_REQUIRE(t != nullptr && verts_host != nullptr, "tuch_topology_set_template: null pointer");
+    TUCH_REQUIRE(t->F > 0, "tuch_topology_set_template: topology has no faces");
+    for (size_t i = 0; i < (size_t)t->V * 3; ++i)
+        TUCH_REQUIRE(std::isfinite(verts_host[i]), "tuch_topology_set_template: non-finite coordinate at %zu", i);
+    return install_clusters(t, verts_host);
+}
+
+TUCH_EXPORT int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float* verts_host,
+                                       int32_t* leaf_face_out, int leaf_capacity, int32_t* super_off_out,
+                                       int super_capacity, int32_t* qperm_out, int* n_leaves, int* n_supers) {
+    TUCH_REQUIRE(faces_host != nullptr && verts_host != nullptr && F > 0 && V > 0, "tuch_cluster_tree_host: need a mesh");
+    for (size_t i = 0; i < (size_t)F * 3; ++i)
+        TUCH_REQUIRE(faces_host[i] >= 0 && faces_host[i] < V, "tuch_cluster_tree_host: face index %d out of range", faces_host[i]);
+    ClusterTree tree;
+    if (int rc = build_cluster_tree(faces_host, F, V, verts_host, tree)) return rc;
+    if (n_leaves) *n_leaves = tree.K;
+    if (n_supers) *n_supers = tree.NS;
+    if (leaf_face_out != nullptr) {
+        TUCH_REQUIRE(leaf_capacity >= tree.K, "tuch_cluster_tree_host: leaf capacity %d < %d", leaf_capacity, tree.K);
+        std::copy(tree.leaf_face.begin(), tree.leaf_face.end(), leaf_face_out);
+    }
+    if (super_off_out != nullptr) {
+        TUCH_REQUIRE(super_capacity >= tree.NS, "tuch_cluster_tree_host: super capacity %d < %d", super_capacity, tree.NS);
+        std::copy(tree.super_off.begin(), tree.super_off.end(), super_off_out);
+    }
+    if (qperm_out != nullptr) std::copy(tree.qperm.begin(), tree.qperm.end(), qperm_out);
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_set_winding_mode(tuch_topology* t, int mode) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_set_winding_mode: null topology");
+    TUCH_REQUIRE(mode == TUCH_WINDING_EXACT || mode == TUCH_WINDING_FAST, "tuch_topology_set_winding_mode: unknown mode %d", mode);
+    t->winding_mode = mode;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_cluster_stats(const tuch_topology* t, int* n_leaves, int* n_supers) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_cluster_stats: null topology");
+    if (n_leaves) *n_leaves = t->has_clusters ? t->K : 0;
+    if (n_supers) *n_supers = t->has_clusters ? t->NS : 0;
     return 0;
 }
 
@@ -461,11 +524,30 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     TUCH_REQUIRE(!want_w || t->F > 0, "tuch_contact_query: winding requested on a topology without faces");
     const bool segs = exterior != nullptr && use_segments && t->n_segments > 0;
     const int V = t->V, Fp = t->Fp, Vp = t->Vp, Lp = t->Lp;
-    const int S = want_w ? strip_splits(B, V, Lp, sm_count()) : 1;
+    if (want_w && t->winding_mode == TUCH_WINDING_FAST && !t->has_clusters) {
+        // no template was given: cluster the faces on the first body seen (one blocking copy, once);
+        // inside a CUDA-graph capture the exact kernel is used instead
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        TUCH_CUDA(cudaStreamIsCapturing(st, &cs));
+        if (cs == cudaStreamCaptureStatusNone) {
+            std::vector<float> h((size_t)V * 3);
+            TUCH_CUDA(cudaMemcpyAsync(h.data(), verts, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+            TUCH_CUDA(cudaStreamSynchronize(st));
+            bool finite = true;
+            for (float x : h) finite = finite && std::isfinite(x);
+            if (finite)
+                if (int rc = install_clusters(const_cast<tuch_topology*>(t), h.data())) return rc;   // lazily built cache
+        }
+    }
+    const bool fast = want_w && t->winding_mode == TUCH_WINDING_FAST && t->has_clusters;
+    const int S = !want_w ? 1 : fast ? cluster_splits(B, V, t->NS, sm_count()) : strip_splits(B, V, Lp, sm_count());
 
     Scratch sc;
-    const size_t h_tri = sc.plan(want_w ? sizeof(float4) * 2 * (size_t)B * Lp : 0);
-    const size_t h_info = sc.plan(want_w ? sizeof(float4) * (size_t)B * (Lp / WS_TILE) : 0);
+    const size_t h_tri = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * 3 * (size_t)B * t->K * WC_LEAF
+                                                    : sizeof(float4) * 2 * (size_t)B * Lp);
+    const size_t h_info = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * WC_NODE_F4 * (size_t)B * (t->NS + t->K)
+                                                     : sizeof(float4) * (size_t)B * (Lp / WS_TILE));
+    const size_t h_ref = sc.plan(fast ? sizeof(int) * ((size_t)B * V + 1) : 0);
     const size_t h_v4 = sc.plan((want_nn && !vert4_out) ? sizeof(float4) * (size_t)B * Vp : 0);
     const size_t h_par = sc.plan(want_w ? sizeof(float) * (size_t)B * S * V : 0);
     const size_t h_w = sc.plan((want_w && !winding) ? sizeof(float) * (size_t)B * V : 0);
@@ -484,9 +566,15 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     if (want_w) {
         float* w = winding ? winding : sc.get<float>(h_w);
         float4* info = sc.get<float4>(h_info);
-        if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
-        StripJob j{strip4, info, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V, nullptr, B, V, Lp, S};
-        if (int rc = launch_winding_strips(j, st)) return rc;
+        if (fast) {
+            ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_super_off, t->d_qperm, strip4, info,
+                         sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NS, S};
+            if (int rc = launch_winding_clusters(j, st)) return rc;
+        } else {
+            if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
+            StripJob j{strip4, info, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V, nullptr, B, V, Lp, S};
+            if (int rc = launch_winding_strips(j, st)) return rc;
+        }
         if (exterior) {
             uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;
             if (any) TUCH_CUDA(cudaMemsetAsync(any, 0, (size_t)B, st));

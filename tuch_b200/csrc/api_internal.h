@@ -12,6 +12,12 @@ struct tuch_topology {
     // triangle-strip stream of the faces (strips.cu): vertex id / flag per element, Lp elements
     int Lp = 0, n_strips = 0;
     int *d_strip_vid = nullptr, *d_strip_fid = nullptr;
+    // face-cluster hierarchy for the far-field winding kernel (clusters.cu); built from the template
+    // (tuch_topology_set_template) or lazily from the first body a contact query sees
+    int K = 0, NS = 0;
+    int *d_leaf_face = nullptr, *d_super_off = nullptr, *d_qperm = nullptr;
+    bool has_clusters = false;
+    int winding_mode = 1;              // TUCH_WINDING_FAST
     uint32_t* d_maskT = nullptr;       // [W][Vq] bit-packed geodesic mask
     bool has_mask = false;
     // DSC regions (CSR) and annotated pairs

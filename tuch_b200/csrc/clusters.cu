@@ -1,0 +1,519 @@
+// Far-field winding numbers over a face-cluster hierarchy ("fast winding numbers", Barill et al. 2018,
+// restated for a fixed-topology batch of posed bodies).
+//
+// The generalized winding number of tuch/utils/contact.py:112-147 is a sum of F signed solid angles per
+// query.  The solid angle of a flat triangle t seen from q is the exact surface integral
+//     Omega_t(q) = int_t  n . (x - q) / |x - q|^3  dA ,
+// so a CLUSTER of triangles far from q can be replaced by the Taylor expansion of that integrand about
+// the cluster centre p, whose coefficients are area-weighted polynomial moments of the cluster
+// (exact for flat triangles: centroid for the linear term, edge-midpoint quadrature for the quadratic):
+//     Omega_C(q) ~ (M0.r + tr M1) / R^3 - (3 r'M1 r + 1.5 u.r) / R^5 + 7.5 T(r,r,r) / R^7,   r = p - q, R = |r|.
+// The topology (constant across bodies and iterations, smplifydc.py:58-61) is cut once, on the host,
+// into leaves of <= 32 faces grouped into super-clusters of <= 8 leaves; per body and iteration one warp
+// per node recomputes centre, radius and moments from the posed vertices.  The winding kernel then
+// walks supers -> leaves per warp of 32 neighbouring queries: a node farther than WC_BETA radii from
+// every query of the warp costs ~50 instructions per query; a leaf that is near for some queries is
+// evaluated exactly for those queries with one LANE PER FACE (same arithmetic as winding_kernel).
+// Callers only consume `winding <= 0.99` (losses.py:82, loss.py:262): every query whose approximate
+// value lies within WC_MARGIN of the threshold is re-evaluated exactly over all faces, so the flags are
+// those of the exact kernel.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <unordered_map>
+
+#include "api_internal.h"
+#include "clusters.h"
+
+namespace tuch {
+
+// ------------------------------------------------------------------------------------------
+// host: hierarchy
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct TreeBuilder {
+    const int* faces;
+    int F;
+    std::vector<float> cen;                  // [F][3] face centroids
+    std::vector<int> adj_off, adj;           // face adjacency (shared edge), CSR
+    std::vector<int> stamp;                  // membership marks
+    int cur_stamp = 0;
+    ClusterTree* out;
+
+    void build_adjacency() {
+        std::unordered_map<uint64_t, std::vector<int>> ef;
+        ef.reserve((size_t)F * 2);
+        auto key = [](int u, int v) {
+            const uint64_t a = (uint64_t)std::min(u, v), b = (uint64_t)std::max(u, v);
+            return (a << 32) | b;
+        };
+        for (int t = 0; t < F; ++t)
+            for (int e = 0; e < 3; ++e) ef[key(faces[3 * t + e], faces[3 * t + (e + 1) % 3])].push_back(t);
+        std::vector<std::vector<int>> nb(F);
+        for (int t = 0; t < F; ++t)
+            for (int e = 0; e < 3; ++e)
+                for (int g : ef[key(faces[3 * t + e], faces[3 * t + (e + 1) % 3])])
+                    if (g != t) nb[t].push_back(g);
+        adj_off.assign(F + 1, 0);
+        for (int t = 0; t < F; ++t) {
+            std::sort(nb[t].begin(), nb[t].end());
+            nb[t].erase(std::unique(nb[t].begin(), nb[t].end()), nb[t].end());
+            adj_off[t + 1] = adj_off[t] + (int)nb[t].size();
+        }
+        adj.resize(adj_off[F]);
+        for (int t = 0; t < F; ++t) std::copy(nb[t].begin(), nb[t].end(), adj.begin() + adj_off[t]);
+    }
+
+    // connected components of `fs` (sorted by their smallest face id, faces ascending inside)
+    std::vector<std::vector<int>> components(const std::vector<int>& fs) {
+        const int in = ++cur_stamp;
+        for (int f : fs) stamp[f] = in;
+        std::vector<std::vector<int>> comps;
+        std::vector<int> stack;
+        for (int f0 : fs) {
+            if (stamp[f0] != in) continue;
+            stamp[f0] = 0;
+            comps.emplace_back();
+            stack.assign(1, f0);
+            while (!stack.empty()) {
+                const int f = stack.back();
+                stack.pop_back();
+                comps.back().push_back(f);
+                for (int k = adj_off[f]; k < adj_off[f + 1]; ++k)
+                    if (stamp[adj[k]] == in) { stamp[adj[k]] = 0; stack.push_back(adj[k]); }
+            }
+            std::sort(comps.back().begin(), comps.back().end());
+        }
+        return comps;
+    }
+
+    void emit_leaf(const std::vector<int>& fs) {
+        for (int i = 0; i < WC_LEAF; ++i) out->leaf_face.push_back(i < (int)fs.size() ? fs[i] : -1);
+        ++out->K;
+    }
+
+    void split(std::vector<int> fs, bool in_super) {           // fs ascending
+        const int n = (int)fs.size();
+        const int n_leaves = (n + WC_LEAF - 1) / WC_LEAF;
+        if (!in_super && n_leaves <= WC_SUPER_LEAVES) {
+            out->super_off.push_back(out->K);
+            ++out->NS;
+            in_super = true;
+        }
+        std::vector<std::vector<int>> comps = components(fs);
+        if (comps.size() > 1) {
+            for (auto& c : comps) split(std::move(c), in_super);
+            return;
+        }
+        if (n <= WC_LEAF) { emit_leaf(fs); return; }
+        // principal axis of the face centroids (power iteration on the 3x3 covariance, fp64)
+        double mean[3] = {0, 0, 0};
+        for (int f : fs) for (int a = 0; a < 3; ++a) mean[a] += cen[3 * f + a];
+        for (int a = 0; a < 3; ++a) mean[a] /= n;
+        double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int f : fs) {
+            double d[3];
+            for (int a = 0; a < 3; ++a) d[a] = cen[3 * f + a] - mean[a];
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[a][b] += d[a] * d[b];
+        }
+        double v[3] = {0.57, 0.58, 0.59};
+        for (int it = 0; it < 64; ++it) {
+            double w[3] = {0, 0, 0};
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) w[a] += C[a][b] * v[b];
+            const double nrm = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+            if (nrm < 1e-300) break;
+            for (int a = 0; a < 3; ++a) v[a] = w[a] / nrm;
+        }
+        std::vector<std::pair<double, int>> key(n);
+        for (int i = 0; i < n; ++i) {
+            const int f = fs[i];
+            key[i] = {(cen[3 * f] - mean[0]) * v[0] + (cen[3 * f + 1] - mean[1]) * v[1] + (cen[3 * f + 2] - mean[2]) * v[2], f};
+        }
+        std::sort(key.begin(), key.end());
+        const int left_leaves = (n_leaves + 1) / 2;
+        int n_left = (int)std::llround((double)n * left_leaves / n_leaves);
+        n_left = std::max(1, std::min(n - 1, n_left));
+        std::vector<int> l(n_left), r(n - n_left);
+        for (int i = 0; i < n; ++i) (i < n_left ? l[i] : r[i - n_left]) = key[i].second;
+        std::sort(l.begin(), l.end());
+        std::sort(r.begin(), r.end());
+        // a planar cut through a triangulated patch leaves ragged fragments (faces whose neighbours all
+        // fell on the other side): hand small cut-off pieces to the other half instead of letting them
+        // become leaves of their own
+        auto give_fragments = [&](std::vector<int>& from, std::vector<int>& to) {
+            std::vector<std::vector<int>> comps = components(from);
+            if (comps.size() < 2) return;
+            size_t big = 0;
+            for (size_t c = 1; c < comps.size(); ++c) if (comps[c].size() > comps[big].size()) big = c;
+            const size_t small = std::max<size_t>(3, from.size() / 8);
+            std::vector<int> keep;
+            for (size_t c = 0; c < comps.size(); ++c) {
+                std::vector<int>& dst = (c != big && comps[c].size() <= small && to.size() + comps[c].size() < (size_t)n) ? to : keep;
+                dst.insert(dst.end(), comps[c].begin(), comps[c].end());
+            }
+            from.swap(keep);
+            std::sort(from.begin(), from.end());
+            std::sort(to.begin(), to.end());
+        };
+        give_fragments(l, r);
+        give_fragments(r, l);
+        if (l.empty() || r.empty()) {           // cannot happen for a connected set; keep the recursion finite
+            std::vector<int>& all = l.empty() ? r : l;
+            std::vector<int> a(all.begin(), all.begin() + all.size() / 2), b2(all.begin() + all.size() / 2, all.end());
+            l.swap(a); r.swap(b2);
+        }
+        split(std::move(l), in_super);
+        split(std::move(r), in_super);
+    }
+};
+
+}  // namespace
+
+int build_cluster_tree(const int* faces, int F, int V, const float* verts, ClusterTree& out) {
+    out = ClusterTree();
+    TUCH_REQUIRE(F > 0 && V > 0 && faces && verts, "build_cluster_tree: empty mesh");
+    TreeBuilder tb;
+    tb.faces = faces; tb.F = F; tb.out = &out;
+    tb.cen.resize((size_t)F * 3);
+    for (int t = 0; t < F; ++t)
+        for (int a = 0; a < 3; ++a)
+            tb.cen[3 * t + a] = (verts[3 * faces[3 * t] + a] + verts[3 * faces[3 * t + 1] + a] + verts[3 * faces[3 * t + 2] + a]) / 3.f;
+    tb.build_adjacency();
+    tb.stamp.assign(F, 0);
+    std::vector<int> all(F);
+    std::iota(all.begin(), all.end(), 0);
+    tb.split(std::move(all), false);
+    out.super_off.push_back(out.K);
+    // self-check: every face in exactly one leaf
+    std::vector<char> seen(F, 0);
+    size_t n = 0;
+    for (int f : out.leaf_face)
+        if (f >= 0) { TUCH_REQUIRE(!seen[f], "cluster tree lists face %d twice", f); seen[f] = 1; ++n; }
+    TUCH_REQUIRE((int)n == F, "cluster tree covers %zu of %d faces", n, F);
+    // query order: vertices sorted by the first leaf that holds one of their faces
+    std::vector<int> first(V, out.K);
+    for (int l = 0; l < out.K; ++l)
+        for (int i = 0; i < WC_LEAF; ++i) {
+            const int f = out.leaf_face[(size_t)l * WC_LEAF + i];
+            if (f < 0) continue;
+            for (int e = 0; e < 3; ++e) first[faces[3 * f + e]] = std::min(first[faces[3 * f + e]], l);
+        }
+    out.qperm.resize(V);
+    std::iota(out.qperm.begin(), out.qperm.end(), 0);
+    std::stable_sort(out.qperm.begin(), out.qperm.end(), [&](int a, int b) { return first[a] < first[b]; });
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// device: per-body node records
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// One warp per node (supers first, then leaves).  Record layout (all moments pre-scaled so that the
+// kernel's sum is Omega / 2, the quantity winding_finalize expects):
+//   f0 = (p, (beta R)^2)                    f1 = 0.5 (M0, tr M1)
+//   f2 = -1.5 (Qxx, Qyy, Qzz, 2Qxy)         f3 = (-1.5 * 2Qxz, -1.5 * 2Qyz, -0.75 ux, -0.75 uy)
+//   f4 = (-0.75 uz, 3.75 Txxx, 3.75 Tyyy, 3.75 Tzzz)
+//   f5 = 3.75 (Txxy, Txxz, Tyyx, Tyyz)      f6 = 3.75 (Tzzx, Tzzy, Txyz, 0)
+// Q = sym(M1), u_k = 2 (a.S)_k + a_k tr S, T = symmetrised sum_t a_t (x) S_t.
+__global__ void __launch_bounds__(128)
+cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restrict__ faces,
+                    const int* __restrict__ leaf_face, const int* __restrict__ super_off, int K, int NS,
+                    float4* __restrict__ ctri, float4* __restrict__ nodes) {
+    const int b = blockIdx.y;
+    const int node = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (node >= NS + K) return;
+    const bool is_leaf = node >= NS;
+    const int l0 = is_leaf ? node - NS : super_off[node];
+    const int l1 = is_leaf ? l0 + 1 : super_off[node + 1];
+    const float* vb = verts + (size_t)b * V * 3;
+
+    // pass 1: area-weighted centre (falls back to the plain centroid mean for zero-area nodes)
+    float wsum = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f, cnt = 0.f;
+    for (int l = l0; l < l1; ++l) {
+        const int f = leaf_face[(size_t)l * WC_LEAF + lane];
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bv = A, C = A;
+        if (f >= 0) {
+            const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+            A = make_float4(vb[3 * i0], vb[3 * i0 + 1], vb[3 * i0 + 2], 1.f);
+            Bv = make_float4(vb[3 * i1], vb[3 * i1 + 1], vb[3 * i1 + 2], 0.f);
+            C = make_float4(vb[3 * i2], vb[3 * i2 + 1], vb[3 * i2 + 2], 0.f);
+            const float e1x = Bv.x - A.x, e1y = Bv.y - A.y, e1z = Bv.z - A.z;
+            const float e2x = C.x - A.x, e2y = C.y - A.y, e2z = C.z - A.z;
+            const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+            const float area = 0.5f * sqrtf(nx * nx + ny * ny + nz * nz);
+            const float gx = (A.x + Bv.x + C.x) * (1.f / 3.f), gy = (A.y + Bv.y + C.y) * (1.f / 3.f),
+                        gz = (A.z + Bv.z + C.z) * (1.f / 3.f);
+            wsum += area; cx += area * gx; cy += area * gy; cz += area * gz;
+            ux += gx; uy += gy; uz += gz; cnt += 1.f;
+        }
+        if (is_leaf) {
+            float4* o = ctri + (((size_t)b * K + l) * WC_LEAF + lane) * 3;
+            o[0] = A; o[1] = Bv; o[2] = C;
+        }
+    }
+    wsum = warp_sum(wsum); cnt = warp_sum(cnt);
+    float px, py, pz;
+    if (wsum > 1e-30f) {
+        const float inv = 1.f / wsum;
+        px = warp_sum(cx) * inv; py = warp_sum(cy) * inv; pz = warp_sum(cz) * inv;
+    } else {
+        const float inv = 1.f / fmaxf(cnt, 1.f);
+        px = warp_sum(ux) * inv; py = warp_sum(uy) * inv; pz = warp_sum(uz) * inv;
+    }
+
+    // pass 2: radius and moments about p
+    float r2 = 0.f;
+    float m0x = 0.f, m0y = 0.f, m0z = 0.f, tr = 0.f;
+    float qxx = 0.f, qyy = 0.f, qzz = 0.f, qxy = 0.f, qxz = 0.f, qyz = 0.f;
+    float uvx = 0.f, uvy = 0.f, uvz = 0.f;
+    float txxx = 0.f, tyyy = 0.f, tzzz = 0.f, txxy = 0.f, txxz = 0.f, tyyx = 0.f, tyyz = 0.f, tzzx = 0.f, tzzy = 0.f,
+          txyz = 0.f;
+    for (int l = l0; l < l1; ++l) {
+        const int f = leaf_face[(size_t)l * WC_LEAF + lane];
+        if (f < 0) continue;
+        const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+        const float ax = vb[3 * i0] - px, ay = vb[3 * i0 + 1] - py, az = vb[3 * i0 + 2] - pz;
+        const float bx = vb[3 * i1] - px, by = vb[3 * i1 + 1] - py, bz = vb[3 * i1 + 2] - pz;
+        const float gx = vb[3 * i2] - px, gy = vb[3 * i2 + 1] - py, gz = vb[3 * i2 + 2] - pz;
+        r2 = fmaxf(r2, fmaxf(ax * ax + ay * ay + az * az, fmaxf(bx * bx + by * by + bz * bz, gx * gx + gy * gy + gz * gz)));
+        const float e1x = bx - ax, e1y = by - ay, e1z = bz - az, e2x = gx - ax, e2y = gy - ay, e2z = gz - az;
+        const float nx = 0.5f * (e1y * e2z - e1z * e2y), ny = 0.5f * (e1z * e2x - e1x * e2z),
+                    nz = 0.5f * (e1x * e2y - e1y * e2x);                        // area vector
+        const float hx = (ax + bx + gx) * (1.f / 3.f), hy = (ay + by + gy) * (1.f / 3.f), hz = (az + bz + gz) * (1.f / 3.f);
+        m0x += nx; m0y += ny; m0z += nz;
+        tr += nx * hx + ny * hy + nz * hz;
+        qxx += nx * hx; qyy += ny * hy; qzz += nz * hz;
+        qxy += nx * hy + ny * hx; qxz += nx * hz + nz * hx; qyz += ny * hz + nz * hy;   // = 2 Q_ij
+        // S = (1/3) sum over the three edge midpoints of m m^T (exact for quadratics on a triangle)
+        const float m1x = 0.5f * (ax + bx), m1y = 0.5f * (ay + by), m1z = 0.5f * (az + bz);
+        const float m2x = 0.5f * (bx + gx), m2y = 0.5f * (by + gy), m2z = 0.5f * (bz + gz);
+        const float m3x = 0.5f * (gx + ax), m3y = 0.5f * (gy + ay), m3z = 0.5f * (gz + az);
+        const float k3 = 1.f / 3.f;
+        const float sxx = k3 * (m1x * m1x + m2x * m2x + m3x * m3x), syy = k3 * (m1y * m1y + m2y * m2y + m3y * m3y),
+                    szz = k3 * (m1z * m1z + m2z * m2z + m3z * m3z);
+        const float sxy = k3 * (m1x * m1y + m2x * m2y + m3x * m3y), sxz = k3 * (m1x * m1z + m2x * m2z + m3x * m3z),
+                    syz = k3 * (m1y * m1z + m2y * m2z + m3y * m3z);
+        const float trs = sxx + syy + szz;
+        uvx += 2.f * (nx * sxx + ny * sxy + nz * sxz) + nx * trs;
+        uvy += 2.f * (nx * sxy + ny * syy + nz * syz) + ny * trs;
+        uvz += 2.f * (nx * sxz + ny * syz + nz * szz) + nz * trs;
+        // (n.r)(r'S r) expanded into its 10 cubic coefficients
+        txxx += nx * sxx; tyyy += ny * syy; tzzz += nz * szz;
+        txxy += 2.f * nx * sxy + ny * sxx; txxz += 2.f * nx * sxz + nz * sxx;
+        tyyx += 2.f * ny * sxy + nx * syy; tyyz += 2.f * ny * syz + nz * syy;
+        tzzx += 2.f * nz * sxz + nx * szz; tzzy += 2.f * nz * syz + ny * szz;
+        txyz += 2.f * (nx * syz + ny * sxz + nz * sxy);
+    }
+    r2 = warp_max(r2);
+    m0x = warp_sum(m0x); m0y = warp_sum(m0y); m0z = warp_sum(m0z); tr = warp_sum(tr);
+    qxx = warp_sum(qxx); qyy = warp_sum(qyy); qzz = warp_sum(qzz);
+    qxy = warp_sum(qxy); qxz = warp_sum(qxz); qyz = warp_sum(qyz);
+    uvx = warp_sum(uvx); uvy = warp_sum(uvy); uvz = warp_sum(uvz);
+    txxx = warp_sum(txxx); tyyy = warp_sum(tyyy); tzzz = warp_sum(tzzz);
+    txxy = warp_sum(txxy); txxz = warp_sum(txxz); tyyx = warp_sum(tyyx); tyyz = warp_sum(tyyz);
+    tzzx = warp_sum(tzzx); tzzy = warp_sum(tzzy); txyz = warp_sum(txyz);
+    if (lane == 0) {
+        float4* o = nodes + ((size_t)b * (NS + K) + node) * WC_NODE_F4;
+        o[0] = make_float4(px, py, pz, r2 * (WC_BETA * WC_BETA * 1.0002f));
+        o[1] = make_float4(0.5f * m0x, 0.5f * m0y, 0.5f * m0z, 0.5f * tr);
+        o[2] = make_float4(-1.5f * qxx, -1.5f * qyy, -1.5f * qzz, -1.5f * qxy);
+        o[3] = make_float4(-1.5f * qxz, -1.5f * qyz, -0.75f * uvx, -0.75f * uvy);
+        o[4] = make_float4(-0.75f * uvz, 3.75f * txxx, 3.75f * tyyy, 3.75f * tzzz);
+        o[5] = make_float4(3.75f * txxy, 3.75f * txxz, 3.75f * tyyx, 3.75f * tyyz);
+        o[6] = make_float4(3.75f * tzzx, 3.75f * tzzy, 3.75f * txyz, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// device: hierarchical winding kernel
+// ------------------------------------------------------------------------------------------
+// half the far-field solid angle of one node; (x, y, z) = node centre - query, d2 = |.|^2 > 0
+__device__ __forceinline__ float node_far_field(const float4* __restrict__ rec, float x, float y, float z, float d2) {
+    const float4 f1 = __ldg(rec + 1), f2 = __ldg(rec + 2), f3 = __ldg(rec + 3), f4 = __ldg(rec + 4),
+                 f5 = __ldg(rec + 5), f6 = __ldg(rec + 6);
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+    float inv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(d2));
+    const float i2 = inv * inv, i3 = i2 * inv, i5 = i3 * i2, i7 = i5 * i2;
+    const float t0 = fmaf(f1.x, x, fmaf(f1.y, y, fmaf(f1.z, z, f1.w)));
+    float t1 = fmaf(f2.x, xx, fmaf(f2.y, yy, f2.z * zz));
+    t1 = fmaf(f2.w, xy, fmaf(f3.x, xz, fmaf(f3.y, yz, t1)));
+    t1 = fmaf(f3.z, x, fmaf(f3.w, y, fmaf(f4.x, z, t1)));
+    const float cxp = fmaf(f4.y, xx, fmaf(f5.x, xy, fmaf(f5.y, xz, fmaf(f5.z, yy, fmaf(f6.x, zz, f6.z * yz)))));
+    const float cyp = fmaf(f4.z, yy, fmaf(f5.w, yz, f6.y * zz));
+    const float t2 = fmaf(x, cxp, fmaf(y, cyp, z * (f4.w * zz)));
+    return fmaf(t0, i3, fmaf(t1, i5, t2 * i7));
+}
+
+// grid (query tiles of WC_WARPS * 32, super splits, bodies); one query per lane, in cluster order
+__global__ void __launch_bounds__(WC_WARPS * 32)
+winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ qperm,
+                       const float4* __restrict__ ctri, const float4* __restrict__ nodes,
+                       const int* __restrict__ super_off, float* __restrict__ partial, int V, int K, int NS,
+                       int supers_per_split, int S) {
+    __shared__ float s_acc[WC_WARPS][32 * 33];
+    const int b = blockIdx.z, split = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * WC_WARPS + warp) * 32 + lane;
+    if (i - lane >= V) return;                                   // whole warp past the end
+    const int qi = qperm[min(i, V - 1)];
+    const float* vb = verts + (size_t)b * V * 3;
+    const float px = vb[3 * qi], py = vb[3 * qi + 1], pz = vb[3 * qi + 2];
+    float* acc = s_acc[warp];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc[q * 33 + lane] = 0.f;
+    __syncwarp();
+
+    const float4* nb = nodes + (size_t)b * (NS + K) * WC_NODE_F4;
+    const float4* tb = ctri + (size_t)b * K * WC_LEAF * 3;
+    const int s0 = split * supers_per_split, s1 = min(NS, s0 + supers_per_split);
+    float far = 0.f;
+    for (int s = s0; s < s1; ++s) {
+        const float4* rec = nb + (size_t)s * WC_NODE_F4;
+        const float4 c = __ldg(rec);
+        const float x = c.x - px, y = c.y - py, z = c.z - pz;
+        const float d2 = fmaf(z, z, fmaf(y, y, x * x));
+        if (!__any_sync(0xffffffffu, d2 < c.w)) {
+            far += node_far_field(rec, x, y, z, d2);
+            continue;
+        }
+        const int l0 = __ldg(super_off + s), l1 = __ldg(super_off + s + 1);
+        for (int l = l0; l < l1; ++l) {
+            const float4* lrec = nb + (size_t)(NS + l) * WC_NODE_F4;
+            const float4 lc = __ldg(lrec);
+            const float lx = lc.x - px, ly = lc.y - py, lz = lc.z - pz;
+            const float ld2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+            const bool near = ld2 < lc.w;
+            unsigned m = __ballot_sync(0xffffffffu, near);
+            if (m != 0xffffffffu) {
+                const float v = node_far_field(lrec, lx, ly, lz, ld2);
+                far += near ? 0.f : v;
+            }
+            if (m != 0u) {                                       // lanes become faces of this leaf
+                const float4* t = tb + ((size_t)l * WC_LEAF + lane) * 3;
+                const float4 A = __ldg(t), Bv = __ldg(t + 1), C = __ldg(t + 2);
+                while (m != 0u) {
+                    const int q = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const float qx = __shfl_sync(0xffffffffu, px, q), qy = __shfl_sync(0xffffffffu, py, q),
+                                qz = __shfl_sync(0xffffffffu, pz, q);
+                    const float sa = half_solid_angle(qx, qy, qz, A, Bv, C);
+                    acc[q * 33 + lane] += (A.w != 0.f) ? sa : 0.f;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    float near_sum = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) near_sum += acc[lane * 33 + j];
+    if (i < V) partial[((size_t)b * S + split) * V + qi] = far + near_sum;
+}
+
+// sums the split partials in a fixed order, scales by 1 / (2 pi) and lists the queries whose value is
+// within WC_MARGIN of the 0.99 threshold of losses.py:82 for exact re-evaluation
+__global__ void cluster_finalize_kernel(const float* __restrict__ partial, int V, int S, float* __restrict__ winding,
+                                        int* __restrict__ refine_list) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= V) return;
+    const float* p = partial + (size_t)b * S * V + q;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += p[(size_t)s * V];
+    const float w = acc * 0.159154943091895336f;
+    winding[(size_t)b * V + q] = w;
+    if (fabsf(w - 0.99f) < WC_MARGIN) {
+        const int k = atomicAdd(refine_list, 1);
+        refine_list[1 + k] = b * V + q;
+    }
+}
+
+// exact winding number (all faces, one lane per face slot) of every listed query; one CTA per entry,
+// its warps stride over the leaves and their partial sums are combined in a fixed order
+__global__ void __launch_bounds__(256)
+cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict__ ctri, int V, int K,
+                      const int* __restrict__ refine_list, float* __restrict__ winding) {
+    __shared__ float s_part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int count = refine_list[0];
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const int id = refine_list[1 + e];
+        const int b = id / V, q = id - b * V;
+        const float* p = verts + ((size_t)b * V + q) * 3;
+        const float px = p[0], py = p[1], pz = p[2];
+        const float4* t = ctri + (((size_t)b * K + warp) * WC_LEAF + lane) * 3;
+        float acc = 0.f;
+#pragma unroll 2
+        for (int l = warp; l < K; l += 8, t += 8 * WC_LEAF * 3) {
+            const float4 A = __ldg(t), Bv = __ldg(t + 1), C = __ldg(t + 2);
+            const float sa = half_solid_angle(px, py, pz, A, Bv, C);
+            acc += (A.w != 0.f) ? sa : 0.f;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_part[w];
+            winding[(size_t)b * V + q] = tot * 0.159154943091895336f;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int cluster_splits(int B, int V, int NS, int sm_count) {
+    const int qtiles = cdiv(V, WC_WARPS * 32);
+    const long long want = (long long)sm_count * 6;                     // CTAs in flight
+    int S = (int)((want + (long long)qtiles * B - 1) / ((long long)qtiles * B));
+    S = std::max(1, std::min(S, NS));
+    const int per = cdiv(NS, S);
+    return cdiv(NS, per);
+}
+
+int launch_winding_clusters(const ClusterJob& j, cudaStream_t st) {
+    if (j.B == 0 || j.V == 0) return 0;
+    {
+        dim3 grid(cdiv(j.NS + j.K, 4), j.B);
+        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.super_off, j.K, j.NS, j.ctri,
+                                                  j.nodes);
+        TUCH_LAUNCH_CHECK(); count_launch();
+    }
+    TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
+    {
+        const int per = cdiv(j.NS, j.S);
+        dim3 grid(cdiv(j.V, WC_WARPS * 32), j.S, j.B);
+        KernelTimer timer("winding_kernel", st);
+        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(j.verts, j.qperm, j.ctri, j.nodes, j.super_off, j.partial,
+                                                               j.V, j.K, j.NS, per, j.S);
+    }
+    TUCH_LAUNCH_CHECK(); count_launch();
+    {
+        dim3 grid(cdiv(j.V, 256), j.B);
+        cluster_finalize_kernel<<<grid, 256, 0, st>>>(j.partial, j.V, j.S, j.winding, j.refine_list);
+        TUCH_LAUNCH_CHECK(); count_launch();
+    }
+    {
+        KernelTimer timer("winding_refine_kernel", st);
+        cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(j.verts, j.ctri, j.V, j.K, j.refine_list, j.winding);
+    }
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+}  // namespace tuch

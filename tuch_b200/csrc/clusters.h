@@ -1,0 +1,43 @@
+// Internal: face-cluster hierarchy and the far-field ("fast winding number") kernels (clusters.cu).
+#pragma once
+#include <vector>
+
+#include "kernels.h"
+
+namespace tuch {
+
+constexpr int WC_LEAF = 32;          // faces per leaf cluster = one warp lane per face in the near pass
+constexpr int WC_SUPER_LEAVES = 8;   // leaves per super-cluster (second level of the far field)
+constexpr int WC_NODE_F4 = 7;        // float4 per node record (centre + radius, scaled moments)
+constexpr int WC_WARPS = 8;          // warps per CTA of the winding kernel; one query per lane
+constexpr float WC_BETA = 2.0f;      // a node is "far" for a query beyond WC_BETA x its radius
+constexpr float WC_MARGIN = 0.03f;   // |w - 0.99| below this is re-evaluated exactly (8 x the worst far-field
+                                     // error measured at WC_BETA = 2: 3.8e-3)
+
+// Host-side hierarchy of one mesh topology, built from the faces and ONE set of vertex positions
+// (the template, or the first body seen).
+struct ClusterTree {
+    std::vector<int> leaf_face;      // [K][WC_LEAF] face id or -1 (padding)
+    std::vector<int> super_off;      // [NS + 1] leaf ranges of the super-clusters
+    std::vector<int> qperm;          // [V] vertex ids in cluster order (queries of a warp are neighbours)
+    int K = 0, NS = 0;
+};
+int build_cluster_tree(const int* faces, int F, int V, const float* verts, ClusterTree& out);
+
+struct ClusterJob {
+    const float* verts;              // [B][V][3] mesh vertices (also the queries, in qperm order)
+    const int* faces;                // [F][3]
+    const int* leaf_face;            // [K][WC_LEAF]
+    const int* super_off;            // [NS + 1]
+    const int* qperm;                // [V]
+    float4* ctri;                    // [B][K][WC_LEAF][3] scratch: packed corner triples per leaf
+    float4* nodes;                   // [B][NS + K][WC_NODE_F4] scratch: super records first, then leaves
+    float* partial;                  // [B][S][V] scratch
+    float* winding;                  // [B][V] out
+    int* refine_list;                // [1 + B * V] scratch: count, then b * V + q entries
+    int B, V, K, NS, S;
+};
+int cluster_splits(int B, int V, int NS, int sm_count);
+int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);
+
+}  // namespace tuch

@@ -80,6 +80,21 @@ def strip_stream(faces):
 
 
 # ------------------------------------------------------------------ a1-a3 forward kernels
+def cluster_tree(faces, verts):
+    """Host-only: the face-cluster hierarchy of clusters.cu -> dict(leaf_face[K,32], super_off[NS+1], qperm[V])."""
+    f = _i32_host(np.asarray(faces).reshape(-1, 3))
+    v = np.ascontiguousarray(np.asarray(verts).reshape(-1, 3), dtype=np.float32)
+    k, ns = C.c_int32(0), C.c_int32(0)
+    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), None, 0, None, 0, None, C.byref(k), C.byref(ns)),
+          'tuch_cluster_tree_host')
+    leaf = np.empty((k.value, 32), np.int32)
+    sup = np.empty(ns.value + 1, np.int32)
+    qp = np.empty(len(v), np.int32)
+    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), _hp(leaf), k.value, _hp(sup), ns.value, _hp(qp),
+                                       C.byref(k), C.byref(ns)), 'tuch_cluster_tree_host')
+    return dict(leaf_face=leaf, super_off=sup, qperm=qp)
+
+
 def pairwise_dist(x, y, squared=True):
     x, y = _f32(x, 'x'), _f32(y, 'y')
     if x.dim() != 3 or y.dim() != 3 or x.shape[2] != 3 or y.shape[2] != 3 or x.shape[0] != y.shape[0]:
@@ -164,6 +179,27 @@ class Topology:
     @property
     def handle(self):
         return self._h
+
+    # winding-number evaluation mode of contact_query (include/tuch_b200.h)
+    WINDING_EXACT, WINDING_FAST = 0, 1
+
+    def set_template(self, verts):
+        """Clusters the faces on these [V,3] positions (the model's v_template) for the hierarchical
+        winding kernel; without it the first queried body is used."""
+        v = verts.detach().cpu().numpy() if isinstance(verts, torch.Tensor) else np.asarray(verts)
+        v = np.ascontiguousarray(v.reshape(-1, 3), dtype=np.float32)
+        if v.shape != (self.V, 3):
+            raise TuchError('template must be [%d,3], got %s' % (self.V, tuple(v.shape)))
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_set_template(self._h, _hp(v)), 'tuch_topology_set_template')
+
+    def set_winding_mode(self, mode):
+        check(lib().tuch_topology_set_winding_mode(self._h, int(mode)), 'tuch_topology_set_winding_mode')
+
+    def cluster_stats(self):
+        k, ns = C.c_int32(0), C.c_int32(0)
+        check(lib().tuch_topology_cluster_stats(self._h, C.byref(k), C.byref(ns)), 'tuch_topology_cluster_stats')
+        return dict(leaves=int(k.value), supers=int(ns.value))
 
     # geomask = geodist > geothres (smplifydc.py:65)
     def set_geodist(self, geodist, geothres):

@@ -57,6 +57,9 @@ class ContactFit:
         global_orient.requires_grad_(True)
         self.opt = _Adam([body_pose, global_orient], lr=owner.step_size)
         self.topo = topology_for(owner.geomask, owner.face_tensor, owner.smpl.get_num_verts(), contactlist, segments)
+        tmpl = getattr(owner.smpl, 'v_template', None)
+        if tmpl is not None and self.topo.F > 0 and self.topo.cluster_stats()['leaves'] == 0:
+            self.topo.set_template(tmpl)           # face clusters of the hierarchical winding kernel
         self.args = dict(camera_t=camera_translation, camera_center=camera_center, joints_2d=joints_2d,
                          joints_conf=joints_conf, pose_prior=owner.pose_prior, cdict=contactlist,
                          gt_contact=gt_contact, ignore_idxs=ignore_idxs, has_discrete_contact=has_discrete_contact,
