@@ -126,11 +126,13 @@ int tuch_topology_set_template(tuch_topology* topo, const float* verts_host);
 int tuch_topology_set_winding_mode(tuch_topology* topo, int mode);
 int tuch_topology_cluster_stats(const tuch_topology* topo, int* n_leaves, int* n_supers);
 /* the hierarchy builder without a device: leaf_face_out[n_leaves][32] (face id or -1),
- * super_off_out[n_supers + 1] (leaf ranges), qperm_out[V] (vertex ids in cluster order); output
- * pointers may be NULL to query the counts only. */
+ * super_off_out[n_supers + 1] (leaf ranges), vtile_out[n_tiles][32] (vertex tiles: the 32 neighbouring
+ * vertices one warp queries / one word of the cluster-ordered geodesic mask covers; -1 = padding);
+ * output pointers may be NULL to query the counts only. */
 int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float* verts_host,
                            int32_t* leaf_face_out, int leaf_capacity, int32_t* super_off_out,
-                           int super_capacity, int32_t* qperm_out, int* n_leaves, int* n_supers);
+                           int super_capacity, int32_t* vtile_out, int tile_capacity, int* n_leaves,
+                           int* n_supers, int* n_tiles);
 
 /* ------------------------------------------------------------------ fused self-contact query
  * Replaces, for every body of the batch, losses.py:76-93 / loss.py:256-270:

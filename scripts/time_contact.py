@@ -51,5 +51,12 @@ print('fast winding %.3f ms (exact %.3f ms): max err %.2e, flag mismatches %d, i
 for k in ('winding_kernel', 'winding_refine_kernel', 'nearest_kernel'):
     print(' ', k, ops.kernel_time(k))
 tn = timeit(lambda: topo.contact_query(verts, use_segments=False, want_winding=False))
+n_fast = topo.contact_query(verts, use_segments=False, want_winding=False)
+topo_old = ops.Topology(m['faces'], V, dev)
+topo_old.set_geodist(geo, 0.3)
+topo_old.set_winding_mode(topo_old.WINDING_EXACT)
+t_old = timeit(lambda: topo_old.contact_query(verts, use_segments=False, want_winding=False))
+n_old = topo_old.contact_query(verts, use_segments=False, want_winding=False)
+print('nearest: tiles %.3f ms, dense %.3f ms, identical %s' % (tn, t_old, bool(torch.equal(n_fast['argmin'], n_old['argmin']) and torch.equal(n_fast['min_sq'], n_old['min_sq']))))
 pairs = B * V * 13776
 print('B=%d winding %.3f ms (%.1f Gpairs/s)  nearest %.3f ms (%.1f Gpairs/s)' % (B, tw, pairs / tw / 1e6, tn, B * V * V / tn / 1e6))

@@ -13,14 +13,14 @@ def check_tree(model):
     faces = model['faces']
     F, V = len(faces), len(model['v_template'])
     t = tree_for(model)
-    leaf, sup, qp = t['leaf_face'], t['super_off'], t['qperm']
+    leaf, sup, vt = t['leaf_face'], t['super_off'], t['vtile']
     ids = leaf[leaf >= 0]
     assert len(ids) == F and np.array_equal(np.sort(ids), np.arange(F))            # a partition of the faces
-    assert np.array_equal(np.sort(qp), np.arange(V))                               # a permutation of the vertices
+    assert np.array_equal(np.sort(vt[vt >= 0]), np.arange(V))                      # a partition of the vertices
     assert sup[0] == 0 and sup[-1] == len(leaf) and np.all(np.diff(sup) >= 1) and np.all(np.diff(sup) <= 24)
-    for row in leaf:                                                               # padding only at the end
+    for row in list(leaf) + list(vt):                                             # ascending ids, padding only at the end
         n = int((row >= 0).sum())
-        assert n >= 1 and np.all(row[:n] >= 0) and np.all(row[n:] < 0)
+        assert n >= 1 and np.all(row[:n] >= 0) and np.all(row[n:] < 0) and np.all(np.diff(row[:n]) > 0)
     return t
 
 
@@ -29,7 +29,7 @@ def test_tree_small_and_full():
     check_tree(syn.make_body_model(10, 12, seed=0))
     t = check_tree(syn.make_lattice_body_model(seed=0))
     # near-minimal leaf count: the far field costs one evaluation per leaf
-    assert len(t['leaf_face']) <= 1.15 * (13776 // 32 + 1)
+    assert len(t['leaf_face']) <= 1.15 * (13776 // 32 + 1) and len(t['vtile']) <= 1.15 * (6890 // 32 + 1)
     check_tree(syn.make_body_model(84, 82, seed=0))
 
 
@@ -42,8 +42,8 @@ def test_tree_disconnected_and_tiny():
     faces = np.concatenate([tet, tet + 4, [[8, 9, 10]]])
     t = ops.cluster_tree(faces, verts)
     assert sorted(t['leaf_face'][t['leaf_face'] >= 0].tolist()) == list(range(9))
-    comps = [set(r[r >= 0].tolist()) for r in t['leaf_face']]
-    assert {0, 1, 2, 3} in comps and {4, 5, 6, 7} in comps and {8} in comps        # components are never mixed
+    assert sorted(t['vtile'][t['vtile'] >= 0].tolist()) == list(range(11))
+    assert len(t['leaf_face']) == 1 and len(t['vtile']) == 1                       # small components share a leaf
 
 
 def test_far_field_expansion_matches_exact_solid_angles():

@@ -150,7 +150,11 @@ def test_contact_fitting_loss_matches_reference_golden(ctx, tag, eu, use_seg, w,
     assert rel(go.grad, g[tag + '/g_orient']) < 2e-4
     if tag == 'thres02_seg':
         assert np.array_equal(aux['argmin'].cpu().numpy(), g['argmin'])
-        assert np.abs(aux['winding'].cpu().numpy() - g['winding']).max() < 2e-5
+        # default winding mode is hierarchical: values within the far-field error, flags identical
+        w = aux['winding'].cpu().numpy()
+        assert np.abs(w - g['winding']).max() < 5e-3
+        safe = np.abs(g['winding'] - 0.99) > 1e-4
+        assert np.array_equal((w <= 0.99)[safe], (g['winding'] <= 0.99)[safe])
 
 
 def test_contact_loss_modes_against_oracle(ctx):

@@ -284,7 +284,7 @@ static void free_segments(tuch_topology* t) {
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
-    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_qperm);
+    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_vtile); free_dev(t->d_maskP);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -311,20 +311,34 @@ TUCH_EXPORT int tuch_strip_stream_host(const int32_t* faces_host, int F, int32_t
     return 0;
 }
 
-static int install_clusters(tuch_topology* t, const float* verts_host) {
+// (re)builds the cluster-ordered copy of the geodesic mask once both inputs exist
+static int refresh_permuted_mask(tuch_topology* t, cudaStream_t st) {
+    t->has_maskP = false;
+    if (!t->has_mask || !t->has_clusters) return 0;
+    const int T = t->T;
+    free_dev(t->d_maskP);
+    t->d_maskP = nullptr;
+    TUCH_CUDA(cudaMalloc((void**)&t->d_maskP, sizeof(uint32_t) * (size_t)T * T * 32));
+    if (int rc = launch_permute_mask(t->d_maskT, t->Vq, t->d_vtile, T, t->d_maskP, st)) return rc;
+    t->has_maskP = true;
+    return 0;
+}
+
+static int install_clusters(tuch_topology* t, const float* verts_host, cudaStream_t st = nullptr) {
     std::vector<int> faces((size_t)t->F * 3);
     TUCH_CUDA(cudaMemcpy(faces.data(), t->d_faces, faces.size() * sizeof(int), cudaMemcpyDeviceToHost));
     ClusterTree tree;
     if (int rc = build_cluster_tree(faces.data(), t->F, t->V, verts_host, tree)) return rc;
-    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_qperm);
-    t->d_leaf_face = t->d_super_off = t->d_qperm = nullptr;
+    TUCH_CUDA(cudaDeviceSynchronize());            // queued work may still read the old hierarchy
+    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_vtile);
+    t->d_leaf_face = t->d_super_off = t->d_vtile = nullptr;
     t->has_clusters = false;
     if (int rc = upload(tree.leaf_face.data(), tree.leaf_face.size(), &t->d_leaf_face)) return rc;
     if (int rc = upload(tree.super_off.data(), tree.super_off.size(), &t->d_super_off)) return rc;
-    if (int rc = upload(tree.qperm.data(), tree.qperm.size(), &t->d_qperm)) return rc;
-    t->K = tree.K; t->NS = tree.NS;
+    if (int rc = upload(tree.vtile.data(), tree.vtile.size(), &t->d_vtile)) return rc;
+    t->K = tree.K; t->NS = tree.NS; t->T = tree.T;
     t->has_clusters = true;
-    return 0;
+    return refresh_permuted_mask(t, st);
 }
 
 TUCH_EXPORT int tuch_topology_set_template(tuch_topology* t, const float* verts_host) {
@@ -337,7 +351,8 @@ TUCH_EXPORT int tuch_topology_set_template(tuch_topology* t, const float* verts_
 
 TUCH_EXPORT int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float* verts_host,
                                        int32_t* leaf_face_out, int leaf_capacity, int32_t* super_off_out,
-                                       int super_capacity, int32_t* qperm_out, int* n_leaves, int* n_supers) {
+                                       int super_capacity, int32_t* vtile_out, int tile_capacity, int* n_leaves,
+                                       int* n_supers, int* n_tiles) {
     TUCH_REQUIRE(faces_host != nullptr && verts_host != nullptr && F > 0 && V > 0, "tuch_cluster_tree_host: need a mesh");
     for (size_t i = 0; i < (size_t)F * 3; ++i)
         TUCH_REQUIRE(faces_host[i] >= 0 && faces_host[i] < V, "tuch_cluster_tree_host: face index %d out of range", faces_host[i]);
@@ -345,6 +360,7 @@ TUCH_EXPORT int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, 
     if (int rc = build_cluster_tree(faces_host, F, V, verts_host, tree)) return rc;
     if (n_leaves) *n_leaves = tree.K;
     if (n_supers) *n_supers = tree.NS;
+    if (n_tiles) *n_tiles = tree.T;
     if (leaf_face_out != nullptr) {
         TUCH_REQUIRE(leaf_capacity >= tree.K, "tuch_cluster_tree_host: leaf capacity %d < %d", leaf_capacity, tree.K);
         std::copy(tree.leaf_face.begin(), tree.leaf_face.end(), leaf_face_out);
@@ -353,7 +369,10 @@ TUCH_EXPORT int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, 
         TUCH_REQUIRE(super_capacity >= tree.NS, "tuch_cluster_tree_host: super capacity %d < %d", super_capacity, tree.NS);
         std::copy(tree.super_off.begin(), tree.super_off.end(), super_off_out);
     }
-    if (qperm_out != nullptr) std::copy(tree.qperm.begin(), tree.qperm.end(), qperm_out);
+    if (vtile_out != nullptr) {
+        TUCH_REQUIRE(tile_capacity >= tree.T, "tuch_cluster_tree_host: tile capacity %d < %d", tile_capacity, tree.T);
+        std::copy(tree.vtile.begin(), tree.vtile.end(), vtile_out);
+    }
     return 0;
 }
 
@@ -386,14 +405,14 @@ TUCH_EXPORT int tuch_topology_set_geodist(tuch_topology* t, const float* geodist
     if (int rc = ensure_mask(t)) return rc;
     if (int rc = launch_pack_mask(nullptr, geodist, geothres, t->V, t->Vq, t->W, t->d_maskT, (cudaStream_t)stream)) return rc;
     t->has_mask = true;
-    return 0;
+    return refresh_permuted_mask(t, (cudaStream_t)stream);
 }
 TUCH_EXPORT int tuch_topology_set_geomask(tuch_topology* t, const uint8_t* geomask, void* stream) {
     TUCH_REQUIRE(t && geomask, "tuch_topology_set_geomask: null pointer");
     if (int rc = ensure_mask(t)) return rc;
     if (int rc = launch_pack_mask(geomask, nullptr, 0.f, t->V, t->Vq, t->W, t->d_maskT, (cudaStream_t)stream)) return rc;
     t->has_mask = true;
-    return 0;
+    return refresh_permuted_mask(t, (cudaStream_t)stream);
 }
 
 TUCH_EXPORT int tuch_topology_set_regions(tuch_topology* t, int n_regions, const int32_t* off, const int32_t* ids,
@@ -536,11 +555,11 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
             bool finite = true;
             for (float x : h) finite = finite && std::isfinite(x);
             if (finite)
-                if (int rc = install_clusters(const_cast<tuch_topology*>(t), h.data())) return rc;   // lazily built cache
+                if (int rc = install_clusters(const_cast<tuch_topology*>(t), h.data(), st)) return rc;   // lazily built cache
         }
     }
     const bool fast = want_w && t->winding_mode == TUCH_WINDING_FAST && t->has_clusters;
-    const int S = !want_w ? 1 : fast ? cluster_splits(B, V, t->NS, sm_count()) : strip_splits(B, V, Lp, sm_count());
+    const int S = !want_w ? 1 : fast ? cluster_splits(B, t->T, t->NS, sm_count()) : strip_splits(B, V, Lp, sm_count());
 
     Scratch sc;
     const size_t h_tri = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * 3 * (size_t)B * t->K * WC_LEAF
@@ -548,7 +567,11 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     const size_t h_info = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * WC_NODE_F4 * (size_t)B * (t->NS + t->K)
                                                      : sizeof(float4) * (size_t)B * (Lp / WS_TILE));
     const size_t h_ref = sc.plan(fast ? sizeof(int) * ((size_t)B * V + 1) : 0);
-    const size_t h_v4 = sc.plan((want_nn && !vert4_out) ? sizeof(float4) * (size_t)B * Vp : 0);
+    const bool nn_tiles = want_nn && t->has_maskP && vert4_out == nullptr;
+    const int T = t->T;
+    const size_t h_v4 = sc.plan(!want_nn ? 0 : nn_tiles ? sizeof(float4) * (size_t)B * T * 32
+                                                        : (vert4_out ? 0 : sizeof(float4) * (size_t)B * Vp));
+    const size_t h_tinfo = sc.plan(nn_tiles ? sizeof(float4) * 2 * (size_t)B * T : 0);
     const size_t h_par = sc.plan(want_w ? sizeof(float) * (size_t)B * S * V : 0);
     const size_t h_w = sc.plan((want_w && !winding) ? sizeof(float) * (size_t)B * V : 0);
     const size_t h_any = sc.plan(segs ? (size_t)B : 0);
@@ -560,15 +583,15 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
 
     float4* strip4 = want_w ? sc.get<float4>(h_tri) : nullptr;
     float4* vert4 = want_nn ? (vert4_out ? vert4_out : sc.get<float4>(h_v4)) : vert4_out;
-    if (vert4 != nullptr)
+    if (vert4 != nullptr && !nn_tiles)
         if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, nullptr, vert4, st)) return rc;
 
     if (want_w) {
         float* w = winding ? winding : sc.get<float>(h_w);
         float4* info = sc.get<float4>(h_info);
         if (fast) {
-            ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_super_off, t->d_qperm, strip4, info,
-                         sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NS, S};
+            ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_super_off, t->d_vtile, strip4, info,
+                         sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NS, S, t->T};
             if (int rc = launch_winding_clusters(j, st)) return rc;
         } else {
             if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
@@ -586,7 +609,11 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     if (want_nn) {
         int* am = argmin ? argmin : sc.get<int>(h_am);
         float* mn = min_sq ? min_sq : sc.get<float>(h_mn);
-        if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;
+        if (nn_tiles) {
+            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_vtile, B, V, T, vert4, sc.get<float4>(h_tinfo), am, mn, st)) return rc;
+        } else {
+            if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;
+        }
     }
     return 0;
 }

@@ -32,40 +32,33 @@ namespace tuch {
 // ------------------------------------------------------------------------------------------
 namespace {
 
+// Recursive bisection of a set of items (faces or vertices) that live on the mesh: connected components
+// are never mixed, a connected set is cut at a balanced position along the principal axis of its item
+// positions, and small pieces cut off by the plane are handed to the other half.  Leaves hold <= `leaf`
+// items (ascending ids); optionally consecutive leaves are grouped into supers of <= `super_leaves`.
 struct TreeBuilder {
-    const int* faces;
-    int F;
-    std::vector<float> cen;                  // [F][3] face centroids
-    std::vector<int> adj_off, adj;           // face adjacency (shared edge), CSR
-    std::vector<int> stamp;                  // membership marks
+    int N = 0, leaf = 32, super_leaves = 0;
+    std::vector<float> cen;                  // [N][3] item positions
+    std::vector<int> adj_off, adj;           // item adjacency, CSR
+    std::vector<int> stamp;
     int cur_stamp = 0;
-    ClusterTree* out;
+    std::vector<int>* leaf_items = nullptr;  // [n_leaves][leaf], -1 = padding
+    std::vector<int>* super_off = nullptr;
+    int n_leaves = 0, n_supers = 0;
 
-    void build_adjacency() {
-        std::unordered_map<uint64_t, std::vector<int>> ef;
-        ef.reserve((size_t)F * 2);
-        auto key = [](int u, int v) {
-            const uint64_t a = (uint64_t)std::min(u, v), b = (uint64_t)std::max(u, v);
-            return (a << 32) | b;
-        };
-        for (int t = 0; t < F; ++t)
-            for (int e = 0; e < 3; ++e) ef[key(faces[3 * t + e], faces[3 * t + (e + 1) % 3])].push_back(t);
-        std::vector<std::vector<int>> nb(F);
-        for (int t = 0; t < F; ++t)
-            for (int e = 0; e < 3; ++e)
-                for (int g : ef[key(faces[3 * t + e], faces[3 * t + (e + 1) % 3])])
-                    if (g != t) nb[t].push_back(g);
-        adj_off.assign(F + 1, 0);
-        for (int t = 0; t < F; ++t) {
+    void set_adjacency(std::vector<std::vector<int>>& nb) {
+        adj_off.assign(N + 1, 0);
+        for (int t = 0; t < N; ++t) {
             std::sort(nb[t].begin(), nb[t].end());
             nb[t].erase(std::unique(nb[t].begin(), nb[t].end()), nb[t].end());
             adj_off[t + 1] = adj_off[t] + (int)nb[t].size();
         }
-        adj.resize(adj_off[F]);
-        for (int t = 0; t < F; ++t) std::copy(nb[t].begin(), nb[t].end(), adj.begin() + adj_off[t]);
+        adj.resize(adj_off[N]);
+        for (int t = 0; t < N; ++t) std::copy(nb[t].begin(), nb[t].end(), adj.begin() + adj_off[t]);
+        stamp.assign(N, 0);
     }
 
-    // connected components of `fs` (sorted by their smallest face id, faces ascending inside)
+    // connected components of `fs` (ordered by their smallest id, ids ascending inside)
     std::vector<std::vector<int>> components(const std::vector<int>& fs) {
         const int in = ++cur_stamp;
         for (int f : fs) stamp[f] = in;
@@ -89,25 +82,32 @@ struct TreeBuilder {
     }
 
     void emit_leaf(const std::vector<int>& fs) {
-        for (int i = 0; i < WC_LEAF; ++i) out->leaf_face.push_back(i < (int)fs.size() ? fs[i] : -1);
-        ++out->K;
+        for (int i = 0; i < leaf; ++i) leaf_items->push_back(i < (int)fs.size() ? fs[i] : -1);
+        ++n_leaves;
     }
 
     void split(std::vector<int> fs, bool in_super) {           // fs ascending
         const int n = (int)fs.size();
-        const int n_leaves = (n + WC_LEAF - 1) / WC_LEAF;
-        if (!in_super && n_leaves <= WC_SUPER_LEAVES) {
-            out->super_off.push_back(out->K);
-            ++out->NS;
+        const int want_leaves = (n + leaf - 1) / leaf;
+        if (super_leaves > 0 && !in_super && want_leaves <= super_leaves) {
+            super_off->push_back(n_leaves);
+            ++n_supers;
             in_super = true;
         }
         std::vector<std::vector<int>> comps = components(fs);
         if (comps.size() > 1) {
-            for (auto& c : comps) split(std::move(c), in_super);
+            // pack small components together (a leaf may hold several of them) as long as they fit
+            std::vector<int> bag;
+            for (auto& c : comps) {
+                if ((int)c.size() > leaf) { split(std::move(c), in_super); continue; }
+                if ((int)(bag.size() + c.size()) > leaf) { std::sort(bag.begin(), bag.end()); emit_leaf(bag); bag.clear(); }
+                bag.insert(bag.end(), c.begin(), c.end());
+            }
+            if (!bag.empty()) { std::sort(bag.begin(), bag.end()); emit_leaf(bag); }
             return;
         }
-        if (n <= WC_LEAF) { emit_leaf(fs); return; }
-        // principal axis of the face centroids (power iteration on the 3x3 covariance, fp64)
+        if (n <= leaf) { emit_leaf(fs); return; }
+        // principal axis of the item positions (power iteration on the 3x3 covariance, fp64)
         double mean[3] = {0, 0, 0};
         for (int f : fs) for (int a = 0; a < 3; ++a) mean[a] += cen[3 * f + a];
         for (int a = 0; a < 3; ++a) mean[a] /= n;
@@ -131,26 +131,26 @@ struct TreeBuilder {
             key[i] = {(cen[3 * f] - mean[0]) * v[0] + (cen[3 * f + 1] - mean[1]) * v[1] + (cen[3 * f + 2] - mean[2]) * v[2], f};
         }
         std::sort(key.begin(), key.end());
-        const int left_leaves = (n_leaves + 1) / 2;
-        int n_left = (int)std::llround((double)n * left_leaves / n_leaves);
+        const int left_leaves = (want_leaves + 1) / 2;
+        int n_left = (int)std::llround((double)n * left_leaves / want_leaves);
         n_left = std::max(1, std::min(n - 1, n_left));
         std::vector<int> l(n_left), r(n - n_left);
         for (int i = 0; i < n; ++i) (i < n_left ? l[i] : r[i - n_left]) = key[i].second;
         std::sort(l.begin(), l.end());
         std::sort(r.begin(), r.end());
-        // a planar cut through a triangulated patch leaves ragged fragments (faces whose neighbours all
+        // a planar cut through a triangulated patch leaves ragged fragments (items whose neighbours all
         // fell on the other side): hand small cut-off pieces to the other half instead of letting them
         // become leaves of their own
         auto give_fragments = [&](std::vector<int>& from, std::vector<int>& to) {
-            std::vector<std::vector<int>> comps = components(from);
-            if (comps.size() < 2) return;
+            std::vector<std::vector<int>> cs = components(from);
+            if (cs.size() < 2) return;
             size_t big = 0;
-            for (size_t c = 1; c < comps.size(); ++c) if (comps[c].size() > comps[big].size()) big = c;
+            for (size_t c = 1; c < cs.size(); ++c) if (cs[c].size() > cs[big].size()) big = c;
             const size_t small = std::max<size_t>(3, from.size() / 8);
             std::vector<int> keep;
-            for (size_t c = 0; c < comps.size(); ++c) {
-                std::vector<int>& dst = (c != big && comps[c].size() <= small && to.size() + comps[c].size() < (size_t)n) ? to : keep;
-                dst.insert(dst.end(), comps[c].begin(), comps[c].end());
+            for (size_t c = 0; c < cs.size(); ++c) {
+                std::vector<int>& dst = (c != big && cs[c].size() <= small) ? to : keep;
+                dst.insert(dst.end(), cs[c].begin(), cs[c].end());
             }
             from.swap(keep);
             std::sort(from.begin(), from.end());
@@ -158,50 +158,72 @@ struct TreeBuilder {
         };
         give_fragments(l, r);
         give_fragments(r, l);
-        if (l.empty() || r.empty()) {           // cannot happen for a connected set; keep the recursion finite
-            std::vector<int>& all = l.empty() ? r : l;
-            std::vector<int> a(all.begin(), all.begin() + all.size() / 2), b2(all.begin() + all.size() / 2, all.end());
-            l.swap(a); r.swap(b2);
-        }
         split(std::move(l), in_super);
         split(std::move(r), in_super);
     }
+
+    void run() {
+        std::vector<int> all(N);
+        std::iota(all.begin(), all.end(), 0);
+        split(std::move(all), false);
+        if (super_off) super_off->push_back(n_leaves);
+    }
 };
+
+uint64_t edge_key(int u, int v) {
+    const uint64_t a = (uint64_t)std::min(u, v), b = (uint64_t)std::max(u, v);
+    return (a << 32) | b;
+}
 
 }  // namespace
 
 int build_cluster_tree(const int* faces, int F, int V, const float* verts, ClusterTree& out) {
     out = ClusterTree();
     TUCH_REQUIRE(F > 0 && V > 0 && faces && verts, "build_cluster_tree: empty mesh");
-    TreeBuilder tb;
-    tb.faces = faces; tb.F = F; tb.out = &out;
-    tb.cen.resize((size_t)F * 3);
+    std::unordered_map<uint64_t, std::vector<int>> ef;
+    ef.reserve((size_t)F * 2);
     for (int t = 0; t < F; ++t)
-        for (int a = 0; a < 3; ++a)
-            tb.cen[3 * t + a] = (verts[3 * faces[3 * t] + a] + verts[3 * faces[3 * t + 1] + a] + verts[3 * faces[3 * t + 2] + a]) / 3.f;
-    tb.build_adjacency();
-    tb.stamp.assign(F, 0);
-    std::vector<int> all(F);
-    std::iota(all.begin(), all.end(), 0);
-    tb.split(std::move(all), false);
-    out.super_off.push_back(out.K);
-    // self-check: every face in exactly one leaf
+        for (int e = 0; e < 3; ++e) ef[edge_key(faces[3 * t + e], faces[3 * t + (e + 1) % 3])].push_back(t);
+    {   // faces: neighbours share an edge
+        TreeBuilder tb;
+        tb.N = F; tb.leaf = WC_LEAF; tb.super_leaves = WC_SUPER_LEAVES;
+        tb.leaf_items = &out.leaf_face; tb.super_off = &out.super_off;
+        tb.cen.resize((size_t)F * 3);
+        for (int t = 0; t < F; ++t)
+            for (int a = 0; a < 3; ++a)
+                tb.cen[3 * t + a] = (verts[3 * faces[3 * t] + a] + verts[3 * faces[3 * t + 1] + a] + verts[3 * faces[3 * t + 2] + a]) / 3.f;
+        std::vector<std::vector<int>> nb(F);
+        for (auto& kv : ef)
+            for (int x : kv.second) for (int y : kv.second) if (x != y) nb[x].push_back(y);
+        tb.set_adjacency(nb);
+        tb.run();
+        out.K = tb.n_leaves; out.NS = tb.n_supers;
+    }
+    {   // vertices: neighbours share an edge; vertices without faces end up in tiles of their own
+        TreeBuilder tb;
+        tb.N = V; tb.leaf = 32;
+        tb.leaf_items = &out.vtile;
+        tb.cen.assign(verts, verts + (size_t)V * 3);
+        std::vector<std::vector<int>> nb(V);
+        for (auto& kv : ef) {
+            const int u = (int)(kv.first >> 32), v = (int)(kv.first & 0xffffffffu);
+            if (u != v) { nb[u].push_back(v); nb[v].push_back(u); }
+        }
+        tb.set_adjacency(nb);
+        tb.run();
+        out.T = tb.n_leaves;
+    }
+    // self-checks: partitions of the faces and of the vertices
     std::vector<char> seen(F, 0);
     size_t n = 0;
     for (int f : out.leaf_face)
         if (f >= 0) { TUCH_REQUIRE(!seen[f], "cluster tree lists face %d twice", f); seen[f] = 1; ++n; }
     TUCH_REQUIRE((int)n == F, "cluster tree covers %zu of %d faces", n, F);
-    // query order: vertices sorted by the first leaf that holds one of their faces
-    std::vector<int> first(V, out.K);
-    for (int l = 0; l < out.K; ++l)
-        for (int i = 0; i < WC_LEAF; ++i) {
-            const int f = out.leaf_face[(size_t)l * WC_LEAF + i];
-            if (f < 0) continue;
-            for (int e = 0; e < 3; ++e) first[faces[3 * f + e]] = std::min(first[faces[3 * f + e]], l);
-        }
-    out.qperm.resize(V);
-    std::iota(out.qperm.begin(), out.qperm.end(), 0);
-    std::stable_sort(out.qperm.begin(), out.qperm.end(), [&](int a, int b) { return first[a] < first[b]; });
+    seen.assign(V, 0);
+    n = 0;
+    for (int v : out.vtile)
+        if (v >= 0) { TUCH_REQUIRE(!seen[v], "vertex tiling lists vertex %d twice", v); seen[v] = 1; ++n; }
+    TUCH_REQUIRE((int)n == V, "vertex tiling covers %zu of %d vertices", n, V);
     return 0;
 }
 
@@ -326,7 +348,8 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
     tzzx = warp_sum(tzzx); tzzy = warp_sum(tzzy); txyz = warp_sum(txyz);
     if (lane == 0) {
         float4* o = nodes + ((size_t)b * (NS + K) + node) * WC_NODE_F4;
-        o[0] = make_float4(px, py, pz, r2 * (WC_BETA * WC_BETA * 1.0002f));
+        const float beta = is_leaf ? WC_BETA : WC_BETA_SUPER;
+        o[0] = make_float4(px, py, pz, r2 * (beta * beta * 1.0002f));
         o[1] = make_float4(0.5f * m0x, 0.5f * m0y, 0.5f * m0z, 0.5f * tr);
         o[2] = make_float4(-1.5f * qxx, -1.5f * qyy, -1.5f * qzz, -1.5f * qxy);
         o[3] = make_float4(-1.5f * qxz, -1.5f * qyz, -0.75f * uvx, -0.75f * uvy);
@@ -357,18 +380,19 @@ __device__ __forceinline__ float node_far_field(const float4* __restrict__ rec, 
     return fmaf(t0, i3, fmaf(t1, i5, t2 * i7));
 }
 
-// grid (query tiles of WC_WARPS * 32, super splits, bodies); one query per lane, in cluster order
+// grid (groups of WC_WARPS vertex tiles, super splits, bodies); one query per lane, one vertex tile per warp
 __global__ void __launch_bounds__(WC_WARPS * 32)
-winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ qperm,
+winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ vtile,
                        const float4* __restrict__ ctri, const float4* __restrict__ nodes,
-                       const int* __restrict__ super_off, float* __restrict__ partial, int V, int K, int NS,
+                       const int* __restrict__ super_off, float* __restrict__ partial, int V, int T, int K, int NS,
                        int supers_per_split, int S) {
     __shared__ float s_acc[WC_WARPS][32 * 33];
     const int b = blockIdx.z, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * WC_WARPS + warp) * 32 + lane;
-    if (i - lane >= V) return;                                   // whole warp past the end
-    const int qi = qperm[min(i, V - 1)];
+    const int tile = blockIdx.x * WC_WARPS + warp;               // one vertex tile per warp
+    if (tile >= T) return;
+    const int qv = vtile[tile * 32 + lane];                      // -1 = padding lane (a tile holds >= 1 vertex)
+    const int qi = qv >= 0 ? qv : vtile[tile * 32];
     const float* vb = verts + (size_t)b * V * 3;
     const float px = vb[3 * qi], py = vb[3 * qi + 1], pz = vb[3 * qi + 2];
     float* acc = s_acc[warp];
@@ -419,7 +443,7 @@ winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ 
     float near_sum = 0.f;
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) near_sum += acc[lane * 33 + j];
-    if (i < V) partial[((size_t)b * S + split) * V + qi] = far + near_sum;
+    if (qv >= 0) partial[((size_t)b * S + split) * V + qi] = far + near_sum;
 }
 
 // sums the split partials in a fixed order, scales by 1 / (2 pi) and lists the queries whose value is
@@ -477,8 +501,8 @@ cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict_
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-int cluster_splits(int B, int V, int NS, int sm_count) {
-    const int qtiles = cdiv(V, WC_WARPS * 32);
+int cluster_splits(int B, int T, int NS, int sm_count) {
+    const int qtiles = cdiv(T, WC_WARPS);
     const long long want = (long long)sm_count * 6;                     // CTAs in flight
     int S = (int)((want + (long long)qtiles * B - 1) / ((long long)qtiles * B));
     S = std::max(1, std::min(S, NS));
@@ -497,10 +521,10 @@ int launch_winding_clusters(const ClusterJob& j, cudaStream_t st) {
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
     {
         const int per = cdiv(j.NS, j.S);
-        dim3 grid(cdiv(j.V, WC_WARPS * 32), j.S, j.B);
+        dim3 grid(cdiv(j.T, WC_WARPS), j.S, j.B);
         KernelTimer timer("winding_kernel", st);
-        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(j.verts, j.qperm, j.ctri, j.nodes, j.super_off, j.partial,
-                                                               j.V, j.K, j.NS, per, j.S);
+        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(j.verts, j.vtile, j.ctri, j.nodes, j.super_off, j.partial,
+                                                               j.V, j.T, j.K, j.NS, per, j.S);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     {

@@ -1,0 +1,170 @@
+// Geodesically-masked nearest vertex with bounding-sphere pruning.
+//
+// nearest_kernel (contact_kernels.cu) evaluates all V^2 masked distances of losses.py:92-93.  Here the
+// vertices are grouped into the vertex tiles of clusters.cu (32 neighbouring vertices each, ascending
+// ids inside a tile), so the 32 candidate rows of a tile -- exactly one word of the bit-packed mask --
+// have a small bounding sphere that is recomputed per body.  One warp owns the 32 query columns of one
+// tile (lane = query):
+//   pass 1: an upper bound of the masked minimum from the tile spheres alone:
+//           ub = min over tiles with at least one unmasked row of (|q - c_t| + R_t)^2
+//   pass 2: a tile survives for a query iff its mask word is non-zero and (|q - c_t| - R_t)^2 <= ub
+//           (with fp32 slack that covers the rounding of the expansion-form distance); the warp evaluates
+//           the 32 candidates of every tile that survives for ANY of its queries.
+// The result is bit-identical to nearest_kernel: same fp32 expansion (|v_r|^2 + |v_c|^2) - 2 v_r.v_c with
+// the same FMA order, minimum over a superset of the candidates that can attain it, lowest ORIGINAL row
+// index on ties, (0, +inf) for a fully masked column.
+#include "api_internal.h"
+#include "clusters.h"
+
+namespace tuch {
+
+constexpr int NT_WARPS = 4;
+
+// maskT [W][Vq] (original ids) -> maskP [T][T * 32] over tile slots: bit k of maskP[t][s] is
+// geomask[vtile[32 t + k]][vtile[s]]; padding slots are 0
+__global__ void permute_mask_kernel(const uint32_t* __restrict__ maskT, int Vq, const int* __restrict__ vtile, int T,
+                                    uint32_t* __restrict__ maskP) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (s >= T * 32) return;
+    uint32_t bits = 0;
+    const int oc = vtile[s];
+    if (oc >= 0) {
+        for (int k = 0; k < 32; ++k) {
+            const int r = vtile[t * 32 + k];
+            if (r < 0) break;                                     // padding only at the end of a tile
+            bits |= ((maskT[(size_t)(r >> 5) * Vq + oc] >> (r & 31)) & 1u) << k;
+        }
+    }
+    maskP[(size_t)t * T * 32 + s] = bits;
+}
+
+// one warp per vertex tile:
+//   vert4p[b][s] = (v, |v|^2) of vertex vtile[s]  (|v|^2 accumulated exactly like pack_mesh_kernel)
+//   tinfo[b][t]  = (centre, radius), (max |v|^2, 0, 0, 0)
+__global__ void __launch_bounds__(128)
+pack_tiles_kernel(const float* __restrict__ verts, int V, const int* __restrict__ vtile, int T,
+                  float4* __restrict__ vert4p, float4* __restrict__ tinfo) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int s = t * 32 + lane;
+    const int id = vtile[s];
+    const bool ok = id >= 0;
+    float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
+    if (ok) {
+        const float* p = verts + ((size_t)b * V + id) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+        w = fmaf(z, z, fmaf(y, y, x * x));
+    }
+    vert4p[(size_t)b * T * 32 + s] = make_float4(x, y, z, w);
+    float n = ok ? 1.f : 0.f, sx = x, sy = y, sz = z, wm = w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    }
+    const float inv = 1.f / fmaxf(n, 1.f);
+    const float cx = sx * inv, cy = sy * inv, cz = sz * inv;
+    float r2 = ok ? (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    if (lane == 0) {
+        float4* o = tinfo + ((size_t)b * T + t) * 2;
+        o[0] = make_float4(cx, cy, cz, sqrtf(r2) * 1.0001f + 1e-7f);
+        o[1] = make_float4(wm, 0.f, 0.f, 0.f);
+    }
+}
+
+// grid (groups of NT_WARPS query tiles, bodies)
+__global__ void __launch_bounds__(NT_WARPS * 32)
+nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
+                     const uint32_t* __restrict__ maskP, const int* __restrict__ vtile, int V, int T,
+                     int* __restrict__ argmin_out, float* __restrict__ min_out) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int qt = blockIdx.x * NT_WARPS + (threadIdx.x >> 5);
+    if (qt >= T) return;
+    const int slot = qt * 32 + lane;                                   // query column (tile slot)
+    const int oc = vtile[slot];                                        // original vertex id, -1 = padding
+    const float4* vb = vert4p + (size_t)b * T * 32;
+    const float4* ib = tinfo + (size_t)b * T * 2;
+    const float4 q = vb[slot];
+    const uint32_t* mcol = maskP + slot;                               // mask words of this column, stride T*32
+    const size_t mstride = (size_t)T * 32;
+
+    // pass 1: upper bound of the (fp32, expansion-form) masked minimum
+    float ub = INFINITY;
+#pragma unroll 2
+    for (int t = 0; t < T; ++t) {
+        const uint32_t m = mcol[(size_t)t * mstride];
+        const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
+        const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
+        const float d = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 1.0001f, s.w);
+        const float u = fmaf(d * d, 1.00001f, 4e-6f * (q.w + s2.x));
+        ub = (m != 0u) ? fminf(ub, u) : ub;
+    }
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int t = 0; t < T; ++t) {
+        const uint32_t m = mcol[(size_t)t * mstride];
+        const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
+        const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
+        // lower bound of the true distance to any row of the tile; the slack covers the rows' fp32
+        // expansion-form values undershooting their true squared distance (<= 3.6e-7 (|v|^2 + |q|^2))
+        const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
+        const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(ub, 1.00001f, 4e-6f * (q.w + s2.x)));
+        if (!__any_sync(0xffffffffu, need)) continue;
+        const float4* tv = vb + t * 32;
+        const int* tid = vtile + t * 32;
+        float lbest = INFINITY;                                        // first minimum inside the tile: rows of
+        int lk = 0;                                                    // a tile are in ascending original order
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float4 v = __ldg(tv + k);
+            const float zz = fmaf(v.z, q.z, fmaf(v.y, q.y, v.x * q.x));
+            float p = fmaf(-2.f, zz, v.w + q.w);
+            p = ((m >> k) & 1u) ? p : INFINITY;
+            if (p < lbest) { lbest = p; lk = k; }
+        }
+        if (lbest < INFINITY) {
+            const int r = __ldg(tid + lk);
+            if (lbest < best || (lbest == best && r < bi)) { best = lbest; bi = r; }
+        }
+    }
+    if (oc >= 0) {
+        const bool none = bi == 0x7fffffff;                            // fully masked column
+        argmin_out[(size_t)b * V + oc] = none ? 0 : bi;
+        min_out[(size_t)b * V + oc] = none ? INFINITY : best;
+    }
+}
+
+int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st) {
+    dim3 grid(cdiv(T * 32, 128), T);
+    permute_mask_kernel<<<grid, 128, 0, st>>>(maskT, Vq, vtile, T, maskP);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, int B, int V, int T,
+                         float4* vert4p, float4* tinfo, int* argmin, float* minval, cudaStream_t st) {
+    if (B == 0) return 0;
+    {
+        dim3 grid(cdiv(T, 4), B);
+        pack_tiles_kernel<<<grid, 128, 0, st>>>(verts, V, vtile, T, vert4p, tinfo);
+        TUCH_LAUNCH_CHECK(); count_launch();
+    }
+    {
+        dim3 grid(cdiv(T, NT_WARPS), B);
+        KernelTimer timer("nearest_kernel", st);
+        nearest_tiles_kernel<<<grid, NT_WARPS * 32, 0, st>>>(vert4p, tinfo, maskP, vtile, V, T, argmin, minval);
+    }
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+}  // namespace tuch

@@ -81,18 +81,18 @@ def strip_stream(faces):
 
 # ------------------------------------------------------------------ a1-a3 forward kernels
 def cluster_tree(faces, verts):
-    """Host-only: the face-cluster hierarchy of clusters.cu -> dict(leaf_face[K,32], super_off[NS+1], qperm[V])."""
+    """Host-only: the hierarchy of clusters.cu -> dict(leaf_face[K,32], super_off[NS+1], vtile[T,32])."""
     f = _i32_host(np.asarray(faces).reshape(-1, 3))
     v = np.ascontiguousarray(np.asarray(verts).reshape(-1, 3), dtype=np.float32)
-    k, ns = C.c_int32(0), C.c_int32(0)
-    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), None, 0, None, 0, None, C.byref(k), C.byref(ns)),
-          'tuch_cluster_tree_host')
+    k, ns, nt = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), None, 0, None, 0, None, 0, C.byref(k), C.byref(ns),
+                                       C.byref(nt)), 'tuch_cluster_tree_host')
     leaf = np.empty((k.value, 32), np.int32)
     sup = np.empty(ns.value + 1, np.int32)
-    qp = np.empty(len(v), np.int32)
-    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), _hp(leaf), k.value, _hp(sup), ns.value, _hp(qp),
-                                       C.byref(k), C.byref(ns)), 'tuch_cluster_tree_host')
-    return dict(leaf_face=leaf, super_off=sup, qperm=qp)
+    vt = np.empty((nt.value, 32), np.int32)
+    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), _hp(leaf), k.value, _hp(sup), ns.value, _hp(vt),
+                                       nt.value, C.byref(k), C.byref(ns), C.byref(nt)), 'tuch_cluster_tree_host')
+    return dict(leaf_face=leaf, super_off=sup, vtile=vt)
 
 
 def pairwise_dist(x, y, squared=True):
