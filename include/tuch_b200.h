@@ -112,9 +112,9 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
 /* Winding-number evaluation inside tuch_contact_query.  Callers of the reference only consume the
  * flag `winding_numbers(...) <= 0.99` (losses.py:82, loss.py:262), so the default mode evaluates the
  * sum hierarchically: the faces are clustered once per topology (leaves of <= 32 faces, super-clusters
- * of <= 8 leaves); per body, clusters farther than 2 radii from a query contribute through a
- * second-order multipole expansion of the solid-angle integrand (max abs error measured 3.8e-3 on the winding
- * number), nearer leaves are summed exactly, and every query whose value falls within 0.03 of the 0.99
+ * of <= 8 leaves); per body, clusters farther than 2 (leaves) / 2.5 (super-clusters) radii from a query contribute through a
+ * second-order multipole expansion of the solid-angle integrand (max abs error measured 4.9e-3 on the winding
+ * number), nearer leaves are summed exactly, and every query whose value falls within 0.04 of the 0.99
  * threshold is re-evaluated exactly over all faces -- the exterior flags are those of the exact sum.
  * TUCH_WINDING_EXACT sums all F solid angles for every query (values within 2e-5 of the reference).
  * The hierarchy is built from the template given to tuch_topology_set_template (HOST [V,3]) or, when

@@ -86,7 +86,7 @@ def test_far_field_expansion_matches_exact_solid_angles():
         far = d > 2.0 * R
         total_err += np.where(far, np.abs(omega - sa[:, fs].sum(1)), 0.0) / (4 * np.pi)
         signed_err += np.where(far, omega - sa[:, fs].sum(1), 0.0) / (4 * np.pi)
-    # even if every leaf's error had the same sign the total stays below a third of the 0.03 re-evaluation
+    # even if every leaf's error had the same sign the total stays below a quarter of the 0.04 re-evaluation
     # margin (WC_MARGIN); the actual error is a few 1e-3
     assert total_err.max() < 1e-2, total_err.max()
     assert np.abs(signed_err).max() < 4e-3, np.abs(signed_err).max()

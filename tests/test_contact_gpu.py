@@ -254,7 +254,7 @@ def _fast_vs_exact(assets, dev, batch, seed, template):
     print('hierarchical winding: max |w_fast - w_exact| = %.2e' % float(err.max()))
     assert float(err.max()) < 5e-3, float(err.max())
     # every query the far field could misclassify was re-evaluated exactly
-    band = (b['winding'] - 0.99).abs() < 0.03
+    band = (b['winding'] - 0.99).abs() < 0.04
     if bool(band.any()):
         assert float(err[band].max()) < 2e-5
     away = (a['winding'] - 0.99).abs() > 1e-4

@@ -276,6 +276,8 @@ static void free_regions(tuch_topology* t) {
 static void free_segments(tuch_topology* t) {
     free_dev(t->d_seg_vidx); free_dev(t->d_seg_faces); free_dev(t->d_slot_face); free_dev(t->d_slot_band0);
     free_dev(t->d_loop_off); free_dev(t->d_loop_ids);
+    free_dev(t->d_member_seg); free_dev(t->d_seg_face_off); free_dev(t->d_seg_band0);
+    t->d_member_seg = t->d_seg_face_off = t->d_seg_band0 = nullptr;
     t->d_seg_vidx = t->d_seg_faces = t->d_slot_face = t->d_slot_band0 = t->d_loop_off = t->d_loop_ids = nullptr;
     t->n_segments = t->n_bands = t->n_sv = t->n_slots = 0;
     t->h_vidx_off.clear(); t->h_slot_off.clear();
@@ -479,6 +481,12 @@ TUCH_EXPORT int tuch_topology_set_segments(tuch_topology* t, int n_segments, con
     if (int rc = upload(slot_band0.data(), slot_band0.size(), &t->d_slot_band0)) return rc;
     if (int rc = upload(loop_off, (size_t)n_bands + 1, &t->d_loop_off)) return rc;
     if (int rc = upload(loop_ids, (size_t)n_loop, &t->d_loop_ids)) return rc;
+    std::vector<int> member_seg((size_t)n_sv);
+    for (int s = 0; s < n_segments; ++s)
+        for (int k = vidx_off[s]; k < vidx_off[s + 1]; ++k) member_seg[k] = s;
+    if (int rc = upload(member_seg.data(), member_seg.size(), &t->d_member_seg)) return rc;
+    if (int rc = upload(face_off, (size_t)n_segments + 1, &t->d_seg_face_off)) return rc;
+    if (int rc = upload(band_off, (size_t)n_segments, &t->d_seg_band0)) return rc;
     t->n_segments = n_segments; t->n_bands = n_bands; t->n_sv = n_sv; t->n_slots = (int)slot_face.size();
     return 0;
 }
@@ -577,8 +585,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     const size_t h_any = sc.plan(segs ? (size_t)B : 0);
     const size_t h_am = sc.plan((want_nn && !argmin) ? sizeof(int) * (size_t)B * V : 0);
     const size_t h_mn = sc.plan((want_nn && !min_sq) ? sizeof(float) * (size_t)B * V : 0);
-    SegPlan sp;
-    if (segs) plan_segments(t, B, sc, sp);
+    const size_t h_apex = sc.plan(segs ? sizeof(float) * 3 * (size_t)B * (t->n_bands > 0 ? t->n_bands : 1) : 0);
     if (int rc = sc.commit(st)) return rc;
 
     float4* strip4 = want_w ? sc.get<float4>(h_tri) : nullptr;
@@ -602,8 +609,13 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
             uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;
             if (any) TUCH_CUDA(cudaMemsetAsync(any, 0, (size_t)B, st));
             if (int rc = launch_exterior_init(w, B, V, exterior, any, st)) return rc;
-            if (segs)
-                if (int rc = run_segments(t, verts, B, sc, sp, any, exterior, nullptr, nullptr, st)) return rc;
+            if (segs) {
+                float* apex = sc.get<float>(h_apex);
+                if (int rc = launch_segment_apex(verts, B, V, t->d_loop_off, t->d_loop_ids, t->n_bands, apex, any, st)) return rc;
+                if (int rc = launch_segment_whitelist(verts, B, V, apex, t->n_bands, t->d_seg_faces, t->d_seg_face_off,
+                                                      t->d_seg_band0, t->d_seg_vidx, t->d_member_seg, t->n_sv, exterior,
+                                                      any, st)) return rc;
+            }
         }
     }
     if (want_nn) {

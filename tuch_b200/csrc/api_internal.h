@@ -31,6 +31,7 @@ struct tuch_topology {
     std::vector<int> h_slot_off;       // [S+1] packed (padded) triangle ranges
     int *d_seg_vidx = nullptr, *d_seg_faces = nullptr, *d_slot_face = nullptr, *d_slot_band0 = nullptr;
     int *d_loop_off = nullptr, *d_loop_ids = nullptr;
+    int *d_member_seg = nullptr, *d_seg_face_off = nullptr, *d_seg_band0 = nullptr;   // whitelist pass
     // HD-point regressor (CSR rows) and the source face of every HD point (loss.py:81-89)
     int n_hd = 0;
     int *d_hd_row_off = nullptr, *d_hd_cols = nullptr, *d_hd_face = nullptr;
@@ -64,6 +65,10 @@ int launch_segment_apex(const float* verts, int B, int V, const int* loop_off, c
 int launch_segment_pack(const float* verts, int B, int V, const float* apex, int n_bands, const int* seg_faces,
                         const int* slot_face, const int* slot_band0, int n_slots, const int* seg_vidx,
                         int n_sv, float4* tri12, float* points, const uint8_t* body_active, cudaStream_t st);
+int launch_segment_whitelist(const float* verts, int B, int V, const float* apex, int n_bands, const int* seg_faces,
+                             const int* seg_face_off, const int* seg_band0, const int* seg_vidx,
+                             const int* member_seg, int n_sv, uint8_t* exterior, const uint8_t* body_active,
+                             cudaStream_t st);
 int launch_exterior_init(const float* winding, int B, int V, uint8_t* exterior, uint8_t* any_interior,
                          cudaStream_t st);
 int launch_segment_apply(const float* seg_winding, const int* seg_vidx, int n_sv, int B, int V,

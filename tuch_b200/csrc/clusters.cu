@@ -19,6 +19,7 @@
 // those of the exact kernel.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <unordered_map>
 
@@ -251,7 +252,7 @@ __device__ __forceinline__ float warp_max(float v) {
 __global__ void __launch_bounds__(128)
 cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restrict__ faces,
                     const int* __restrict__ leaf_face, const int* __restrict__ super_off, int K, int NS,
-                    float4* __restrict__ ctri, float4* __restrict__ nodes) {
+                    float beta_leaf, float beta_super, float4* __restrict__ ctri, float4* __restrict__ nodes) {
     const int b = blockIdx.y;
     const int node = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -268,12 +269,13 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bv = A, C = A;
         if (f >= 0) {
             const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-            A = make_float4(vb[3 * i0], vb[3 * i0 + 1], vb[3 * i0 + 2], 1.f);
+            A = make_float4(vb[3 * i0], vb[3 * i0 + 1], vb[3 * i0 + 2], 0.f);
             Bv = make_float4(vb[3 * i1], vb[3 * i1 + 1], vb[3 * i1 + 2], 0.f);
             C = make_float4(vb[3 * i2], vb[3 * i2 + 1], vb[3 * i2 + 2], 0.f);
             const float e1x = Bv.x - A.x, e1y = Bv.y - A.y, e1z = Bv.z - A.z;
             const float e2x = C.x - A.x, e2y = C.y - A.y, e2z = C.z - A.z;
             const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+            A.w = nx; Bv.w = ny; C.w = nz;                       // face normal for half_solid_angle_n
             const float area = 0.5f * sqrtf(nx * nx + ny * ny + nz * nz);
             const float gx = (A.x + Bv.x + C.x) * (1.f / 3.f), gy = (A.y + Bv.y + C.y) * (1.f / 3.f),
                         gz = (A.z + Bv.z + C.z) * (1.f / 3.f);
@@ -348,7 +350,7 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
     tzzx = warp_sum(tzzx); tzzy = warp_sum(tzzy); txyz = warp_sum(txyz);
     if (lane == 0) {
         float4* o = nodes + ((size_t)b * (NS + K) + node) * WC_NODE_F4;
-        const float beta = is_leaf ? WC_BETA : WC_BETA_SUPER;
+        const float beta = is_leaf ? beta_leaf : beta_super;
         o[0] = make_float4(px, py, pz, r2 * (beta * beta * 1.0002f));
         o[1] = make_float4(0.5f * m0x, 0.5f * m0y, 0.5f * m0z, 0.5f * tr);
         o[2] = make_float4(-1.5f * qxx, -1.5f * qyy, -1.5f * qzz, -1.5f * qxy);
@@ -433,8 +435,7 @@ winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ 
                     m &= m - 1u;
                     const float qx = __shfl_sync(0xffffffffu, px, q), qy = __shfl_sync(0xffffffffu, py, q),
                                 qz = __shfl_sync(0xffffffffu, pz, q);
-                    const float sa = half_solid_angle(qx, qy, qz, A, Bv, C);
-                    acc[q * 33 + lane] += (A.w != 0.f) ? sa : 0.f;
+                    acc[q * 33 + lane] += half_solid_angle_n(qx, qy, qz, A, Bv, C);
                 }
             }
         }
@@ -482,8 +483,7 @@ cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict_
 #pragma unroll 2
         for (int l = warp; l < K; l += 8, t += 8 * WC_LEAF * 3) {
             const float4 A = __ldg(t), Bv = __ldg(t + 1), C = __ldg(t + 2);
-            const float sa = half_solid_angle(px, py, pz, A, Bv, C);
-            acc += (A.w != 0.f) ? sa : 0.f;
+            acc += half_solid_angle_n(px, py, pz, A, Bv, C);
         }
         acc = warp_sum(acc);
         if (lane == 0) s_part[warp] = acc;
@@ -514,8 +514,11 @@ int launch_winding_clusters(const ClusterJob& j, cudaStream_t st) {
     if (j.B == 0 || j.V == 0) return 0;
     {
         dim3 grid(cdiv(j.NS + j.K, 4), j.B);
-        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.super_off, j.K, j.NS, j.ctri,
-                                                  j.nodes);
+        // development knobs (scripts/time_contact.py sweeps them); the shipped values are the constants
+        static const float beta_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : WC_BETA;
+        static const float beta_super = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : WC_BETA_SUPER;
+        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.super_off, j.K, j.NS, beta_leaf,
+                                                  beta_super, j.ctri, j.nodes);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));

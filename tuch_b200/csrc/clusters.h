@@ -11,9 +11,9 @@ constexpr int WC_SUPER_LEAVES = 8;   // leaves per super-cluster (second level o
 constexpr int WC_NODE_F4 = 7;        // float4 per node record (centre + radius, scaled moments)
 constexpr int WC_WARPS = 8;          // warps per CTA of the winding kernel; one query per lane
 constexpr float WC_BETA = 2.0f;      // a leaf is "far" for a query beyond WC_BETA x its radius ...
-constexpr float WC_BETA_SUPER = 3.0f;   // ... a super-cluster (larger, so larger absolute error) beyond 3 x
-constexpr float WC_MARGIN = 0.03f;   // |w - 0.99| below this is re-evaluated exactly (8 x the worst far-field
-                                     // error measured at WC_BETA = 2: 3.8e-3)
+constexpr float WC_BETA_SUPER = 2.5f;   // ... a super-cluster (larger, so larger absolute error) beyond 2.5 x
+constexpr float WC_MARGIN = 0.04f;   // |w - 0.99| below this is re-evaluated exactly (8 x the worst far-field
+                                     // error measured at these opening parameters: 4.9e-3)
 
 // Host-side hierarchy of one mesh topology, built from the faces and ONE set of vertex positions
 // (the template, or the first body seen).
@@ -33,7 +33,8 @@ struct ClusterJob {
     const int* leaf_face;            // [K][WC_LEAF]
     const int* super_off;            // [NS + 1]
     const int* vtile;                // [T][32]
-    float4* ctri;                    // [B][K][WC_LEAF][3] scratch: packed corner triples per leaf
+    float4* ctri;                    // [B][K][WC_LEAF][3] scratch: corners a | b | c per face slot, the face's
+                                     // normal (b - a) x (c - a) in the three w components
     float4* nodes;                   // [B][NS + K][WC_NODE_F4] scratch: super records first, then leaves
     float* partial;                  // [B][S][V] scratch
     float* winding;                  // [B][V] out

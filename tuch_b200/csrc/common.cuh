@@ -91,6 +91,30 @@ __device__ __forceinline__ float half_solid_angle(float px, float py, float pz,
     return atan2_poly(num, den);
 }
 
+// Same term with the numerator taken from the face normal N = (B - A) x (C - A) carried in the w
+// components: a.(b x c) is affine in the query and equals N.(A - q), which saves the cross product.
+// N.(A - q) is only mathematically 0 when q is another corner of the face; the reference's triple product
+// is exactly 0 there and so is the denominator, which is what the guard keys on.  An all-zero padding
+// slot contributes exactly 0.
+__device__ __forceinline__ float half_solid_angle_n(float px, float py, float pz,
+                                                    const float4& A, const float4& B, const float4& C) {
+    const float ax = A.x - px, ay = A.y - py, az = A.z - pz;
+    const float bx = B.x - px, by = B.y - py, bz = B.z - pz;
+    const float cx = C.x - px, cy = C.y - py, cz = C.z - pz;
+    const float la = sqrt_approx(fmaf(az, az, fmaf(ay, ay, ax * ax)));
+    const float lb = sqrt_approx(fmaf(bz, bz, fmaf(by, by, bx * bx)));
+    const float lc = sqrt_approx(fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
+    const float num = fmaf(C.w, az, fmaf(B.w, ay, A.w * ax));
+    const float dab = fmaf(az, bz, fmaf(ay, by, ax * bx));
+    const float dac = fmaf(az, cz, fmaf(ay, cy, ax * cx));
+    const float dbc = fmaf(bz, cz, fmaf(by, cy, bx * cx));
+    float den = (la * lb) * lc;
+    den = fmaf(dab, lc, den);
+    den = fmaf(dac, lb, den);
+    den = fmaf(dbc, la, den);
+    return atan2_poly(den == 0.f ? 0.f : num, den);
+}
+
 // ---------------------------------------------------------------- mbarrier + 1-D TMA bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

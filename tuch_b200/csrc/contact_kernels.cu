@@ -358,19 +358,36 @@ region_min_kernel(const float4* __restrict__ vert4, int Vp, const uint32_t* __re
     float best = INFINITY;
     unsigned long long best_flat = 0ull;     // ties and the all-masked case resolve to flat index 0
     bool have = false;
-    const long long total = (long long)na * nb;
-    for (long long e = threadIdx.x; e < total; e += RM_THREADS) {
-        const int a = (int)(e / nb), c = (int)(e - (long long)a * nb);
-        const int i = ia[a], j = ib[c];
-        float p = INFINITY;
-        bool ok = true;
-        if (maskT != nullptr) ok = (maskT[(size_t)(i >> 5) * Vq + j] >> (i & 31)) & 1u;   // geomask[i][j]
-        if (ok) {
-            const float4 x = v[i], y = v[j];
-            const float zz = fmaf(x.z, y.z, fmaf(x.y, y.y, x.x * y.x));
-            p = fmaf(-2.f, zz, x.w + y.w);
+    // region B is staged through shared memory in chunks; every thread owns rows a = tid, tid + T, ...
+    // and walks the chunk in ascending c, so its running minimum is the first one in flat order
+    __shared__ float4 s_vb[RM_THREADS];
+    __shared__ int s_jb[RM_THREADS];
+    for (int c0 = 0; c0 < nb; c0 += RM_THREADS) {
+        const int nc = min(RM_THREADS, nb - c0);
+        __syncthreads();
+        if ((int)threadIdx.x < nc) {
+            const int j = ib[c0 + threadIdx.x];
+            s_jb[threadIdx.x] = j;
+            s_vb[threadIdx.x] = v[j];
         }
-        if (!have || p < best) { best = p; best_flat = (unsigned long long)e; have = true; }
+        __syncthreads();
+        for (int a = threadIdx.x; a < na; a += RM_THREADS) {
+            const int i = ia[a];
+            const float4 x = v[i];
+            const uint32_t* mrow = maskT != nullptr ? maskT + (size_t)(i >> 5) * Vq : nullptr;
+            const int sh = i & 31;
+            float rbest = INFINITY;
+            int rc = -1;
+            for (int c = 0; c < nc; ++c) {
+                const float4 y = s_vb[c];
+                const float zz = fmaf(x.z, y.z, fmaf(x.y, y.y, x.x * y.x));
+                float p = fmaf(-2.f, zz, x.w + y.w);
+                if (mrow != nullptr && !((mrow[s_jb[c]] >> sh) & 1u)) p = INFINITY;      // geomask[i][j]
+                if (rc < 0 || p < rbest) { rbest = p; rc = c; }
+            }
+            const unsigned long long flat = (unsigned long long)a * nb + (unsigned long long)(c0 + rc);
+            if (!have || rbest < best || (rbest == best && flat < best_flat)) { best = rbest; best_flat = flat; have = true; }
+        }
     }
     // block argmin with lowest-flat-index tie-break
     __shared__ float s_val[RM_THREADS];

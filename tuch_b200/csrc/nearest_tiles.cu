@@ -5,9 +5,10 @@
 // ids inside a tile), so the 32 candidate rows of a tile -- exactly one word of the bit-packed mask --
 // have a small bounding sphere that is recomputed per body.  One warp owns the 32 query columns of one
 // tile (lane = query):
-//   pass 1: an upper bound of the masked minimum from the tile spheres alone:
-//           ub = min over tiles with at least one unmasked row of (|q - c_t| + R_t)^2
-//   pass 2: a tile survives for a query iff its mask word is non-zero and (|q - c_t| - R_t)^2 <= ub
+//   pass 1: the tile with the smallest |q - c_t| + R_t among those with at least one unmasked row; the
+//           (few distinct) such tiles of the warp are evaluated first, which gives every query a tight
+//           running minimum `best`
+//   pass 2: a tile survives for a query iff its mask word is non-zero and (|q - c_t| - R_t)^2 <= best
 //           (with fp32 slack that covers the rounding of the expansion-form distance); the warp evaluates
 //           the 32 candidates of every tile that survives for ANY of its queries.
 // The result is bit-identical to nearest_kernel: same fp32 expansion (|v_r|^2 + |v_c|^2) - 2 v_r.v_c with
@@ -80,6 +81,26 @@ pack_tiles_kernel(const float* __restrict__ verts, int V, const int* __restrict_
     }
 }
 
+// the 32 candidate rows of tile t against this lane's query: first minimum inside the tile (its rows are
+// in ascending original order), merged into (best, bi) with the lowest-original-index tie-break
+__device__ __forceinline__ void nearest_eval_tile(const float4* __restrict__ tv, const int* __restrict__ tid,
+                                                  uint32_t m, const float4& q, float& best, int& bi) {
+    float lbest = INFINITY;
+    int lk = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const float4 v = __ldg(tv + k);
+        const float zz = fmaf(v.z, q.z, fmaf(v.y, q.y, v.x * q.x));
+        float p = fmaf(-2.f, zz, v.w + q.w);
+        p = ((m >> k) & 1u) ? p : INFINITY;
+        if (p < lbest) { lbest = p; lk = k; }
+    }
+    if (lbest < INFINITY) {
+        const int r = __ldg(tid + lk);
+        if (lbest < best || (lbest == best && r < bi)) { best = lbest; bi = r; }
+    }
+}
+
 // grid (groups of NT_WARPS query tiles, bodies)
 __global__ void __launch_bounds__(NT_WARPS * 32)
 nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
@@ -97,19 +118,28 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     const uint32_t* mcol = maskP + slot;                               // mask words of this column, stride T*32
     const size_t mstride = (size_t)T * 32;
 
-    // pass 1: upper bound of the (fp32, expansion-form) masked minimum
+    // pass 1: the tile whose sphere promises the smallest masked distance, (d + R)^2
     float ub = INFINITY;
+    int tstar = -1;
 #pragma unroll 2
     for (int t = 0; t < T; ++t) {
         const uint32_t m = mcol[(size_t)t * mstride];
-        const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
+        const float4 s = __ldg(ib + 2 * t);
         const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
-        const float d = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 1.0001f, s.w);
-        const float u = fmaf(d * d, 1.00001f, 4e-6f * (q.w + s2.x));
-        ub = (m != 0u) ? fminf(ub, u) : ub;
+        const float d = sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + s.w;
+        if (m != 0u && d < ub) { ub = d; tstar = t; }
     }
+    // evaluate those tiles first (a warp's queries are neighbours: few distinct ones): from here on
+    // `best` is a tight bound for the sphere test
     float best = INFINITY;
     int bi = 0x7fffffff;
+    unsigned todo = __ballot_sync(0xffffffffu, tstar >= 0);
+    while (todo != 0u) {
+        const int ts = __shfl_sync(0xffffffffu, tstar, __ffs(todo) - 1);
+        nearest_eval_tile(vb + ts * 32, vtile + ts * 32, mcol[(size_t)ts * mstride], q, best, bi);
+        todo &= ~__ballot_sync(0xffffffffu, tstar == ts);
+    }
+    // pass 2: every tile whose sphere can still hold a row at or below the running minimum
     for (int t = 0; t < T; ++t) {
         const uint32_t m = mcol[(size_t)t * mstride];
         const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
@@ -117,24 +147,9 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         // lower bound of the true distance to any row of the tile; the slack covers the rows' fp32
         // expansion-form values undershooting their true squared distance (<= 3.6e-7 (|v|^2 + |q|^2))
         const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
-        const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(ub, 1.00001f, 4e-6f * (q.w + s2.x)));
+        const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(best, 1.00001f, 4e-6f * (q.w + s2.x)));
         if (!__any_sync(0xffffffffu, need)) continue;
-        const float4* tv = vb + t * 32;
-        const int* tid = vtile + t * 32;
-        float lbest = INFINITY;                                        // first minimum inside the tile: rows of
-        int lk = 0;                                                    // a tile are in ascending original order
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const float4 v = __ldg(tv + k);
-            const float zz = fmaf(v.z, q.z, fmaf(v.y, q.y, v.x * q.x));
-            float p = fmaf(-2.f, zz, v.w + q.w);
-            p = ((m >> k) & 1u) ? p : INFINITY;
-            if (p < lbest) { lbest = p; lk = k; }
-        }
-        if (lbest < INFINITY) {
-            const int r = __ldg(tid + lk);
-            if (lbest < best || (lbest == best && r < bi)) { best = lbest; bi = r; }
-        }
+        nearest_eval_tile(vb + t * 32, vtile + t * 32, m, q, best, bi);
     }
     if (oc >= 0) {
         const bool none = bi == 0x7fffffff;                            // fully masked column

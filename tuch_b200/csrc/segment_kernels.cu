@@ -89,6 +89,56 @@ __global__ void segment_apply_kernel(const float* __restrict__ seg_winding, cons
     if (exterior != nullptr && !seg_ext) exterior[(size_t)b * V + seg_vidx[k]] = 1;
 }
 
+// Whitelist pass of the fused contact query: only INTERIOR member vertices can change (the write-back
+// sets exterior = 1), so one warp per (body, member slot) exits unless its vertex is interior, and
+// otherwise sums the solid angles of its segment's closed face list with one lane per face.
+__global__ void __launch_bounds__(256)
+segment_whitelist_kernel(const float* __restrict__ verts, int V, const float* __restrict__ apex, int n_bands,
+                         const int* __restrict__ seg_faces, const int* __restrict__ seg_face_off,
+                         const int* __restrict__ seg_band0, const int* __restrict__ seg_vidx,
+                         const int* __restrict__ member_seg, int n_sv, uint8_t* __restrict__ exterior,
+                         const uint8_t* __restrict__ body_active) {
+    const int b = blockIdx.y;
+    if (body_active != nullptr && !body_active[b]) return;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= n_sv) return;
+    const int v = seg_vidx[k];
+    uint8_t* flag = exterior + (size_t)b * V + v;
+    if (*flag != 0) return;                                  // exterior already: nothing to whitelist
+    const int s = member_seg[k];
+    const float* vb = verts + (size_t)b * V * 3;
+    const float* ab = apex + ((size_t)b * n_bands + seg_band0[s]) * 3;
+    const float px = vb[3 * v], py = vb[3 * v + 1], pz = vb[3 * v + 2];
+    float acc = 0.f;
+    for (int f = seg_face_off[s] + lane; f < seg_face_off[s + 1]; f += 32) {
+        float4 c[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int i = seg_faces[3 * f + e];
+            const float* p = (i < V) ? (vb + 3 * i) : (ab + 3 * (i - V));
+            c[e] = make_float4(p[0], p[1], p[2], 0.f);
+        }
+        acc += half_solid_angle(px, py, pz, c[0], c[1], c[2]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && !(acc * 0.159154943091895336f <= 0.99f)) *flag = 1;      // inside its own segment
+}
+
+int launch_segment_whitelist(const float* verts, int B, int V, const float* apex, int n_bands, const int* seg_faces,
+                             const int* seg_face_off, const int* seg_band0, const int* seg_vidx,
+                             const int* member_seg, int n_sv, uint8_t* exterior, const uint8_t* body_active,
+                             cudaStream_t st) {
+    if (n_sv == 0 || B == 0) return 0;
+    dim3 grid(cdiv(n_sv, 8), B);
+    KernelTimer timer("winding_kernel_segments", st);
+    segment_whitelist_kernel<<<grid, 256, 0, st>>>(verts, V, apex, n_bands, seg_faces, seg_face_off, seg_band0,
+                                                   seg_vidx, member_seg, n_sv, exterior, body_active);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
 int launch_segment_apex(const float* verts, int B, int V, const int* loop_off, const int* loop_ids,
                         int n_bands, float* apex, const uint8_t* body_active, cudaStream_t st) {
     if (n_bands == 0 || B == 0) return 0;
