@@ -213,33 +213,37 @@ def run_ours(args):
     wind_avg_ms = wind_ms / max(wind_n, 1)
     achieved = alg_bytes / (wind_avg_ms * 1e-3) / 1e9 if wind_n else None
     pairs = float(B) * V * F
-    roofline = dict(bound='hbm', kernel='winding_kernel', achieved=achieved, peak=peak, unit='GB/s',
+    roofline = dict(bound='hbm', kernel='winding_cluster_kernel', achieved=achieved, peak=peak, unit='GB/s',
                     frac=(achieved / peak) if achieved else None, traffic=None, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=wind_avg_ms, launches_timed=wind_n,
                     share_of_step=(wind_ms / ms) if ms > 0 else None,
-                    pair_evals_per_s=(pairs / (wind_avg_ms * 1e-3)) if wind_n else None,
+                    equivalent_pair_evals_per_s=(pairs / (wind_avg_ms * 1e-3)) if wind_n else None,
                     nearest_kernel_avg_ms=near_ms / max(near_n, 1), segment_winding_ms_per_step=seg_ms / args.steps,
-                    note='fused kernel keeps the V x F solid-angle tensor on chip: it is bound by fp32 issue slots '
-                         '(ncu: ~84% issue-active), not by HBM; see DESIGN.md and profiles/')
-    # the binding roof: warp-instruction issue slots (148 SMs x 4 schedulers x clock), at the issued
-    # instructions per (query, triangle) pair that ncu reports for this kernel build
-    ipp, sm_hz = None, (clocks or {}).get('sm_mhz') if clocks else None
+                    clusters=fit.topo.cluster_stats(),
+                    note='the winding numbers never touch HBM as a [V,F] tensor: the kernel is bound by fp32 issue slots '
+                         '(see roofline_compute), not by HBM; its algorithmic bytes are the vertices in, the faces and '
+                         'the winding numbers out.  See DESIGN.md section 5 and profiles/')
+    # the binding roof: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock).  The issued warp
+    # instructions per launch come from the committed ncu capture of the same workload shape
+    # (profiles/winding_traffic.json); the launch time is measured live above.
+    sm_hz = (clocks or {}).get('sm_mhz') if clocks else None
     traffic_file = os.path.join(ROOT, 'profiles', 'winding_traffic.json')
-    if os.path.exists(traffic_file):
-        with open(traffic_file) as f:
-            ipp = json.load(f).get('warp_instr_per_32_pairs')
-    roofline_compute = None
-    if ipp and sm_hz and wind_n:
-        peak_pairs = 148 * 4 * sm_hz * 1e6 * 32.0 / ipp
-        roofline_compute = dict(bound='fp32-issue', kernel='winding_kernel', achieved=pairs / (wind_avg_ms * 1e-3),
-                                peak=peak_pairs, unit='pair-evals/s', frac=pairs / (wind_avg_ms * 1e-3) / peak_pairs,
-                                warp_instr_per_32_pairs=ipp, sm_mhz=sm_hz,
-                                note='peak = 148 SM x 4 issue slots x SM clock x 32 lanes / issued instr per pair (ncu)')
+    tf = None
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             tf = json.load(f)
-        if tf.get('batch') == B:
-            roofline['traffic'] = tf.get('dram_bytes_per_launch')
+    roofline_compute = None
+    if tf and tf.get('batch') == B and tf.get('kernel') == 'winding_cluster_kernel':
+        roofline['traffic'] = tf.get('dram_bytes_per_launch')
+        wi = tf.get('warp_instr_per_launch')
+        if wi and sm_hz and wind_n:
+            peak_issue = 148 * 4 * sm_hz * 1e6
+            ach = wi / (wind_avg_ms * 1e-3)
+            roofline_compute = dict(bound='fp32-issue', kernel='winding_cluster_kernel', achieved=ach, peak=peak_issue,
+                                    unit='warp-instr/s', frac=ach / peak_issue, warp_instr_per_launch=wi, sm_mhz=sm_hz,
+                                    ncu_issue_active_pct=tf.get('issue_active_pct'),
+                                    note='peak = 148 SM x 4 issue slots x SM clock; instructions per launch from the ncu '
+                                         'capture in profiles/ (same batch and body), launch time measured live')
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -254,8 +258,8 @@ def run_ours(args):
                                          'batch=%d bodies per GPU, V=%d, F=%d, synthetic DSC contact pairs' % (B, V, F),
                                 bodies_per_gpu=B, total_bodies=world * B, geothres=GEOTHRES, euclthres=EUCLTHRES,
                                 contact_loss_weight=CONTACT_W, segments=len(a['segs']), region_pairs=len(a['regions']['classes']),
-                                l2_policy='per-step working set (tri12 %.0f MB + partials) exceeds the 126 MB L2'
-                                          % (B * 13824 * 48 / 1e6),
+                                l2_policy='per-step working set (packed leaf triangles %.0f MB + node records + partials) '
+                                          'exceeds the 126 MB L2' % (B * fit.topo.cluster_stats()['leaves'] * 32 * 48 / 1e6),
                                 body_iters_per_s=world * B / (ms_per_step * 1e-3), final_loss=final_loss),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              ms_per_step=e2e_ms),
