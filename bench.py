@@ -259,7 +259,7 @@ def run_ours(args):
                                 bodies_per_gpu=B, total_bodies=world * B, geothres=GEOTHRES, euclthres=EUCLTHRES,
                                 contact_loss_weight=CONTACT_W, segments=len(a['segs']), region_pairs=len(a['regions']['classes']),
                                 l2_policy='per-step working set (packed leaf triangles %.0f MB + node records + partials) '
-                                          'exceeds the 126 MB L2' % (B * fit.topo.cluster_stats()['leaves'] * 32 * 48 / 1e6),
+                                          'exceeds the 126 MB L2' % (B * fit.topo.cluster_stats()['leaves'] * fit.topo.cluster_stats()['leaf_faces'] * 48 / 1e6),
                                 body_iters_per_s=world * B / (ms_per_step * 1e-3), final_loss=final_loss),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              ms_per_step=e2e_ms),

@@ -111,8 +111,9 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
 
 /* Winding-number evaluation inside tuch_contact_query.  Callers of the reference only consume the
  * flag `winding_numbers(...) <= 0.99` (losses.py:82, loss.py:262), so the default mode evaluates the
- * sum hierarchically: the faces are clustered once per topology (leaves of <= 32 faces, super-clusters
- * of <= 8 leaves); per body, clusters farther than 2 (leaves) / 2.5 (super-clusters) radii from a query contribute through a
+ * sum hierarchically: the faces are clustered once per topology (leaves of <= 16 faces, mid groups of
+ * <= 8 leaves, top groups of <= 64 leaves); per body, nodes farther than 2 (leaves) / 2.5 (groups) radii
+ * from a query contribute through a
  * second-order multipole expansion of the solid-angle integrand (max abs error measured 4.9e-3 on the winding
  * number), nearer leaves are summed exactly, and every query whose value falls within 0.04 of the 0.99
  * threshold is re-evaluated exactly over all faces -- the exterior flags are those of the exact sum.
@@ -124,15 +125,16 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
 #define TUCH_WINDING_FAST 1
 int tuch_topology_set_template(tuch_topology* topo, const float* verts_host);
 int tuch_topology_set_winding_mode(tuch_topology* topo, int mode);
-int tuch_topology_cluster_stats(const tuch_topology* topo, int* n_leaves, int* n_supers);
-/* the hierarchy builder without a device: leaf_face_out[n_leaves][32] (face id or -1),
- * super_off_out[n_supers + 1] (leaf ranges), vtile_out[n_tiles][32] (vertex tiles: the 32 neighbouring
- * vertices one warp queries / one word of the cluster-ordered geodesic mask covers; -1 = padding);
- * output pointers may be NULL to query the counts only. */
+int tuch_topology_cluster_stats(const tuch_topology* topo, int* n_leaves, int* n_mids, int* n_tops, int* n_tiles,
+                                int* leaf_faces);
+/* the hierarchy builder without a device: leaf_face_out[n_leaves][16] (face id or -1),
+ * mid_off_out[n_mids + 1] (leaf ranges), top_off_out[n_tops + 1] (mid ranges), vtile_out[n_tiles][32]
+ * (vertex tiles: the 32 neighbouring vertices one warp queries / one word of the cluster-ordered geodesic
+ * mask covers; -1 = padding); output pointers may be NULL to query the counts only. */
 int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float* verts_host,
-                           int32_t* leaf_face_out, int leaf_capacity, int32_t* super_off_out,
-                           int super_capacity, int32_t* vtile_out, int tile_capacity, int* n_leaves,
-                           int* n_supers, int* n_tiles);
+                           int32_t* leaf_face_out, int leaf_capacity, int32_t* mid_off_out, int mid_capacity,
+                           int32_t* top_off_out, int top_capacity, int32_t* vtile_out, int tile_capacity,
+                           int* n_leaves, int* n_mids, int* n_tops, int* n_tiles);
 
 /* ------------------------------------------------------------------ fused self-contact query
  * Replaces, for every body of the batch, losses.py:76-93 / loss.py:256-270:

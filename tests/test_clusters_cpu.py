@@ -13,11 +13,12 @@ def check_tree(model):
     faces = model['faces']
     F, V = len(faces), len(model['v_template'])
     t = tree_for(model)
-    leaf, sup, vt = t['leaf_face'], t['super_off'], t['vtile']
+    leaf, mid, top, vt = t['leaf_face'], t['mid_off'], t['top_off'], t['vtile']
     ids = leaf[leaf >= 0]
     assert len(ids) == F and np.array_equal(np.sort(ids), np.arange(F))            # a partition of the faces
     assert np.array_equal(np.sort(vt[vt >= 0]), np.arange(V))                      # a partition of the vertices
-    assert sup[0] == 0 and sup[-1] == len(leaf) and np.all(np.diff(sup) >= 1) and np.all(np.diff(sup) <= 24)
+    assert mid[0] == 0 and mid[-1] == len(leaf) and np.all(np.diff(mid) >= 1) and np.all(np.diff(mid) <= 24)
+    assert top[0] == 0 and top[-1] == len(mid) - 1 and np.all(np.diff(top) >= 1)
     for row in list(leaf) + list(vt):                                             # ascending ids, padding only at the end
         n = int((row >= 0).sum())
         assert n >= 1 and np.all(row[:n] >= 0) and np.all(row[n:] < 0) and np.all(np.diff(row[:n]) > 0)
@@ -29,7 +30,7 @@ def test_tree_small_and_full():
     check_tree(syn.make_body_model(10, 12, seed=0))
     t = check_tree(syn.make_lattice_body_model(seed=0))
     # near-minimal leaf count: the far field costs one evaluation per leaf
-    assert len(t['leaf_face']) <= 1.15 * (13776 // 32 + 1) and len(t['vtile']) <= 1.15 * (6890 // 32 + 1)
+    assert len(t['leaf_face']) <= 1.15 * (13776 // 16 + 1) and len(t['vtile']) <= 1.15 * (6890 // 32 + 1)
     check_tree(syn.make_body_model(84, 82, seed=0))
 
 

@@ -249,7 +249,7 @@ def _fast_vs_exact(assets, dev, batch, seed, template):
     a = ex.contact_query(verts, use_segments=False, want_nearest=False)
     b = fa.contact_query(verts, use_segments=False, want_nearest=False)
     stats = fa.cluster_stats()
-    assert stats['leaves'] >= len(assets['model']['faces']) // 32 and stats['supers'] >= 1
+    assert stats['leaves'] >= len(assets['model']['faces']) // stats['leaf_faces'] and stats['mids'] >= 1 and stats['tops'] >= 1
     err = (a['winding'] - b['winding']).abs()
     print('hierarchical winding: max |w_fast - w_exact| = %.2e' % float(err.max()))
     assert float(err.max()) < 5e-3, float(err.max())

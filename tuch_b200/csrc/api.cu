@@ -286,7 +286,7 @@ static void free_segments(tuch_topology* t) {
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
-    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_vtile); free_dev(t->d_maskP);
+    free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_maskP);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -332,13 +332,14 @@ static int install_clusters(tuch_topology* t, const float* verts_host, cudaStrea
     ClusterTree tree;
     if (int rc = build_cluster_tree(faces.data(), t->F, t->V, verts_host, tree)) return rc;
     TUCH_CUDA(cudaDeviceSynchronize());            // queued work may still read the old hierarchy
-    free_dev(t->d_leaf_face); free_dev(t->d_super_off); free_dev(t->d_vtile);
-    t->d_leaf_face = t->d_super_off = t->d_vtile = nullptr;
+    free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile);
+    t->d_leaf_face = t->d_mid_off = t->d_top_off = t->d_vtile = nullptr;
     t->has_clusters = false;
     if (int rc = upload(tree.leaf_face.data(), tree.leaf_face.size(), &t->d_leaf_face)) return rc;
-    if (int rc = upload(tree.super_off.data(), tree.super_off.size(), &t->d_super_off)) return rc;
+    if (int rc = upload(tree.mid_off.data(), tree.mid_off.size(), &t->d_mid_off)) return rc;
+    if (int rc = upload(tree.top_off.data(), tree.top_off.size(), &t->d_top_off)) return rc;
     if (int rc = upload(tree.vtile.data(), tree.vtile.size(), &t->d_vtile)) return rc;
-    t->K = tree.K; t->NS = tree.NS; t->T = tree.T;
+    t->K = tree.K; t->NM = tree.NM; t->NT = tree.NT; t->T = tree.T;
     t->has_clusters = true;
     return refresh_permuted_mask(t, st);
 }
@@ -352,24 +353,30 @@ TUCH_EXPORT int tuch_topology_set_template(tuch_topology* t, const float* verts_
 }
 
 TUCH_EXPORT int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float* verts_host,
-                                       int32_t* leaf_face_out, int leaf_capacity, int32_t* super_off_out,
-                                       int super_capacity, int32_t* vtile_out, int tile_capacity, int* n_leaves,
-                                       int* n_supers, int* n_tiles) {
+                                       int32_t* leaf_face_out, int leaf_capacity, int32_t* mid_off_out,
+                                       int mid_capacity, int32_t* top_off_out, int top_capacity,
+                                       int32_t* vtile_out, int tile_capacity, int* n_leaves, int* n_mids,
+                                       int* n_tops, int* n_tiles) {
     TUCH_REQUIRE(faces_host != nullptr && verts_host != nullptr && F > 0 && V > 0, "tuch_cluster_tree_host: need a mesh");
     for (size_t i = 0; i < (size_t)F * 3; ++i)
         TUCH_REQUIRE(faces_host[i] >= 0 && faces_host[i] < V, "tuch_cluster_tree_host: face index %d out of range", faces_host[i]);
     ClusterTree tree;
     if (int rc = build_cluster_tree(faces_host, F, V, verts_host, tree)) return rc;
     if (n_leaves) *n_leaves = tree.K;
-    if (n_supers) *n_supers = tree.NS;
+    if (n_mids) *n_mids = tree.NM;
+    if (n_tops) *n_tops = tree.NT;
     if (n_tiles) *n_tiles = tree.T;
     if (leaf_face_out != nullptr) {
         TUCH_REQUIRE(leaf_capacity >= tree.K, "tuch_cluster_tree_host: leaf capacity %d < %d", leaf_capacity, tree.K);
         std::copy(tree.leaf_face.begin(), tree.leaf_face.end(), leaf_face_out);
     }
-    if (super_off_out != nullptr) {
-        TUCH_REQUIRE(super_capacity >= tree.NS, "tuch_cluster_tree_host: super capacity %d < %d", super_capacity, tree.NS);
-        std::copy(tree.super_off.begin(), tree.super_off.end(), super_off_out);
+    if (mid_off_out != nullptr) {
+        TUCH_REQUIRE(mid_capacity >= tree.NM, "tuch_cluster_tree_host: mid capacity %d < %d", mid_capacity, tree.NM);
+        std::copy(tree.mid_off.begin(), tree.mid_off.end(), mid_off_out);
+    }
+    if (top_off_out != nullptr) {
+        TUCH_REQUIRE(top_capacity >= tree.NT, "tuch_cluster_tree_host: top capacity %d < %d", top_capacity, tree.NT);
+        std::copy(tree.top_off.begin(), tree.top_off.end(), top_off_out);
     }
     if (vtile_out != nullptr) {
         TUCH_REQUIRE(tile_capacity >= tree.T, "tuch_cluster_tree_host: tile capacity %d < %d", tile_capacity, tree.T);
@@ -385,10 +392,14 @@ TUCH_EXPORT int tuch_topology_set_winding_mode(tuch_topology* t, int mode) {
     return 0;
 }
 
-TUCH_EXPORT int tuch_topology_cluster_stats(const tuch_topology* t, int* n_leaves, int* n_supers) {
+TUCH_EXPORT int tuch_topology_cluster_stats(const tuch_topology* t, int* n_leaves, int* n_mids, int* n_tops,
+                                            int* n_tiles, int* leaf_faces) {
     TUCH_REQUIRE(t != nullptr, "tuch_topology_cluster_stats: null topology");
     if (n_leaves) *n_leaves = t->has_clusters ? t->K : 0;
-    if (n_supers) *n_supers = t->has_clusters ? t->NS : 0;
+    if (n_mids) *n_mids = t->has_clusters ? t->NM : 0;
+    if (n_tops) *n_tops = t->has_clusters ? t->NT : 0;
+    if (n_tiles) *n_tiles = t->has_clusters ? t->T : 0;
+    if (leaf_faces) *leaf_faces = WC_LEAF;
     return 0;
 }
 
@@ -567,12 +578,12 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         }
     }
     const bool fast = want_w && t->winding_mode == TUCH_WINDING_FAST && t->has_clusters;
-    const int S = !want_w ? 1 : fast ? cluster_splits(B, t->T, t->NS, sm_count()) : strip_splits(B, V, Lp, sm_count());
+    const int S = !want_w ? 1 : fast ? cluster_splits(B, t->T, t->NT, sm_count()) : strip_splits(B, V, Lp, sm_count());
 
     Scratch sc;
     const size_t h_tri = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * 3 * (size_t)B * t->K * WC_LEAF
                                                     : sizeof(float4) * 2 * (size_t)B * Lp);
-    const size_t h_info = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * WC_NODE_F4 * (size_t)B * (t->NS + t->K)
+    const size_t h_info = sc.plan(!want_w ? 0 : fast ? sizeof(float4) * WC_NODE_F4 * (size_t)B * (t->NT + t->NM + t->K)
                                                      : sizeof(float4) * (size_t)B * (Lp / WS_TILE));
     const size_t h_ref = sc.plan(fast ? sizeof(int) * ((size_t)B * V + 1) : 0);
     const bool nn_tiles = want_nn && t->has_maskP && vert4_out == nullptr;
@@ -597,8 +608,8 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         float* w = winding ? winding : sc.get<float>(h_w);
         float4* info = sc.get<float4>(h_info);
         if (fast) {
-            ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_super_off, t->d_vtile, strip4, info,
-                         sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NS, S, t->T};
+            ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, t->d_vtile, strip4, info,
+                         sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
             if (int rc = launch_winding_clusters(j, st)) return rc;
         } else {
             if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;

@@ -36,16 +36,18 @@ namespace {
 // Recursive bisection of a set of items (faces or vertices) that live on the mesh: connected components
 // are never mixed, a connected set is cut at a balanced position along the principal axis of its item
 // positions, and small pieces cut off by the plane are handed to the other half.  Leaves hold <= `leaf`
-// items (ascending ids); optionally consecutive leaves are grouped into supers of <= `super_leaves`.
+// items (ascending ids); optionally consecutive leaves are grouped into mids of <= `mid_leaves` leaves and
+// consecutive mids into tops of <= `top_leaves` leaves.
 struct TreeBuilder {
-    int N = 0, leaf = 32, super_leaves = 0;
+    int N = 0, leaf = 32, mid_leaves = 0, top_leaves = 0;
     std::vector<float> cen;                  // [N][3] item positions
     std::vector<int> adj_off, adj;           // item adjacency, CSR
     std::vector<int> stamp;
     int cur_stamp = 0;
     std::vector<int>* leaf_items = nullptr;  // [n_leaves][leaf], -1 = padding
-    std::vector<int>* super_off = nullptr;
-    int n_leaves = 0, n_supers = 0;
+    std::vector<int>* mid_off = nullptr;     // [n_mids + 1] leaf ranges
+    std::vector<int>* top_off = nullptr;     // [n_tops + 1] mid ranges
+    int n_leaves = 0, n_mids = 0, n_tops = 0;
 
     void set_adjacency(std::vector<std::vector<int>>& nb) {
         adj_off.assign(N + 1, 0);
@@ -82,32 +84,34 @@ struct TreeBuilder {
         return comps;
     }
 
-    void emit_leaf(const std::vector<int>& fs) {
+    void open_groups(bool& in_mid, bool& in_top, int want_leaves) {
+        if (top_off != nullptr && !in_top && want_leaves <= top_leaves) { top_off->push_back(n_mids); ++n_tops; in_top = true; }
+        if (mid_off != nullptr && !in_mid && want_leaves <= mid_leaves) { mid_off->push_back(n_leaves); ++n_mids; in_mid = true; }
+    }
+
+    void emit_leaf(const std::vector<int>& fs, bool in_mid, bool in_top) {
+        open_groups(in_mid, in_top, 1);                          // a leaf outside any group gets its own
         for (int i = 0; i < leaf; ++i) leaf_items->push_back(i < (int)fs.size() ? fs[i] : -1);
         ++n_leaves;
     }
 
-    void split(std::vector<int> fs, bool in_super) {           // fs ascending
+    void split(std::vector<int> fs, bool in_mid, bool in_top) {           // fs ascending
         const int n = (int)fs.size();
         const int want_leaves = (n + leaf - 1) / leaf;
-        if (super_leaves > 0 && !in_super && want_leaves <= super_leaves) {
-            super_off->push_back(n_leaves);
-            ++n_supers;
-            in_super = true;
-        }
+        open_groups(in_mid, in_top, want_leaves);
         std::vector<std::vector<int>> comps = components(fs);
         if (comps.size() > 1) {
             // pack small components together (a leaf may hold several of them) as long as they fit
             std::vector<int> bag;
             for (auto& c : comps) {
-                if ((int)c.size() > leaf) { split(std::move(c), in_super); continue; }
-                if ((int)(bag.size() + c.size()) > leaf) { std::sort(bag.begin(), bag.end()); emit_leaf(bag); bag.clear(); }
+                if ((int)c.size() > leaf) { split(std::move(c), in_mid, in_top); continue; }
+                if ((int)(bag.size() + c.size()) > leaf) { std::sort(bag.begin(), bag.end()); emit_leaf(bag, in_mid, in_top); bag.clear(); }
                 bag.insert(bag.end(), c.begin(), c.end());
             }
-            if (!bag.empty()) { std::sort(bag.begin(), bag.end()); emit_leaf(bag); }
+            if (!bag.empty()) { std::sort(bag.begin(), bag.end()); emit_leaf(bag, in_mid, in_top); }
             return;
         }
-        if (n <= leaf) { emit_leaf(fs); return; }
+        if (n <= leaf) { emit_leaf(fs, in_mid, in_top); return; }
         // principal axis of the item positions (power iteration on the 3x3 covariance, fp64)
         double mean[3] = {0, 0, 0};
         for (int f : fs) for (int a = 0; a < 3; ++a) mean[a] += cen[3 * f + a];
@@ -159,15 +163,16 @@ struct TreeBuilder {
         };
         give_fragments(l, r);
         give_fragments(r, l);
-        split(std::move(l), in_super);
-        split(std::move(r), in_super);
+        split(std::move(l), in_mid, in_top);
+        split(std::move(r), in_mid, in_top);
     }
 
     void run() {
         std::vector<int> all(N);
         std::iota(all.begin(), all.end(), 0);
-        split(std::move(all), false);
-        if (super_off) super_off->push_back(n_leaves);
+        split(std::move(all), false, false);
+        if (mid_off) mid_off->push_back(n_leaves);
+        if (top_off) top_off->push_back(n_mids);
     }
 };
 
@@ -187,8 +192,8 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
         for (int e = 0; e < 3; ++e) ef[edge_key(faces[3 * t + e], faces[3 * t + (e + 1) % 3])].push_back(t);
     {   // faces: neighbours share an edge
         TreeBuilder tb;
-        tb.N = F; tb.leaf = WC_LEAF; tb.super_leaves = WC_SUPER_LEAVES;
-        tb.leaf_items = &out.leaf_face; tb.super_off = &out.super_off;
+        tb.N = F; tb.leaf = WC_LEAF; tb.mid_leaves = WC_MID_LEAVES; tb.top_leaves = WC_TOP_LEAVES;
+        tb.leaf_items = &out.leaf_face; tb.mid_off = &out.mid_off; tb.top_off = &out.top_off;
         tb.cen.resize((size_t)F * 3);
         for (int t = 0; t < F; ++t)
             for (int a = 0; a < 3; ++a)
@@ -198,7 +203,7 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
             for (int x : kv.second) for (int y : kv.second) if (x != y) nb[x].push_back(y);
         tb.set_adjacency(nb);
         tb.run();
-        out.K = tb.n_leaves; out.NS = tb.n_supers;
+        out.K = tb.n_leaves; out.NM = tb.n_mids; out.NT = tb.n_tops;
     }
     {   // vertices: neighbours share an edge; vertices without faces end up in tiles of their own
         TreeBuilder tb;
@@ -242,8 +247,9 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// One warp per node (supers first, then leaves).  Record layout (all moments pre-scaled so that the
-// kernel's sum is Omega / 2, the quantity winding_finalize expects):
+// One warp per node; nodes are laid out [tops | mids | leaves].  The two half-warps walk alternate leaves
+// of the node, one lane per face slot.  Record layout (all moments pre-scaled so that the kernel's sum is
+// Omega / 2, the quantity the finalize step expects):
 //   f0 = (p, (beta R)^2)                    f1 = 0.5 (M0, tr M1)
 //   f2 = -1.5 (Qxx, Qyy, Qzz, 2Qxy)         f3 = (-1.5 * 2Qxz, -1.5 * 2Qyz, -0.75 ux, -0.75 uy)
 //   f4 = (-0.75 uz, 3.75 Txxx, 3.75 Tyyy, 3.75 Tzzz)
@@ -251,21 +257,25 @@ __device__ __forceinline__ float warp_max(float v) {
 // Q = sym(M1), u_k = 2 (a.S)_k + a_k tr S, T = symmetrised sum_t a_t (x) S_t.
 __global__ void __launch_bounds__(128)
 cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restrict__ faces,
-                    const int* __restrict__ leaf_face, const int* __restrict__ super_off, int K, int NS,
-                    float beta_leaf, float beta_super, float4* __restrict__ ctri, float4* __restrict__ nodes) {
+                    const int* __restrict__ leaf_face, const int* __restrict__ mid_off,
+                    const int* __restrict__ top_off, int K, int NM, int NT, float beta_leaf, float beta_group,
+                    float4* __restrict__ ctri, float4* __restrict__ nodes) {
     const int b = blockIdx.y;
     const int node = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (node >= NS + K) return;
-    const bool is_leaf = node >= NS;
-    const int l0 = is_leaf ? node - NS : super_off[node];
-    const int l1 = is_leaf ? l0 + 1 : super_off[node + 1];
+    if (node >= NT + NM + K) return;
+    const bool is_leaf = node >= NT + NM;
+    int l0, l1;
+    if (is_leaf) { l0 = node - NT - NM; l1 = l0 + 1; }
+    else if (node >= NT) { l0 = mid_off[node - NT]; l1 = mid_off[node - NT + 1]; }
+    else { l0 = mid_off[top_off[node]]; l1 = mid_off[top_off[node + 1]]; }
     const float* vb = verts + (size_t)b * V * 3;
+    const int half = lane >> 4, slot = lane & (WC_LEAF - 1);
 
     // pass 1: area-weighted centre (falls back to the plain centroid mean for zero-area nodes)
     float wsum = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f, cnt = 0.f;
-    for (int l = l0; l < l1; ++l) {
-        const int f = leaf_face[(size_t)l * WC_LEAF + lane];
+    for (int l = l0 + half; l < l1; l += 2) {
+        const int f = leaf_face[(size_t)l * WC_LEAF + slot];
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bv = A, C = A;
         if (f >= 0) {
             const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
@@ -283,7 +293,7 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
             ux += gx; uy += gy; uz += gz; cnt += 1.f;
         }
         if (is_leaf) {
-            float4* o = ctri + (((size_t)b * K + l) * WC_LEAF + lane) * 3;
+            float4* o = ctri + (((size_t)b * K + l) * WC_LEAF + slot) * 3;
             o[0] = A; o[1] = Bv; o[2] = C;
         }
     }
@@ -304,8 +314,8 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
     float uvx = 0.f, uvy = 0.f, uvz = 0.f;
     float txxx = 0.f, tyyy = 0.f, tzzz = 0.f, txxy = 0.f, txxz = 0.f, tyyx = 0.f, tyyz = 0.f, tzzx = 0.f, tzzy = 0.f,
           txyz = 0.f;
-    for (int l = l0; l < l1; ++l) {
-        const int f = leaf_face[(size_t)l * WC_LEAF + lane];
+    for (int l = l0 + half; l < l1; l += 2) {
+        const int f = leaf_face[(size_t)l * WC_LEAF + slot];
         if (f < 0) continue;
         const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
         const float ax = vb[3 * i0] - px, ay = vb[3 * i0 + 1] - py, az = vb[3 * i0 + 2] - pz;
@@ -349,8 +359,8 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
     txxy = warp_sum(txxy); txxz = warp_sum(txxz); tyyx = warp_sum(tyyx); tyyz = warp_sum(tyyz);
     tzzx = warp_sum(tzzx); tzzy = warp_sum(tzzy); txyz = warp_sum(txyz);
     if (lane == 0) {
-        float4* o = nodes + ((size_t)b * (NS + K) + node) * WC_NODE_F4;
-        const float beta = is_leaf ? beta_leaf : beta_super;
+        float4* o = nodes + ((size_t)b * (NT + NM + K) + node) * WC_NODE_F4;
+        const float beta = is_leaf ? beta_leaf : beta_group;
         o[0] = make_float4(px, py, pz, r2 * (beta * beta * 1.0002f));
         o[1] = make_float4(0.5f * m0x, 0.5f * m0y, 0.5f * m0z, 0.5f * tr);
         o[2] = make_float4(-1.5f * qxx, -1.5f * qyy, -1.5f * qzz, -1.5f * qxy);
@@ -382,13 +392,15 @@ __device__ __forceinline__ float node_far_field(const float4* __restrict__ rec, 
     return fmaf(t0, i3, fmaf(t1, i5, t2 * i7));
 }
 
-// grid (groups of WC_WARPS vertex tiles, super splits, bodies); one query per lane, one vertex tile per warp
+// grid (groups of WC_WARPS vertex tiles, top splits, bodies); one query per lane, one vertex tile per warp.
+// Tops and mids open for the whole warp as soon as one query is near; leaves are near or far per query.
+// In the near pass the two half-warps serve two near queries at a time, one lane per face of the leaf.
 __global__ void __launch_bounds__(WC_WARPS * 32)
 winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ vtile,
                        const float4* __restrict__ ctri, const float4* __restrict__ nodes,
-                       const int* __restrict__ super_off, float* __restrict__ partial, int V, int T, int K, int NS,
-                       int supers_per_split, int S) {
-    __shared__ float s_acc[WC_WARPS][32 * 33];
+                       const int* __restrict__ mid_off, const int* __restrict__ top_off,
+                       float* __restrict__ partial, int V, int T, int K, int NM, int NT, int tops_per_split, int S) {
+    __shared__ float s_acc[WC_WARPS][32 * (WC_LEAF + 1)];
     const int b = blockIdx.z, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WC_WARPS + warp;               // one vertex tile per warp
@@ -398,52 +410,67 @@ winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ 
     const float* vb = verts + (size_t)b * V * 3;
     const float px = vb[3 * qi], py = vb[3 * qi + 1], pz = vb[3 * qi + 2];
     float* acc = s_acc[warp];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) acc[q * 33 + lane] = 0.f;
+    for (int k = lane; k < 32 * (WC_LEAF + 1); k += 32) acc[k] = 0.f;
     __syncwarp();
 
-    const float4* nb = nodes + (size_t)b * (NS + K) * WC_NODE_F4;
+    const float4* nb = nodes + (size_t)b * (NT + NM + K) * WC_NODE_F4;
     const float4* tb = ctri + (size_t)b * K * WC_LEAF * 3;
-    const int s0 = split * supers_per_split, s1 = min(NS, s0 + supers_per_split);
+    const int half = lane >> 4, slot = lane & (WC_LEAF - 1);
+    const int t0 = split * tops_per_split, t1 = min(NT, t0 + tops_per_split);
     float far = 0.f;
-    for (int s = s0; s < s1; ++s) {
-        const float4* rec = nb + (size_t)s * WC_NODE_F4;
-        const float4 c = __ldg(rec);
-        const float x = c.x - px, y = c.y - py, z = c.z - pz;
-        const float d2 = fmaf(z, z, fmaf(y, y, x * x));
-        if (!__any_sync(0xffffffffu, d2 < c.w)) {
-            far += node_far_field(rec, x, y, z, d2);
+    for (int t = t0; t < t1; ++t) {
+        const float4* trec = nb + (size_t)t * WC_NODE_F4;
+        const float4 tc = __ldg(trec);
+        const float tx = tc.x - px, ty = tc.y - py, tz = tc.z - pz;
+        const float td2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+        if (!__any_sync(0xffffffffu, td2 < tc.w)) {
+            far += node_far_field(trec, tx, ty, tz, td2);
             continue;
         }
-        const int l0 = __ldg(super_off + s), l1 = __ldg(super_off + s + 1);
-        for (int l = l0; l < l1; ++l) {
-            const float4* lrec = nb + (size_t)(NS + l) * WC_NODE_F4;
-            const float4 lc = __ldg(lrec);
-            const float lx = lc.x - px, ly = lc.y - py, lz = lc.z - pz;
-            const float ld2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
-            const bool near = ld2 < lc.w;
-            unsigned m = __ballot_sync(0xffffffffu, near);
-            if (m != 0xffffffffu) {
-                const float v = node_far_field(lrec, lx, ly, lz, ld2);
-                far += near ? 0.f : v;
+        const int m0 = __ldg(top_off + t), m1 = __ldg(top_off + t + 1);
+        for (int m = m0; m < m1; ++m) {
+            const float4* mrec = nb + (size_t)(NT + m) * WC_NODE_F4;
+            const float4 mc = __ldg(mrec);
+            const float mx = mc.x - px, my = mc.y - py, mz = mc.z - pz;
+            const float md2 = fmaf(mz, mz, fmaf(my, my, mx * mx));
+            if (!__any_sync(0xffffffffu, md2 < mc.w)) {
+                far += node_far_field(mrec, mx, my, mz, md2);
+                continue;
             }
-            if (m != 0u) {                                       // lanes become faces of this leaf
-                const float4* t = tb + ((size_t)l * WC_LEAF + lane) * 3;
-                const float4 A = __ldg(t), Bv = __ldg(t + 1), C = __ldg(t + 2);
-                while (m != 0u) {
-                    const int q = __ffs(m) - 1;
-                    m &= m - 1u;
-                    const float qx = __shfl_sync(0xffffffffu, px, q), qy = __shfl_sync(0xffffffffu, py, q),
-                                qz = __shfl_sync(0xffffffffu, pz, q);
-                    acc[q * 33 + lane] += half_solid_angle_n(qx, qy, qz, A, Bv, C);
+            const int l0 = __ldg(mid_off + m), l1 = __ldg(mid_off + m + 1);
+            for (int l = l0; l < l1; ++l) {
+                const float4* lrec = nb + (size_t)(NT + NM + l) * WC_NODE_F4;
+                const float4 lc = __ldg(lrec);
+                const float lx = lc.x - px, ly = lc.y - py, lz = lc.z - pz;
+                const float ld2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                const bool near = ld2 < lc.w;
+                unsigned nm = __ballot_sync(0xffffffffu, near);
+                if (nm != 0xffffffffu) {
+                    const float v = node_far_field(lrec, lx, ly, lz, ld2);
+                    far += near ? 0.f : v;
+                }
+                if (nm != 0u) {                                  // lanes become faces of this leaf
+                    const float4* f = tb + ((size_t)l * WC_LEAF + slot) * 3;
+                    const float4 A = __ldg(f), Bv = __ldg(f + 1), C = __ldg(f + 2);
+                    while (nm != 0u) {                           // two near queries per step, one per half-warp
+                        const int q0 = __ffs(nm) - 1;
+                        nm &= nm - 1u;
+                        const int q1 = nm != 0u ? __ffs(nm) - 1 : -1;
+                        nm &= nm - 1u;                           // 0 & anything = 0 when nothing is left
+                        const int q = half == 0 ? q0 : q1;
+                        const int src = q >= 0 ? q : q0;
+                        const float qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src),
+                                    qz = __shfl_sync(0xffffffffu, pz, src);
+                        if (q >= 0) acc[q * (WC_LEAF + 1) + slot] += half_solid_angle_n(qx, qy, qz, A, Bv, C);
+                    }
                 }
             }
         }
     }
     __syncwarp();
     float near_sum = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) near_sum += acc[lane * 33 + j];
+#pragma unroll
+    for (int j = 0; j < WC_LEAF; ++j) near_sum += acc[lane * (WC_LEAF + 1) + j];
     if (qv >= 0) partial[((size_t)b * S + split) * V + qi] = far + near_sum;
 }
 
@@ -465,24 +492,25 @@ __global__ void cluster_finalize_kernel(const float* __restrict__ partial, int V
     }
 }
 
-// exact winding number (all faces, one lane per face slot) of every listed query; one CTA per entry,
-// its warps stride over the leaves and their partial sums are combined in a fixed order
+// exact winding number (all face slots, one lane per slot) of every listed query; one CTA per entry, its
+// warps stride over the packed face slots and their partial sums are combined in a fixed order
 __global__ void __launch_bounds__(256)
 cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict__ ctri, int V, int K,
                       const int* __restrict__ refine_list, float* __restrict__ winding) {
     __shared__ float s_part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = refine_list[0];
+    const int n_slots = K * WC_LEAF;
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const int id = refine_list[1 + e];
         const int b = id / V, q = id - b * V;
         const float* p = verts + ((size_t)b * V + q) * 3;
         const float px = p[0], py = p[1], pz = p[2];
-        const float4* t = ctri + (((size_t)b * K + warp) * WC_LEAF + lane) * 3;
+        const float4* t = ctri + (size_t)b * n_slots * 3;
         float acc = 0.f;
 #pragma unroll 2
-        for (int l = warp; l < K; l += 8, t += 8 * WC_LEAF * 3) {
-            const float4 A = __ldg(t), Bv = __ldg(t + 1), C = __ldg(t + 2);
+        for (int i = threadIdx.x; i < n_slots; i += 256) {
+            const float4 A = __ldg(t + 3 * i), Bv = __ldg(t + 3 * i + 1), C = __ldg(t + 3 * i + 2);
             acc += half_solid_angle_n(px, py, pz, A, Bv, C);
         }
         acc = warp_sum(acc);
@@ -501,33 +529,33 @@ cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict_
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-int cluster_splits(int B, int T, int NS, int sm_count) {
+int cluster_splits(int B, int T, int NT, int sm_count) {
     const int qtiles = cdiv(T, WC_WARPS);
     const long long want = (long long)sm_count * 6;                     // CTAs in flight
     int S = (int)((want + (long long)qtiles * B - 1) / ((long long)qtiles * B));
-    S = std::max(1, std::min(S, NS));
-    const int per = cdiv(NS, S);
-    return cdiv(NS, per);
+    S = std::max(1, std::min(S, NT));
+    const int per = cdiv(NT, S);
+    return cdiv(NT, per);
 }
 
 int launch_winding_clusters(const ClusterJob& j, cudaStream_t st) {
     if (j.B == 0 || j.V == 0) return 0;
     {
-        dim3 grid(cdiv(j.NS + j.K, 4), j.B);
-        // development knobs (scripts/time_contact.py sweeps them); the shipped values are the constants
+        dim3 grid(cdiv(j.NT + j.NM + j.K, 4), j.B);
+        // development knobs (scripts/sweep_beta.sh sweeps them); the shipped values are the constants
         static const float beta_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : WC_BETA;
-        static const float beta_super = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : WC_BETA_SUPER;
-        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.super_off, j.K, j.NS, beta_leaf,
-                                                  beta_super, j.ctri, j.nodes);
+        static const float beta_group = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : WC_BETA_GROUP;
+        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.mid_off, j.top_off, j.K, j.NM,
+                                                  j.NT, beta_leaf, beta_group, j.ctri, j.nodes);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
     {
-        const int per = cdiv(j.NS, j.S);
+        const int per = cdiv(j.NT, j.S);
         dim3 grid(cdiv(j.T, WC_WARPS), j.S, j.B);
         KernelTimer timer("winding_kernel", st);
-        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(j.verts, j.vtile, j.ctri, j.nodes, j.super_off, j.partial,
-                                                               j.V, j.T, j.K, j.NS, per, j.S);
+        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(j.verts, j.vtile, j.ctri, j.nodes, j.mid_off, j.top_off,
+                                                               j.partial, j.V, j.T, j.K, j.NM, j.NT, per, j.S);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     {

@@ -6,12 +6,13 @@
 
 namespace tuch {
 
-constexpr int WC_LEAF = 32;          // faces per leaf cluster = one warp lane per face in the near pass
-constexpr int WC_SUPER_LEAVES = 8;   // leaves per super-cluster (second level of the far field)
+constexpr int WC_LEAF = 16;          // faces per leaf cluster = one half-warp lane per face in the near pass
+constexpr int WC_MID_LEAVES = 8;     // leaves per mid-level group (128 faces) ...
+constexpr int WC_TOP_LEAVES = 64;    // ... and per top-level group (1024 faces) of the far field
 constexpr int WC_NODE_F4 = 7;        // float4 per node record (centre + radius, scaled moments)
 constexpr int WC_WARPS = 8;          // warps per CTA of the winding kernel; one query per lane
 constexpr float WC_BETA = 2.0f;      // a leaf is "far" for a query beyond WC_BETA x its radius ...
-constexpr float WC_BETA_SUPER = 2.5f;   // ... a super-cluster (larger, so larger absolute error) beyond 2.5 x
+constexpr float WC_BETA_GROUP = 2.5f;   // ... a mid / top group (larger, so larger absolute error) beyond 2.5 x
 constexpr float WC_MARGIN = 0.04f;   // |w - 0.99| below this is re-evaluated exactly (8 x the worst far-field
                                      // error measured at these opening parameters: 4.9e-3)
 
@@ -19,11 +20,12 @@ constexpr float WC_MARGIN = 0.04f;   // |w - 0.99| below this is re-evaluated ex
 // (the template, or the first body seen).
 struct ClusterTree {
     std::vector<int> leaf_face;      // [K][WC_LEAF] face id or -1 (padding)
-    std::vector<int> super_off;      // [NS + 1] leaf ranges of the super-clusters
+    std::vector<int> mid_off;        // [NM + 1] leaf ranges of the mid-level groups
+    std::vector<int> top_off;        // [NT + 1] mid ranges of the top-level groups
     std::vector<int> vtile;          // [T][32] vertex tiles: vertex id or -1 (padding); the 32 vertices of
                                      // a tile are neighbours on the mesh (queries of one warp, candidate
                                      // rows of one mask word)
-    int K = 0, NS = 0, T = 0;
+    int K = 0, NM = 0, NT = 0, T = 0;
 };
 int build_cluster_tree(const int* faces, int F, int V, const float* verts, ClusterTree& out);
 
@@ -31,22 +33,23 @@ struct ClusterJob {
     const float* verts;              // [B][V][3] mesh vertices (also the queries, in qperm order)
     const int* faces;                // [F][3]
     const int* leaf_face;            // [K][WC_LEAF]
-    const int* super_off;            // [NS + 1]
+    const int* mid_off;              // [NM + 1]
+    const int* top_off;              // [NT + 1]
     const int* vtile;                // [T][32]
     float4* ctri;                    // [B][K][WC_LEAF][3] scratch: corners a | b | c per face slot, the face's
                                      // normal (b - a) x (c - a) in the three w components
-    float4* nodes;                   // [B][NS + K][WC_NODE_F4] scratch: super records first, then leaves
+    float4* nodes;                   // [B][NT + NM + K][WC_NODE_F4] scratch: tops, then mids, then leaves
     float* partial;                  // [B][S][V] scratch
     float* winding;                  // [B][V] out
     int* refine_list;                // [1 + B * V] scratch: count, then b * V + q entries
-    int B, V, K, NS, S, T;
+    int B, V, K, NM, NT, S, T;
 };
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);
 int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, int B, int V, int T,
                          float4* vert4p, float4* tinfo, int* argmin, float* minval, cudaStream_t st);
 
-int cluster_splits(int B, int T, int NS, int sm_count);
+int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);
 
 }  // namespace tuch

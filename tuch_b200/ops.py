@@ -81,18 +81,20 @@ def strip_stream(faces):
 
 # ------------------------------------------------------------------ a1-a3 forward kernels
 def cluster_tree(faces, verts):
-    """Host-only: the hierarchy of clusters.cu -> dict(leaf_face[K,32], super_off[NS+1], vtile[T,32])."""
+    """Host-only: the hierarchy of clusters.cu -> dict(leaf_face[K,16], mid_off[NM+1], top_off[NT+1], vtile[T,32])."""
     f = _i32_host(np.asarray(faces).reshape(-1, 3))
     v = np.ascontiguousarray(np.asarray(verts).reshape(-1, 3), dtype=np.float32)
-    k, ns, nt = C.c_int32(0), C.c_int32(0), C.c_int32(0)
-    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), None, 0, None, 0, None, 0, C.byref(k), C.byref(ns),
-                                       C.byref(nt)), 'tuch_cluster_tree_host')
-    leaf = np.empty((k.value, 32), np.int32)
-    sup = np.empty(ns.value + 1, np.int32)
-    vt = np.empty((nt.value, 32), np.int32)
-    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), _hp(leaf), k.value, _hp(sup), ns.value, _hp(vt),
-                                       nt.value, C.byref(k), C.byref(ns), C.byref(nt)), 'tuch_cluster_tree_host')
-    return dict(leaf_face=leaf, super_off=sup, vtile=vt)
+    k, nm, nt, t = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    refs = (C.byref(k), C.byref(nm), C.byref(nt), C.byref(t))
+    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), None, 0, None, 0, None, 0, None, 0, *refs),
+          'tuch_cluster_tree_host')
+    leaf = np.empty((k.value, 16), np.int32)
+    mid = np.empty(nm.value + 1, np.int32)
+    top = np.empty(nt.value + 1, np.int32)
+    vt = np.empty((t.value, 32), np.int32)
+    check(lib().tuch_cluster_tree_host(_hp(f), len(f), len(v), _hp(v), _hp(leaf), k.value, _hp(mid), nm.value, _hp(top),
+                                       nt.value, _hp(vt), t.value, *refs), 'tuch_cluster_tree_host')
+    return dict(leaf_face=leaf, mid_off=mid, top_off=top, vtile=vt)
 
 
 def pairwise_dist(x, y, squared=True):
@@ -197,9 +199,11 @@ class Topology:
         check(lib().tuch_topology_set_winding_mode(self._h, int(mode)), 'tuch_topology_set_winding_mode')
 
     def cluster_stats(self):
-        k, ns = C.c_int32(0), C.c_int32(0)
-        check(lib().tuch_topology_cluster_stats(self._h, C.byref(k), C.byref(ns)), 'tuch_topology_cluster_stats')
-        return dict(leaves=int(k.value), supers=int(ns.value))
+        k, nm, nt, t, lf = (C.c_int32(0) for _ in range(5))
+        check(lib().tuch_topology_cluster_stats(self._h, C.byref(k), C.byref(nm), C.byref(nt), C.byref(t), C.byref(lf)),
+              'tuch_topology_cluster_stats')
+        return dict(leaves=int(k.value), mids=int(nm.value), tops=int(nt.value), vertex_tiles=int(t.value),
+                    leaf_faces=int(lf.value))
 
     # geomask = geodist > geothres (smplifydc.py:65)
     def set_geodist(self, geodist, geothres):
