@@ -286,6 +286,27 @@ int tuch_regressor_contact_loss(const tuch_topology* topo, const float* verts, i
                                 float* g_verts, int32_t* counts_out, int32_t* sel_out, int32_t* hd_argmin_out,
                                 uint8_t* hd_exterior_out, void* stream);
 
+/* ------------------------------------------------------------------ f2  estimate_translation
+ * tuch/utils/geometry.py:114-205: camera translation that brings the 3-D joints S closest to their 2-D
+ * detections (weighted least squares, weights sqrt(conf)); bodies with has_2d_kp_anno use the joints
+ * [n_openpose, J), the others [0, n_openpose) (:192-199); a body whose selected confidences sum to 0 gets
+ * zeros (:201).  fp32 inputs, fp64 arithmetic, fp32 result -- as the reference's numpy code.  A singular
+ * system (the reference raises LinAlgError) yields non-finite output.
+ * S[B,J,3], joints_2d[B,J,3] (x, y, conf), has_2d_kp_anno uint8 [B] -> out[B,3]. */
+int tuch_estimate_translation(const float* S, const float* joints_2d, const uint8_t* has_2d_kp_anno, int B, int J,
+                              int n_openpose, float focal_length, float img_size, float* out, void* stream);
+
+/* ------------------------------------------------------------------ f3  pose bookkeeping
+ * rotation_matrix_to_angle_axis of torchgeometry==0.1.2 (third-party; call site train_module.py:208-211):
+ * rotmat[N,3,cols] with cols = 3 or 4 (homogeneous [R | t]) -> out[N,3]. */
+int tuch_rotmat_to_angle_axis(const float* rotmat, int N, int cols, float* out, void* stream);
+/* FitsDict.rotate_pose / flip_pose (tuch/train/fits_dict.py:89-119) for a batch of poses [B,D]:
+ * rot_deg[B] in-plane rotation in degrees (NULL = none), is_flipped uint8 [B] (NULL = none),
+ * flip_perm[D] = SMPL_POSE_FLIP_PERM.  flip_first == 0: out = flip(rotate(pose, rot)) (__getitem__, :73);
+ * flip_first != 0: out = rotate(flip(pose), rot) (__setitem__ passes -rot, :83). */
+int tuch_fits_pose_transform(const float* pose, const float* rot_deg, const uint8_t* is_flipped,
+                             const int32_t* flip_perm, int B, int D, int flip_first, float* out, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer conveniences
  * Same as the calls above with HOST buffers; copies in/out on an internal stream and
  * synchronises.  Used by non-torch callers and by the end-to-end benchmark leg. */

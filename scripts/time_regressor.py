@@ -1,0 +1,40 @@
+"""Dev tool: time RegressorLoss.contact_loss's fused path (tuch_regressor_contact_loss, forward + vertex
+gradient) on SMPL-sized bodies with a 20k-point HD model."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tuch_b200 import ops, synthetic as syn
+from tuch_b200.utils.segmentation import BatchBodySegment
+from oracle import lbs as olbs
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+dev = torch.device('cuda:0')
+m = syn.make_lattice_body_model()
+V = len(m['v_template'])
+geo = syn.make_geodesics(m['v_template'], m['faces'], cache_dir='/tmp/tuch_b200_cache')
+segs = syn.make_segments(m)
+hd_reg, hd_fidx = syn.make_hd_regressor(m, n_hd=20000)
+topo = ops.Topology(m['faces'], V, dev)
+topo.set_template(m['v_template'])
+topo.set_geodist(torch.tensor(geo, device=dev), 0.3)
+bbs = BatchBodySegment(list(segs.keys()), torch.tensor(m['faces'], device=dev), segment_data=segs)
+topo.set_segments(bbs.topology_entries())
+topo.set_hd(hd_reg, hd_fidx)
+tm = olbs.to_torch_model(m)
+nb = min(B, 16)
+pose = torch.tensor(syn.fold_arms_pose(nb, seed=7))
+betas = torch.tensor(np.random.default_rng(7).normal(0, 0.5, size=(nb, 10)).astype(np.float32))
+pv = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev)
+verts = pv.repeat((B + nb - 1) // nb, 1, 1)[:B].contiguous()
+g = torch.zeros_like(verts)
+
+def run(use_hd):
+    return topo.regressor_contact_loss(verts, euclthres=0.02, use_hd=use_hd, g_verts=g)
+
+for use_hd in (False, True):
+    run(use_hd); torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(5): loss = run(use_hd)
+    e.record(); torch.cuda.synchronize()
+    print('B=%d use_hd=%s: %.3f ms per call, mean loss %.4f' % (B, use_hd, s.elapsed_time(e) / 5, float(loss.mean())))

@@ -68,6 +68,9 @@ def _declare(lib):
     lib.tuch_topology_set_hd.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.tuch_topology_num_hd.argtypes = [vp]
     lib.tuch_regressor_contact_loss.argtypes = [vp, vp, i32, vp, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tuch_estimate_translation.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp]
+    lib.tuch_rotmat_to_angle_axis.argtypes = [vp, i32, i32, vp, vp]
+    lib.tuch_fits_pose_transform.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.tuch_winding_numbers_host.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.tuch_contact_query_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
 

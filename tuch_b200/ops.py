@@ -595,3 +595,44 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr, beta1=0.9, beta2=0
         check(lib().tuch_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
                                    _ptr(step_dev), float(lr), float(beta1), float(beta2), float(eps), _stream()),
               'tuch_adam_step')
+
+
+# ------------------------------------------------------------------ f2 / f3: camera + pose bookkeeping
+def estimate_translation(S, joints_2d, has_2d_kp_anno, focal_length=5000.0, img_size=224.0, n_openpose=25):
+    """tuch/utils/geometry.py:156-205 on the device: S[B,J,3], joints_2d[B,J,3], has_2d_kp_anno[B] -> [B,3]."""
+    S, k = _f32(S, 'S'), _f32(joints_2d, 'joints_2d')
+    B, J = S.shape[0], S.shape[1]
+    if k.shape != (B, J, 3) or S.shape[2] != 3:
+        raise TuchError('estimate_translation: S and joints_2d must be [B,J,3]')
+    has = has_2d_kp_anno.to(device=S.device, dtype=torch.uint8).contiguous()
+    out = torch.empty(B, 3, device=S.device, dtype=torch.float32)
+    with torch.cuda.device(S.device):
+        check(lib().tuch_estimate_translation(_ptr(S), _ptr(k), _ptr(has), B, J, int(n_openpose), float(focal_length),
+                                              float(img_size), _ptr(out), _stream()), 'tuch_estimate_translation')
+    return out
+
+
+def rotmat_to_angle_axis(rotmat):
+    """torchgeometry.rotation_matrix_to_angle_axis: [N,3,3] or [N,3,4] -> [N,3]."""
+    r = _f32(rotmat, 'rotmat')
+    if r.dim() != 3 or r.shape[1] != 3 or r.shape[2] not in (3, 4):
+        raise TuchError('rotmat_to_angle_axis: input must be [N,3,3] or [N,3,4], got %s' % (tuple(r.shape),))
+    out = torch.empty(r.shape[0], 3, device=r.device, dtype=torch.float32)
+    with torch.cuda.device(r.device):
+        check(lib().tuch_rotmat_to_angle_axis(_ptr(r), r.shape[0], r.shape[2], _ptr(out), _stream()),
+              'tuch_rotmat_to_angle_axis')
+    return out
+
+
+def fits_pose_transform(pose, rot_deg=None, is_flipped=None, flip_perm=None, flip_first=False):
+    """FitsDict.rotate_pose / flip_pose (fits_dict.py:89-119) fused: pose[B,D] -> [B,D]."""
+    p = _f32(pose, 'pose')
+    B, D = p.shape
+    rot = None if rot_deg is None else rot_deg.to(device=p.device, dtype=torch.float32).contiguous()
+    fl = None if is_flipped is None else is_flipped.to(device=p.device, dtype=torch.uint8).contiguous()
+    perm = None if flip_perm is None else flip_perm.to(device=p.device, dtype=torch.int32).contiguous()
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        check(lib().tuch_fits_pose_transform(_ptr(p), _ptr(rot), _ptr(fl), _ptr(perm), B, D, int(bool(flip_first)),
+                                             _ptr(out), _stream()), 'tuch_fits_pose_transform')
+    return out

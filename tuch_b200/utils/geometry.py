@@ -1,5 +1,6 @@
 """Host-side mirror of tuch/utils/geometry.py: batch_rodrigues (:29-43), quat_to_rotmat (:45-65),
-rot6d_to_rotmat (:67-81), perspective_projection (:83-111).
+rot6d_to_rotmat (:67-81), perspective_projection (:83-111), estimate_translation (:156-205), plus
+torchgeometry's rotation_matrix_to_angle_axis as called at tuch/train/train_module.py:208-211.
 
 These are the small glue functions around the hot path (a few dozen floats per body); they are
 expressed with torch tensor ops on the caller's device and are differentiable.  Inside the
@@ -49,3 +50,20 @@ def perspective_projection(points, rotation, translation, focal_length, camera_c
     if isinstance(f, torch.Tensor) and f.dim() > 0:
         f = f.view(-1, 1, 1)
     return f * p[:, :, :2] + camera_center.unsqueeze(1)
+
+
+def estimate_translation(S, joints_2d, focal_length=5000., img_size=224., has_2d_kp_anno=None):
+    """Camera translation that brings the 3-D joints S[B,49,3] closest to joints_2d[B,49,3] (x, y, conf):
+    GT joints 25:49 where has_2d_kp_anno, OpenPose joints 0:25 elsewhere -> [B,3] on S's device.
+    The reference loops over the batch with a device->host copy and a numpy solve per body
+    (geometry.py:191-203); here the whole batch is one kernel (tuch_estimate_translation)."""
+    from .. import ops
+    if has_2d_kp_anno is None:
+        raise ops.TuchError('estimate_translation: has_2d_kp_anno is required (geometry.py:192 indexes it)')
+    return ops.estimate_translation(S, joints_2d, has_2d_kp_anno, focal_length, img_size)
+
+
+def rotation_matrix_to_angle_axis(rotation_matrix):
+    """torchgeometry.rotation_matrix_to_angle_axis: [N,3,4] (or [N,3,3]) -> [N,3] (tuch_rotmat_to_angle_axis)."""
+    from .. import ops
+    return ops.rotmat_to_angle_axis(rotation_matrix)
