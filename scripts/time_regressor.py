@@ -28,6 +28,7 @@ pv = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev)
 verts = pv.repeat((B + nb - 1) // nb, 1, 1)[:B].contiguous()
 g = torch.zeros_like(verts)
 
+ops.kernel_timing(enable=True, reset=True)
 def run(use_hd):
     return topo.regressor_contact_loss(verts, euclthres=0.02, use_hd=use_hd, g_verts=g)
 
@@ -38,3 +39,15 @@ for use_hd in (False, True):
     for _ in range(5): loss = run(use_hd)
     e.record(); torch.cuda.synchronize()
     print('B=%d use_hd=%s: %.3f ms per call, mean loss %.4f' % (B, use_hd, s.elapsed_time(e) / 5, float(loss.mean())))
+
+# hierarchical vs all-faces inside test of the HD points: flags and loss
+topo.set_winding_mode(topo.WINDING_EXACT)
+le, de = topo.regressor_contact_loss(verts[:16].contiguous(), euclthres=0.02, use_hd=True, debug=True)
+topo.set_winding_mode(topo.WINDING_FAST)
+lf, df = topo.regressor_contact_loss(verts[:16].contiguous(), euclthres=0.02, use_hd=True, debug=True)
+n = df['counts']
+mism = sum(int((de['hd_exterior'][b, :int(n[b])] != df['hd_exterior'][b, :int(n[b])]).sum()) for b in range(16))
+print('selected HD points per body', n.tolist()[:8], 'interior frac %.3f' % float(sum(int((df['hd_exterior'][b, :int(n[b])] == 0).sum()) for b in range(16)) / float(n.sum())))
+print('HD exterior flag mismatches fast vs exact: %d of %d; loss rel diff %.2e' % (mism, int(n.sum()), float(((le - lf).abs() / le.abs().clamp_min(1e-9)).max())))
+for k in ('winding_kernel_points', 'winding_refine_kernel'):
+    print(' ', k, ops.kernel_time(k))

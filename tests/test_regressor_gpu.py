@@ -128,3 +128,35 @@ def test_contact_loss_full_size(full_assets):
     g, gr = pv.grad.cpu().double().flatten(), p32.grad.double().flatten()
     assert float((g * gr).sum() / (g.norm() * gr.norm())) > 0.9995
     assert rel(pv.grad, p32.grad.numpy()) < 5e-2
+
+
+def test_hd_inside_test_hierarchical_vs_all_faces(full_assets):
+    """The offset HD points sit 1 mm off the surface, so their winding numbers are near-integers and
+    interior points are only 0.01 above the 0.99 threshold: the hierarchical far field (tighter opening
+    radii, narrower re-evaluation band than for on-surface queries) must give the flags, the loss and the
+    gradient of the all-faces sum."""
+    from tuch_b200 import synthetic as syn
+    from test_contact_gpu import posed_verts
+    a = dict(full_assets)
+    a['hd_reg'], a['hd_fidx'] = syn.make_hd_regressor(a['model'], n_hd=20000)
+    crit = make_criterion(a, True, B=6)
+    topo = crit._topo
+    verts = torch.tensor(posed_verts(a, 6, seed=31), device=DEV)
+    valid = torch.tensor([True, True, False, True, True, True], device=DEV)
+    out = {}
+    for mode in (topo.WINDING_EXACT, topo.WINDING_FAST):
+        topo.set_winding_mode(mode)
+        g = torch.zeros_like(verts)
+        loss, dbg = topo.regressor_contact_loss(verts, valid=valid, euclthres=0.02, use_hd=True, g_verts=g, debug=True)
+        out[mode] = (loss, dbg, g)
+    (le, de, ge), (lf, df, gf) = out[topo.WINDING_EXACT], out[topo.WINDING_FAST]
+    assert topo.cluster_stats()['leaves'] > 0
+    assert torch.equal(de['counts'], df['counts']) and int(df['counts'][2]) == 0 and float(lf[2]) == 0
+    n_int = 0
+    for b in range(6):
+        n = int(df['counts'][b])
+        assert torch.equal(de['hd_exterior'][b, :n], df['hd_exterior'][b, :n])
+        assert torch.equal(de['hd_argmin'][b, :n], df['hd_argmin'][b, :n])
+        n_int += int((df['hd_exterior'][b, :n] == 0).sum())
+    assert n_int > 100
+    assert torch.equal(le, lf) and (ge - gf).abs().max() <= 1e-6 * ge.abs().max()

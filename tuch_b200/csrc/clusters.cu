@@ -259,8 +259,9 @@ __global__ void __launch_bounds__(128)
 cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restrict__ faces,
                     const int* __restrict__ leaf_face, const int* __restrict__ mid_off,
                     const int* __restrict__ top_off, int K, int NM, int NT, float beta_leaf, float beta_group,
-                    float4* __restrict__ ctri, float4* __restrict__ nodes) {
+                    float4* __restrict__ ctri, float4* __restrict__ nodes, const uint8_t* __restrict__ body_active) {
     const int b = blockIdx.y;
+    if (body_active != nullptr && !body_active[b]) return;
     const int node = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (node >= NT + NM + K) return;
@@ -396,18 +397,29 @@ __device__ __forceinline__ float node_far_field(const float4* __restrict__ rec, 
 // Tops and mids open for the whole warp as soon as one query is near; leaves are near or far per query.
 // In the near pass the two half-warps serve two near queries at a time, one lane per face of the leaf.
 __global__ void __launch_bounds__(WC_WARPS * 32)
-winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ vtile,
+winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__ vtile,
                        const float4* __restrict__ ctri, const float4* __restrict__ nodes,
                        const int* __restrict__ mid_off, const int* __restrict__ top_off,
-                       float* __restrict__ partial, int V, int T, int K, int NM, int NT, int tops_per_split, int S) {
+                       float* __restrict__ partial, int Q, int T, int K, int NM, int NT, int tops_per_split, int S,
+                       const int* __restrict__ q_counts, const uint8_t* __restrict__ body_active) {
     __shared__ float s_acc[WC_WARPS][32 * (WC_LEAF + 1)];
     const int b = blockIdx.z, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * WC_WARPS + warp;               // one vertex tile per warp
+    if (body_active != nullptr && !body_active[b]) return;
+    const int tile = blockIdx.x * WC_WARPS + warp;               // one query tile per warp
     if (tile >= T) return;
-    const int qv = vtile[tile * 32 + lane];                      // -1 = padding lane (a tile holds >= 1 vertex)
-    const int qi = qv >= 0 ? qv : vtile[tile * 32];
-    const float* vb = verts + (size_t)b * V * 3;
+    int qv, qi;
+    if (vtile != nullptr) {                                      // mesh vertices in tile order
+        qv = vtile[tile * 32 + lane];                            // -1 = padding lane (a tile holds >= 1 vertex)
+        qi = qv >= 0 ? qv : vtile[tile * 32];
+    } else {                                                     // 32 consecutive points
+        const int n = q_counts != nullptr ? min(Q, q_counts[b]) : Q;
+        if (tile * 32 >= n) return;
+        qi = tile * 32 + lane;
+        qv = qi < n ? qi : -1;
+        qi = min(qi, n - 1);
+    }
+    const float* vb = points + (size_t)b * Q * 3;
     const float px = vb[3 * qi], py = vb[3 * qi + 1], pz = vb[3 * qi + 2];
     float* acc = s_acc[warp];
     for (int k = lane; k < 32 * (WC_LEAF + 1); k += 32) acc[k] = 0.f;
@@ -471,22 +483,27 @@ winding_cluster_kernel(const float* __restrict__ verts, const int* __restrict__ 
     float near_sum = 0.f;
 #pragma unroll
     for (int j = 0; j < WC_LEAF; ++j) near_sum += acc[lane * (WC_LEAF + 1) + j];
-    if (qv >= 0) partial[((size_t)b * S + split) * V + qi] = far + near_sum;
+    if (qv >= 0) partial[((size_t)b * S + split) * Q + qi] = far + near_sum;
 }
 
 // sums the split partials in a fixed order, scales by 1 / (2 pi) and lists the queries whose value is
 // within WC_MARGIN of the 0.99 threshold of losses.py:82 for exact re-evaluation
 __global__ void cluster_finalize_kernel(const float* __restrict__ partial, int V, int S, float* __restrict__ winding,
-                                        int* __restrict__ refine_list) {
+                                        int* __restrict__ refine_list, const int* __restrict__ q_counts,
+                                        const uint8_t* __restrict__ body_active, float margin) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= V) return;
+    if ((body_active != nullptr && !body_active[b]) || (q_counts != nullptr && q >= q_counts[b])) {
+        winding[(size_t)b * V + q] = 0.f;
+        return;
+    }
     const float* p = partial + (size_t)b * S * V + q;
     float acc = 0.f;
     for (int s = 0; s < S; ++s) acc += p[(size_t)s * V];
     const float w = acc * 0.159154943091895336f;
     winding[(size_t)b * V + q] = w;
-    if (fabsf(w - 0.99f) < WC_MARGIN) {
+    if (fabsf(w - 0.99f) < margin) {
         const int k = atomicAdd(refine_list, 1);
         refine_list[1 + k] = b * V + q;
     }
@@ -538,37 +555,53 @@ int cluster_splits(int B, int T, int NT, int sm_count) {
     return cdiv(NT, per);
 }
 
-int launch_winding_clusters(const ClusterJob& j, cudaStream_t st) {
-    if (j.B == 0 || j.V == 0) return 0;
-    {
-        dim3 grid(cdiv(j.NT + j.NM + j.K, 4), j.B);
-        // development knobs (scripts/sweep_beta.sh sweeps them); the shipped values are the constants
-        static const float beta_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : WC_BETA;
-        static const float beta_group = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : WC_BETA_GROUP;
-        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.mid_off, j.top_off, j.K, j.NM,
-                                                  j.NT, beta_leaf, beta_group, j.ctri, j.nodes);
-        TUCH_LAUNCH_CHECK(); count_launch();
-    }
+int launch_cluster_pack(const ClusterJob& j, cudaStream_t st) {
+    if (j.B == 0) return 0;
+    dim3 grid(cdiv(j.NT + j.NM + j.K, 4), j.B);
+    // development knobs (scripts/sweep_beta.sh sweeps them); the shipped values are the constants
+    static const float env_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : 0.f;
+    static const float env_group = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : 0.f;
+    const float beta_leaf = env_leaf > 0.f ? env_leaf : j.beta_leaf, beta_group = env_group > 0.f ? env_group : j.beta_group;
+    cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.mid_off, j.top_off, j.K, j.NM, j.NT,
+                                              beta_leaf, beta_group, j.ctri, j.nodes, j.body_active);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+// queries against the packed hierarchy of launch_cluster_pack
+int launch_cluster_query(const ClusterJob& j, cudaStream_t st) {
+    const float* points = j.points != nullptr ? j.points : j.verts;
+    const int Q = j.points != nullptr ? j.Q : j.V;
+    const int T = j.vtile != nullptr ? j.T : cdiv(Q, 32);
+    if (j.B == 0 || Q == 0) return 0;
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
     {
         const int per = cdiv(j.NT, j.S);
-        dim3 grid(cdiv(j.T, WC_WARPS), j.S, j.B);
-        KernelTimer timer("winding_kernel", st);
-        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(j.verts, j.vtile, j.ctri, j.nodes, j.mid_off, j.top_off,
-                                                               j.partial, j.V, j.T, j.K, j.NM, j.NT, per, j.S);
+        dim3 grid(cdiv(T, WC_WARPS), j.S, j.B);
+        KernelTimer timer(j.vtile != nullptr ? "winding_kernel" : "winding_kernel_points", st);
+        winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(points, j.vtile, j.ctri, j.nodes, j.mid_off, j.top_off,
+                                                               j.partial, Q, T, j.K, j.NM, j.NT, per, j.S, j.q_counts,
+                                                               j.body_active);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     {
-        dim3 grid(cdiv(j.V, 256), j.B);
-        cluster_finalize_kernel<<<grid, 256, 0, st>>>(j.partial, j.V, j.S, j.winding, j.refine_list);
+        dim3 grid(cdiv(Q, 256), j.B);
+        cluster_finalize_kernel<<<grid, 256, 0, st>>>(j.partial, Q, j.S, j.winding, j.refine_list, j.q_counts, j.body_active,
+                                                      j.margin);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     {
         KernelTimer timer("winding_refine_kernel", st);
-        cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(j.verts, j.ctri, j.V, j.K, j.refine_list, j.winding);
+        cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(points, j.ctri, Q, j.K, j.refine_list, j.winding);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
+}
+
+int launch_winding_clusters(const ClusterJob& j, cudaStream_t st) {
+    if (j.B == 0 || j.V == 0) return 0;
+    if (int rc = launch_cluster_pack(j, st)) return rc;
+    return launch_cluster_query(j, st);
 }
 
 }  // namespace tuch

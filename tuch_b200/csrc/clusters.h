@@ -13,6 +13,7 @@ constexpr int WC_NODE_F4 = 7;        // float4 per node record (centre + radius,
 constexpr int WC_WARPS = 8;          // warps per CTA of the winding kernel; one query per lane
 constexpr float WC_BETA = 2.0f;      // a leaf is "far" for a query beyond WC_BETA x its radius ...
 constexpr float WC_BETA_GROUP = 2.5f;   // ... a mid / top group (larger, so larger absolute error) beyond 2.5 x
+constexpr float WC_BETA_POINTS = 3.0f, WC_BETA_GROUP_POINTS = 3.5f, WC_MARGIN_POINTS = 0.005f;
 constexpr float WC_MARGIN = 0.04f;   // |w - 0.99| below this is re-evaluated exactly (8 x the worst far-field
                                      // error measured at these opening parameters: 4.9e-3)
 
@@ -30,19 +31,29 @@ struct ClusterTree {
 int build_cluster_tree(const int* faces, int F, int V, const float* verts, ClusterTree& out);
 
 struct ClusterJob {
-    const float* verts;              // [B][V][3] mesh vertices (also the queries, in qperm order)
+    const float* verts;              // [B][V][3] mesh vertices
     const int* faces;                // [F][3]
     const int* leaf_face;            // [K][WC_LEAF]
     const int* mid_off;              // [NM + 1]
     const int* top_off;              // [NT + 1]
-    const int* vtile;                // [T][32]
+    const int* vtile;                // [T][32] query order when the queries are the mesh vertices, else NULL
     float4* ctri;                    // [B][K][WC_LEAF][3] scratch: corners a | b | c per face slot, the face's
                                      // normal (b - a) x (c - a) in the three w components
     float4* nodes;                   // [B][NT + NM + K][WC_NODE_F4] scratch: tops, then mids, then leaves
-    float* partial;                  // [B][S][V] scratch
-    float* winding;                  // [B][V] out
-    int* refine_list;                // [1 + B * V] scratch: count, then b * V + q entries
+    float* partial;                  // [B][S][Q] scratch
+    float* winding;                  // [B][Q] out
+    int* refine_list;                // [1 + B * Q] scratch: count, then b * Q + q entries
     int B, V, K, NM, NT, S, T;
+    // queries: the mesh vertices themselves (points == verts, Q == V, vtile != NULL), or arbitrary points
+    // [B][Q][3] taken 32 consecutive ones per warp, of which only the first q_counts[b] are valid
+    const float* points = nullptr;
+    int Q = 0;
+    const int* q_counts = nullptr;
+    const uint8_t* body_active = nullptr;   // optional [B]: 0 = skip body (winding 0)
+    // opening radii and re-evaluation band; the defaults suit queries ON the surface (values near 0.5 /
+    // 1.5).  Off-surface queries see near-integer winding numbers, i.e. interior points sit at 1.0, only
+    // 0.01 above the threshold: they need a tighter far field and a narrower band (WC_*_POINTS).
+    float beta_leaf = WC_BETA, beta_group = WC_BETA_GROUP, margin = WC_MARGIN;
 };
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);
@@ -50,6 +61,8 @@ int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* v
                          float4* vert4p, float4* tinfo, int* argmin, float* minval, cudaStream_t st);
 
 int cluster_splits(int B, int T, int NT, int sm_count);
-int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);
+int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
+int launch_cluster_query(const ClusterJob& job, cudaStream_t st);     // winding kernel + finalize + exact refine
+int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);  // both
 
 }  // namespace tuch

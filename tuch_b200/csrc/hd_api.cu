@@ -1,5 +1,6 @@
 // C ABI of the regressor contact loss (include/tuch_b200.h, section a12): tuch/train/loss.py:240-317.
 #include "hd_internal.h"
+#include "clusters.h"
 #include "objective_internal.h"
 #include "strips.h"
 
@@ -63,10 +64,16 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     const size_t h_ham = sc.plan(sizeof(int) * BN), h_hw = sc.plan(sizeof(float) * BN), h_hex = sc.plan(BN);
     const size_t h_ghd = sc.plan(sizeof(float) * 3 * BN);
     const int Lp = t->Lp;
-    const int S = use_hd ? strip_splits(B, N, Lp, sm_count()) : 1;
-    const size_t h_tri = sc.plan(use_hd ? sizeof(float4) * 2 * (size_t)B * Lp : 0);
-    const size_t h_info = sc.plan(use_hd ? sizeof(float4) * (size_t)B * (Lp / WS_TILE) : 0);
+    // inside test of the HD points: hierarchical far field when the topology has its face hierarchy
+    // (the default), else the all-faces strip kernel
+    const bool fast = use_hd && t->winding_mode == TUCH_WINDING_FAST && t->has_clusters;
+    const int S = !use_hd ? 1 : fast ? cluster_splits(B, cdiv(N, 32), t->NT, sm_count()) : strip_splits(B, N, Lp, sm_count());
+    const size_t h_tri = sc.plan(!use_hd ? 0 : fast ? sizeof(float4) * 3 * (size_t)B * t->K * WC_LEAF
+                                                    : sizeof(float4) * 2 * (size_t)B * Lp);
+    const size_t h_info = sc.plan(!use_hd ? 0 : fast ? sizeof(float4) * WC_NODE_F4 * (size_t)B * (t->NT + t->NM + t->K)
+                                                     : sizeof(float4) * (size_t)B * (Lp / WS_TILE));
     const size_t h_par = sc.plan(use_hd ? sizeof(float) * (size_t)B * S * N : 0);
+    const size_t h_ref = sc.plan(fast ? sizeof(int) * (BN + 1) : 0);
     if (int rc = sc.commit_slot(st, 1)) return rc;
     int* am = sc.get<int>(h_am);
     float* mn = sc.get<float>(h_mn);
@@ -95,10 +102,18 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     // loss.py:297 -- inside test of the offset HD points against the full mesh
     float4* strip4 = sc.get<float4>(h_tri);
     float4* info = sc.get<float4>(h_info);
-    if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
-    StripJob j{strip4, info, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Lp, S};
-    j.q_counts = cnt;
-    if (int rc = launch_winding_strips(j, st)) return rc;
+    if (fast) {
+        ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, nullptr, strip4, info,
+                     sc.get<float>(h_par), hw, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
+        j.points = off; j.Q = N; j.q_counts = cnt; j.body_active = valid;
+        j.beta_leaf = WC_BETA_POINTS; j.beta_group = WC_BETA_GROUP_POINTS; j.margin = WC_MARGIN_POINTS;
+        if (int rc = launch_winding_clusters(j, st)) return rc;
+    } else {
+        if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
+        StripJob j{strip4, info, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Lp, S};
+        j.q_counts = cnt;
+        if (int rc = launch_winding_strips(j, st)) return rc;
+    }
     if (int rc = launch_exterior_init(hw, B, N, hex, nullptr, st)) return rc;
     // loss.py:299-315
     float* g_hd = nullptr;
