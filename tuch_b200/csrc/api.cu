@@ -286,7 +286,8 @@ static void free_segments(tuch_topology* t) {
 TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
-    free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_maskP);
+    free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_vgroup_off);
+    free_dev(t->d_maskP);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -332,14 +333,15 @@ static int install_clusters(tuch_topology* t, const float* verts_host, cudaStrea
     ClusterTree tree;
     if (int rc = build_cluster_tree(faces.data(), t->F, t->V, verts_host, tree)) return rc;
     TUCH_CUDA(cudaDeviceSynchronize());            // queued work may still read the old hierarchy
-    free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile);
-    t->d_leaf_face = t->d_mid_off = t->d_top_off = t->d_vtile = nullptr;
+    free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_vgroup_off);
+    t->d_leaf_face = t->d_mid_off = t->d_top_off = t->d_vtile = t->d_vgroup_off = nullptr;
     t->has_clusters = false;
     if (int rc = upload(tree.leaf_face.data(), tree.leaf_face.size(), &t->d_leaf_face)) return rc;
     if (int rc = upload(tree.mid_off.data(), tree.mid_off.size(), &t->d_mid_off)) return rc;
     if (int rc = upload(tree.top_off.data(), tree.top_off.size(), &t->d_top_off)) return rc;
     if (int rc = upload(tree.vtile.data(), tree.vtile.size(), &t->d_vtile)) return rc;
-    t->K = tree.K; t->NM = tree.NM; t->NT = tree.NT; t->T = tree.T;
+    if (int rc = upload(tree.vgroup_off.data(), tree.vgroup_off.size(), &t->d_vgroup_off)) return rc;
+    t->K = tree.K; t->NM = tree.NM; t->NT = tree.NT; t->T = tree.T; t->NG = tree.NG; t->max_top_leaves = tree.max_top_leaves;
     t->has_clusters = true;
     return refresh_permuted_mask(t, st);
 }
@@ -590,7 +592,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     const int T = t->T;
     const size_t h_v4 = sc.plan(!want_nn ? 0 : nn_tiles ? sizeof(float4) * (size_t)B * T * 32
                                                         : (vert4_out ? 0 : sizeof(float4) * (size_t)B * Vp));
-    const size_t h_tinfo = sc.plan(nn_tiles ? sizeof(float4) * 2 * (size_t)B * T : 0);
+    const size_t h_tinfo = sc.plan(nn_tiles ? sizeof(float4) * 2 * (size_t)B * (T + t->NG) : 0);
     const size_t h_par = sc.plan(want_w ? sizeof(float) * (size_t)B * S * V : 0);
     const size_t h_w = sc.plan((want_w && !winding) ? sizeof(float) * (size_t)B * V : 0);
     const size_t h_any = sc.plan(segs ? (size_t)B : 0);
@@ -610,6 +612,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         if (fast) {
             ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, t->d_vtile, strip4, info,
                          sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
+            j.max_top_leaves = t->max_top_leaves;
             if (int rc = launch_winding_clusters(j, st)) return rc;
         } else {
             if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
@@ -633,7 +636,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         int* am = argmin ? argmin : sc.get<int>(h_am);
         float* mn = min_sq ? min_sq : sc.get<float>(h_mn);
         if (nn_tiles) {
-            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_vtile, B, V, T, vert4, sc.get<float4>(h_tinfo), am, mn, st)) return rc;
+            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4, sc.get<float4>(h_tinfo), am, mn, st)) return rc;
         } else {
             if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;
         }

@@ -14,8 +14,8 @@ struct tuch_topology {
     int *d_strip_vid = nullptr, *d_strip_fid = nullptr;
     // face-cluster hierarchy for the far-field winding kernel (clusters.cu); built from the template
     // (tuch_topology_set_template) or lazily from the first body a contact query sees
-    int K = 0, NM = 0, NT = 0, T = 0;
-    int *d_leaf_face = nullptr, *d_mid_off = nullptr, *d_top_off = nullptr, *d_vtile = nullptr;
+    int K = 0, NM = 0, NT = 0, T = 0, NG = 0, max_top_leaves = 0;
+    int *d_leaf_face = nullptr, *d_mid_off = nullptr, *d_top_off = nullptr, *d_vtile = nullptr, *d_vgroup_off = nullptr;
     bool has_clusters = false;
     uint32_t* d_maskP = nullptr;       // geodesic mask in cluster order (nearest_tiles.cu); valid when both
     bool has_maskP = false;            // the mask and the hierarchy exist

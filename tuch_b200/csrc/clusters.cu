@@ -204,11 +204,13 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
         tb.set_adjacency(nb);
         tb.run();
         out.K = tb.n_leaves; out.NM = tb.n_mids; out.NT = tb.n_tops;
+        for (int t = 0; t < out.NT; ++t)
+            out.max_top_leaves = std::max(out.max_top_leaves, out.mid_off[out.top_off[t + 1]] - out.mid_off[out.top_off[t]]);
     }
     {   // vertices: neighbours share an edge; vertices without faces end up in tiles of their own
         TreeBuilder tb;
-        tb.N = V; tb.leaf = 32;
-        tb.leaf_items = &out.vtile;
+        tb.N = V; tb.leaf = 32; tb.mid_leaves = 8;
+        tb.leaf_items = &out.vtile; tb.mid_off = &out.vgroup_off;
         tb.cen.assign(verts, verts + (size_t)V * 3);
         std::vector<std::vector<int>> nb(V);
         for (auto& kv : ef) {
@@ -217,7 +219,7 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
         }
         tb.set_adjacency(nb);
         tb.run();
-        out.T = tb.n_leaves;
+        out.T = tb.n_leaves; out.NG = tb.n_mids;
     }
     // self-checks: partitions of the faces and of the vertices
     std::vector<char> seen(F, 0);
@@ -369,6 +371,141 @@ cluster_pack_kernel(const float* __restrict__ verts, int V, const int* __restric
         o[4] = make_float4(-0.75f * uvz, 3.75f * txxx, 3.75f * tyyy, 3.75f * tzzz);
         o[5] = make_float4(3.75f * txxy, 3.75f * txxz, 3.75f * tyyx, 3.75f * tyyz);
         o[6] = make_float4(3.75f * tzzx, 3.75f * tzzy, 3.75f * txyz, 0.f);
+    }
+}
+
+// Same records, one CTA per TOP group: the corners of the group's face slots are gathered from the posed
+// vertices once into shared memory (9 floats per slot, stride 9 = conflict-free) and every node of the
+// group -- the top itself, its mids, its leaves -- is then reduced from there by one warp, instead of
+// gathering every face six times (three levels x two passes).
+struct NodeMoments {
+    float r2 = 0.f, m0x = 0.f, m0y = 0.f, m0z = 0.f, tr = 0.f;
+    float qxx = 0.f, qyy = 0.f, qzz = 0.f, qxy = 0.f, qxz = 0.f, qyz = 0.f, uvx = 0.f, uvy = 0.f, uvz = 0.f;
+    float txxx = 0.f, tyyy = 0.f, tzzz = 0.f, txxy = 0.f, txxz = 0.f, tyyx = 0.f, tyyz = 0.f, tzzx = 0.f, tzzy = 0.f, txyz = 0.f;
+    __device__ __forceinline__ void add(float ax, float ay, float az, float bx, float by, float bz, float gx, float gy, float gz) {
+        r2 = fmaxf(r2, fmaxf(ax * ax + ay * ay + az * az, fmaxf(bx * bx + by * by + bz * bz, gx * gx + gy * gy + gz * gz)));
+        const float e1x = bx - ax, e1y = by - ay, e1z = bz - az, e2x = gx - ax, e2y = gy - ay, e2z = gz - az;
+        const float nx = 0.5f * (e1y * e2z - e1z * e2y), ny = 0.5f * (e1z * e2x - e1x * e2z), nz = 0.5f * (e1x * e2y - e1y * e2x);
+        const float hx = (ax + bx + gx) * (1.f / 3.f), hy = (ay + by + gy) * (1.f / 3.f), hz = (az + bz + gz) * (1.f / 3.f);
+        m0x += nx; m0y += ny; m0z += nz;
+        tr += nx * hx + ny * hy + nz * hz;
+        qxx += nx * hx; qyy += ny * hy; qzz += nz * hz;
+        qxy += nx * hy + ny * hx; qxz += nx * hz + nz * hx; qyz += ny * hz + nz * hy;
+        const float m1x = 0.5f * (ax + bx), m1y = 0.5f * (ay + by), m1z = 0.5f * (az + bz);
+        const float m2x = 0.5f * (bx + gx), m2y = 0.5f * (by + gy), m2z = 0.5f * (bz + gz);
+        const float m3x = 0.5f * (gx + ax), m3y = 0.5f * (gy + ay), m3z = 0.5f * (gz + az);
+        const float k3 = 1.f / 3.f;
+        const float sxx = k3 * (m1x * m1x + m2x * m2x + m3x * m3x), syy = k3 * (m1y * m1y + m2y * m2y + m3y * m3y),
+                    szz = k3 * (m1z * m1z + m2z * m2z + m3z * m3z);
+        const float sxy = k3 * (m1x * m1y + m2x * m2y + m3x * m3y), sxz = k3 * (m1x * m1z + m2x * m2z + m3x * m3z),
+                    syz = k3 * (m1y * m1z + m2y * m2z + m3y * m3z);
+        const float trs = sxx + syy + szz;
+        uvx += 2.f * (nx * sxx + ny * sxy + nz * sxz) + nx * trs;
+        uvy += 2.f * (nx * sxy + ny * syy + nz * syz) + ny * trs;
+        uvz += 2.f * (nx * sxz + ny * syz + nz * szz) + nz * trs;
+        txxx += nx * sxx; tyyy += ny * syy; tzzz += nz * szz;
+        txxy += 2.f * nx * sxy + ny * sxx; txxz += 2.f * nx * sxz + nz * sxx;
+        tyyx += 2.f * ny * sxy + nx * syy; tyyz += 2.f * ny * syz + nz * syy;
+        tzzx += 2.f * nz * sxz + nx * szz; tzzy += 2.f * nz * syz + ny * szz;
+        txyz += 2.f * (nx * syz + ny * sxz + nz * sxy);
+    }
+    __device__ __forceinline__ void reduce() {
+        r2 = warp_max(r2);
+        m0x = warp_sum(m0x); m0y = warp_sum(m0y); m0z = warp_sum(m0z); tr = warp_sum(tr);
+        qxx = warp_sum(qxx); qyy = warp_sum(qyy); qzz = warp_sum(qzz);
+        qxy = warp_sum(qxy); qxz = warp_sum(qxz); qyz = warp_sum(qyz);
+        uvx = warp_sum(uvx); uvy = warp_sum(uvy); uvz = warp_sum(uvz);
+        txxx = warp_sum(txxx); tyyy = warp_sum(tyyy); tzzz = warp_sum(tzzz);
+        txxy = warp_sum(txxy); txxz = warp_sum(txxz); tyyx = warp_sum(tyyx); tyyz = warp_sum(tyyz);
+        tzzx = warp_sum(tzzx); tzzy = warp_sum(tzzy); txyz = warp_sum(txyz);
+    }
+    __device__ __forceinline__ void write(float4* o, float px, float py, float pz, float beta) const {
+        o[0] = make_float4(px, py, pz, r2 * (beta * beta * 1.0002f));
+        o[1] = make_float4(0.5f * m0x, 0.5f * m0y, 0.5f * m0z, 0.5f * tr);
+        o[2] = make_float4(-1.5f * qxx, -1.5f * qyy, -1.5f * qzz, -1.5f * qxy);
+        o[3] = make_float4(-1.5f * qxz, -1.5f * qyz, -0.75f * uvx, -0.75f * uvy);
+        o[4] = make_float4(-0.75f * uvz, 3.75f * txxx, 3.75f * tyyy, 3.75f * tzzz);
+        o[5] = make_float4(3.75f * txxy, 3.75f * txxz, 3.75f * tyyx, 3.75f * tyyz);
+        o[6] = make_float4(3.75f * tzzx, 3.75f * tzzy, 3.75f * txyz, 0.f);
+    }
+};
+
+__global__ void __launch_bounds__(256)
+cluster_pack_top_kernel(const float* __restrict__ verts, int V, const int* __restrict__ faces,
+                        const int* __restrict__ leaf_face, const int* __restrict__ mid_off,
+                        const int* __restrict__ top_off, int K, int NM, int NT, float beta_leaf, float beta_group,
+                        float4* __restrict__ ctri, float4* __restrict__ nodes, const uint8_t* __restrict__ body_active) {
+    extern __shared__ float s_c[];                               // [n_slots][9] corners, then [n_slots] validity
+    const int b = blockIdx.y, t = blockIdx.x;
+    if (body_active != nullptr && !body_active[b]) return;
+    const int m0 = top_off[t], m1 = top_off[t + 1];
+    const int l0 = mid_off[m0], l1 = mid_off[m1];
+    const int n_slots = (l1 - l0) * WC_LEAF;
+    float* s_ok = s_c + (size_t)n_slots * 9;
+    const float* vb = verts + (size_t)b * V * 3;
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+        const int f = leaf_face[(size_t)l0 * WC_LEAF + i];
+        float c[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (f >= 0) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int v = faces[3 * f + e];
+                c[3 * e] = vb[3 * v]; c[3 * e + 1] = vb[3 * v + 1]; c[3 * e + 2] = vb[3 * v + 2];
+            }
+            const float e1x = c[3] - c[0], e1y = c[4] - c[1], e1z = c[5] - c[2];
+            const float e2x = c[6] - c[0], e2y = c[7] - c[1], e2z = c[8] - c[2];
+            nx = e1y * e2z - e1z * e2y; ny = e1z * e2x - e1x * e2z; nz = e1x * e2y - e1y * e2x;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_c[(size_t)i * 9 + k] = c[k];
+        s_ok[i] = f >= 0 ? 1.f : 0.f;
+        float4* o = ctri + (((size_t)b * K + l0) * WC_LEAF + i) * 3;
+        o[0] = make_float4(c[0], c[1], c[2], nx);                // face normal for half_solid_angle_n
+        o[1] = make_float4(c[3], c[4], c[5], ny);
+        o[2] = make_float4(c[6], c[7], c[8], nz);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nm = m1 - m0, nl = l1 - l0;
+    for (int n = warp; n < 1 + nm + nl; n += 8) {
+        int s0, s1, node;
+        float beta = beta_group;
+        if (n == 0) { s0 = 0; s1 = n_slots; node = t; }
+        else if (n <= nm) { s0 = (mid_off[m0 + n - 1] - l0) * WC_LEAF; s1 = (mid_off[m0 + n] - l0) * WC_LEAF; node = NT + m0 + n - 1; }
+        else { s0 = (n - 1 - nm) * WC_LEAF; s1 = s0 + WC_LEAF; node = NT + NM + l0 + (n - 1 - nm); beta = beta_leaf; }
+        // pass 1: area-weighted centre (plain centroid mean for zero-area nodes)
+        float wsum = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f, cnt = 0.f;
+        for (int i = s0 + lane; i < s1; i += 32) {
+            if (s_ok[i] == 0.f) continue;
+            const float* c = s_c + (size_t)i * 9;
+            const float e1x = c[3] - c[0], e1y = c[4] - c[1], e1z = c[5] - c[2];
+            const float e2x = c[6] - c[0], e2y = c[7] - c[1], e2z = c[8] - c[2];
+            const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+            const float area = 0.5f * sqrtf(nx * nx + ny * ny + nz * nz);
+            const float gx = (c[0] + c[3] + c[6]) * (1.f / 3.f), gy = (c[1] + c[4] + c[7]) * (1.f / 3.f),
+                        gz = (c[2] + c[5] + c[8]) * (1.f / 3.f);
+            wsum += area; cx += area * gx; cy += area * gy; cz += area * gz;
+            ux += gx; uy += gy; uz += gz; cnt += 1.f;
+        }
+        wsum = warp_sum(wsum); cnt = warp_sum(cnt);
+        float px, py, pz;
+        if (wsum > 1e-30f) {
+            const float inv = 1.f / wsum;
+            px = warp_sum(cx) * inv; py = warp_sum(cy) * inv; pz = warp_sum(cz) * inv;
+        } else {
+            const float inv = 1.f / fmaxf(cnt, 1.f);
+            px = warp_sum(ux) * inv; py = warp_sum(uy) * inv; pz = warp_sum(uz) * inv;
+        }
+        // pass 2: radius and moments about p
+        NodeMoments mo;
+        for (int i = s0 + lane; i < s1; i += 32) {
+            if (s_ok[i] == 0.f) continue;
+            const float* c = s_c + (size_t)i * 9;
+            mo.add(c[0] - px, c[1] - py, c[2] - pz, c[3] - px, c[4] - py, c[5] - pz, c[6] - px, c[7] - py, c[8] - pz);
+        }
+        mo.reduce();
+        if (lane == 0) mo.write(nodes + ((size_t)b * (NT + NM + K) + node) * WC_NODE_F4, px, py, pz, beta);
     }
 }
 
@@ -562,8 +699,20 @@ int launch_cluster_pack(const ClusterJob& j, cudaStream_t st) {
     static const float env_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : 0.f;
     static const float env_group = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : 0.f;
     const float beta_leaf = env_leaf > 0.f ? env_leaf : j.beta_leaf, beta_group = env_group > 0.f ? env_group : j.beta_group;
-    cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.mid_off, j.top_off, j.K, j.NM, j.NT,
-                                              beta_leaf, beta_group, j.ctri, j.nodes, j.body_active);
+    const size_t smem = (size_t)j.max_top_leaves * WC_LEAF * 10 * sizeof(float);
+    if (j.max_top_leaves > 0 && smem <= 200 * 1024) {
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            TUCH_CUDA(cudaFuncSetAttribute(cluster_pack_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        dim3 g2(j.NT, j.B);
+        cluster_pack_top_kernel<<<g2, 256, smem, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.mid_off, j.top_off, j.K, j.NM,
+                                                       j.NT, beta_leaf, beta_group, j.ctri, j.nodes, j.body_active);
+    } else {                                                     // a top group too large for shared memory
+        cluster_pack_kernel<<<grid, 128, 0, st>>>(j.verts, j.V, j.faces, j.leaf_face, j.mid_off, j.top_off, j.K, j.NM, j.NT,
+                                                  beta_leaf, beta_group, j.ctri, j.nodes, j.body_active);
+    }
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

@@ -26,7 +26,8 @@ struct ClusterTree {
     std::vector<int> vtile;          // [T][32] vertex tiles: vertex id or -1 (padding); the 32 vertices of
                                      // a tile are neighbours on the mesh (queries of one warp, candidate
                                      // rows of one mask word)
-    int K = 0, NM = 0, NT = 0, T = 0;
+    std::vector<int> vgroup_off;     // [NG + 1] tile ranges of the vertex-tile groups (<= 8 tiles each)
+    int K = 0, NM = 0, NT = 0, T = 0, NG = 0, max_top_leaves = 0;
 };
 int build_cluster_tree(const int* faces, int F, int V, const float* verts, ClusterTree& out);
 
@@ -54,11 +55,14 @@ struct ClusterJob {
     // 1.5).  Off-surface queries see near-integer winding numbers, i.e. interior points sit at 1.0, only
     // 0.01 above the threshold: they need a tighter far field and a narrower band (WC_*_POINTS).
     float beta_leaf = WC_BETA, beta_group = WC_BETA_GROUP, margin = WC_MARGIN;
+    int max_top_leaves = 0;          // largest top group in leaves (shared-memory staging of the pack kernel)
 };
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);
-int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, int B, int V, int T,
-                         float4* vert4p, float4* tinfo, int* argmin, float* minval, cudaStream_t st);
+// tinfo: [B][T + NG][2] float4 -- tile spheres, then group spheres
+int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, const int* vgroup_off, int B,
+                         int V, int T, int NG, float4* vert4p, float4* tinfo, int* argmin, float* minval,
+                         cudaStream_t st);
 
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles

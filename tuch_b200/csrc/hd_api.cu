@@ -105,7 +105,7 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     if (fast) {
         ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, nullptr, strip4, info,
                      sc.get<float>(h_par), hw, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
-        j.points = off; j.Q = N; j.q_counts = cnt; j.body_active = valid;
+        j.points = off; j.Q = N; j.q_counts = cnt; j.body_active = valid; j.max_top_leaves = t->max_top_leaves;
         j.beta_leaf = WC_BETA_POINTS; j.beta_group = WC_BETA_GROUP_POINTS; j.margin = WC_MARGIN_POINTS;
         if (int rc = launch_winding_clusters(j, st)) return rc;
     } else {

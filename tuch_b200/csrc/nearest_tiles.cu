@@ -42,9 +42,9 @@ __global__ void permute_mask_kernel(const uint32_t* __restrict__ maskT, int Vq, 
 
 // one warp per vertex tile:
 //   vert4p[b][s] = (v, |v|^2) of vertex vtile[s]  (|v|^2 accumulated exactly like pack_mesh_kernel)
-//   tinfo[b][t]  = (centre, radius), (max |v|^2, 0, 0, 0)
+//   tinfo[b][t]  = (centre, radius), (max |v|^2, 0, 0, 0); group spheres follow at [T, T + NG)
 __global__ void __launch_bounds__(128)
-pack_tiles_kernel(const float* __restrict__ verts, int V, const int* __restrict__ vtile, int T,
+pack_tiles_kernel(const float* __restrict__ verts, int V, const int* __restrict__ vtile, int T, int NG,
                   float4* __restrict__ vert4p, float4* __restrict__ tinfo) {
     const int b = blockIdx.y;
     const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -75,9 +75,46 @@ pack_tiles_kernel(const float* __restrict__ verts, int V, const int* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
     if (lane == 0) {
-        float4* o = tinfo + ((size_t)b * T + t) * 2;
+        float4* o = tinfo + ((size_t)b * (T + NG) + t) * 2;
         o[0] = make_float4(cx, cy, cz, sqrtf(r2) * 1.0001f + 1e-7f);
         o[1] = make_float4(wm, 0.f, 0.f, 0.f);
+    }
+}
+
+// one warp per tile group: bounding sphere of its tile spheres and the largest |v|^2
+__global__ void __launch_bounds__(128)
+pack_groups_kernel(const int* __restrict__ vgroup_off, int T, int NG, float4* __restrict__ tinfo) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= NG) return;
+    float4* ib = tinfo + (size_t)b * (T + NG) * 2;
+    const int t0 = vgroup_off[g], t1 = vgroup_off[g + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, wm = 0.f;
+    for (int t = t0 + lane; t < t1; t += 32) {
+        const float4 s = ib[2 * t];
+        sx += s.x; sy += s.y; sz += s.z;
+        wm = fmaxf(wm, ib[2 * t + 1].x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    }
+    const float inv = 1.f / (float)(t1 - t0);
+    const float cx = sx * inv, cy = sy * inv, cz = sz * inv;
+    float r = 0.f;
+    for (int t = t0 + lane; t < t1; t += 32) {
+        const float4 s = ib[2 * t];
+        r = fmaxf(r, sqrtf((s.x - cx) * (s.x - cx) + (s.y - cy) * (s.y - cy) + (s.z - cz) * (s.z - cz)) + s.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if (lane == 0) {
+        ib[2 * (T + g)] = make_float4(cx, cy, cz, r * 1.0001f + 1e-7f);
+        ib[2 * (T + g) + 1] = make_float4(wm, 0.f, 0.f, 0.f);
     }
 }
 
@@ -104,7 +141,8 @@ __device__ __forceinline__ void nearest_eval_tile(const float4* __restrict__ tv,
 // grid (groups of NT_WARPS query tiles, bodies)
 __global__ void __launch_bounds__(NT_WARPS * 32)
 nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
-                     const uint32_t* __restrict__ maskP, const int* __restrict__ vtile, int V, int T,
+                     const uint32_t* __restrict__ maskP, const int* __restrict__ vtile,
+                     const int* __restrict__ vgroup_off, int V, int T, int NG,
                      int* __restrict__ argmin_out, float* __restrict__ min_out) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -113,21 +151,28 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     const int slot = qt * 32 + lane;                                   // query column (tile slot)
     const int oc = vtile[slot];                                        // original vertex id, -1 = padding
     const float4* vb = vert4p + (size_t)b * T * 32;
-    const float4* ib = tinfo + (size_t)b * T * 2;
+    const float4* ib = tinfo + (size_t)b * (T + NG) * 2;
     const float4 q = vb[slot];
     const uint32_t* mcol = maskP + slot;                               // mask words of this column, stride T*32
     const size_t mstride = (size_t)T * 32;
 
-    // pass 1: the tile whose sphere promises the smallest masked distance, (d + R)^2
+    // pass 1: the tile whose sphere promises the smallest masked distance |q - c| + R.  A whole group of
+    // tiles is skipped when its sphere cannot beat the running bound of any query of the warp.
     float ub = INFINITY;
     int tstar = -1;
-#pragma unroll 2
-    for (int t = 0; t < T; ++t) {
-        const uint32_t m = mcol[(size_t)t * mstride];
-        const float4 s = __ldg(ib + 2 * t);
-        const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
-        const float d = sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + s.w;
-        if (m != 0u && d < ub) { ub = d; tstar = t; }
+    for (int g = 0; g < NG; ++g) {
+        const float4 gs = __ldg(ib + 2 * (T + g));
+        const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
+        const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
+        if (!__any_sync(0xffffffffu, glo < ub)) continue;
+        const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
+        for (int t = t0; t < t1; ++t) {
+            const uint32_t m = mcol[(size_t)t * mstride];
+            const float4 s = __ldg(ib + 2 * t);
+            const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
+            const float d = sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + s.w;
+            if (m != 0u && d < ub) { ub = d; tstar = t; }
+        }
     }
     // evaluate those tiles first (a warp's queries are neighbours: few distinct ones): from here on
     // `best` is a tight bound for the sphere test
@@ -139,17 +184,25 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         nearest_eval_tile(vb + ts * 32, vtile + ts * 32, mcol[(size_t)ts * mstride], q, best, bi);
         todo &= ~__ballot_sync(0xffffffffu, tstar == ts);
     }
-    // pass 2: every tile whose sphere can still hold a row at or below the running minimum
-    for (int t = 0; t < T; ++t) {
-        const uint32_t m = mcol[(size_t)t * mstride];
-        const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
-        const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
-        // lower bound of the true distance to any row of the tile; the slack covers the rows' fp32
-        // expansion-form values undershooting their true squared distance (<= 3.6e-7 (|v|^2 + |q|^2))
-        const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
-        const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(best, 1.00001f, 4e-6f * (q.w + s2.x)));
-        if (!__any_sync(0xffffffffu, need)) continue;
-        nearest_eval_tile(vb + t * 32, vtile + t * 32, m, q, best, bi);
+    // pass 2: every tile whose sphere can still hold a row at or below the running minimum; groups of
+    // tiles are tested first.  The slack covers the rows' fp32 expansion-form values undershooting their
+    // true squared distance (<= 3.6e-7 (|v|^2 + |q|^2)).
+    for (int g = 0; g < NG; ++g) {
+        const float4 gs = __ldg(ib + 2 * (T + g)), gs2 = __ldg(ib + 2 * (T + g) + 1);
+        const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
+        const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
+        const bool gneed = glo <= 0.f || glo * glo <= fmaf(best, 1.00001f, 4e-6f * (q.w + gs2.x));
+        if (!__any_sync(0xffffffffu, gneed)) continue;
+        const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
+        for (int t = t0; t < t1; ++t) {
+            const uint32_t m = mcol[(size_t)t * mstride];
+            const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
+            const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
+            const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
+            const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(best, 1.00001f, 4e-6f * (q.w + s2.x)));
+            if (!__any_sync(0xffffffffu, need)) continue;
+            nearest_eval_tile(vb + t * 32, vtile + t * 32, m, q, best, bi);
+        }
     }
     if (oc >= 0) {
         const bool none = bi == 0x7fffffff;                            // fully masked column
@@ -165,18 +218,22 @@ int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, 
     return 0;
 }
 
-int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, int B, int V, int T,
-                         float4* vert4p, float4* tinfo, int* argmin, float* minval, cudaStream_t st) {
+int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, const int* vgroup_off, int B,
+                         int V, int T, int NG, float4* vert4p, float4* tinfo, int* argmin, float* minval,
+                         cudaStream_t st) {
     if (B == 0) return 0;
     {
         dim3 grid(cdiv(T, 4), B);
-        pack_tiles_kernel<<<grid, 128, 0, st>>>(verts, V, vtile, T, vert4p, tinfo);
+        pack_tiles_kernel<<<grid, 128, 0, st>>>(verts, V, vtile, T, NG, vert4p, tinfo);
+        TUCH_LAUNCH_CHECK(); count_launch();
+        dim3 g2(cdiv(NG, 4), B);
+        pack_groups_kernel<<<g2, 128, 0, st>>>(vgroup_off, T, NG, tinfo);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     {
         dim3 grid(cdiv(T, NT_WARPS), B);
         KernelTimer timer("nearest_kernel", st);
-        nearest_tiles_kernel<<<grid, NT_WARPS * 32, 0, st>>>(vert4p, tinfo, maskP, vtile, V, T, argmin, minval);
+        nearest_tiles_kernel<<<grid, NT_WARPS * 32, 0, st>>>(vert4p, tinfo, maskP, vtile, vgroup_off, V, T, NG, argmin, minval);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
