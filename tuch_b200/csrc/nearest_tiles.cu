@@ -164,7 +164,7 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         const float4 gs = __ldg(ib + 2 * (T + g));
         const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
         const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
-        if (!__any_sync(0xffffffffu, glo < ub)) continue;
+        if (!__any_sync(0xffffffffu, oc >= 0 && glo < ub)) continue;      // padding lanes never vote
         const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
         for (int t = t0; t < t1; ++t) {
             const uint32_t m = mcol[(size_t)t * mstride];
@@ -191,7 +191,8 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         const float4 gs = __ldg(ib + 2 * (T + g)), gs2 = __ldg(ib + 2 * (T + g) + 1);
         const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
         const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
-        const bool gneed = glo <= 0.f || glo * glo <= fmaf(best, 1.00001f, 4e-6f * (q.w + gs2.x));
+        // lanes without any unmasked row (padding slots, fully masked columns) never vote
+        const bool gneed = tstar >= 0 && (glo <= 0.f || glo * glo <= fmaf(best, 1.00001f, 4e-6f * (q.w + gs2.x)));
         if (!__any_sync(0xffffffffu, gneed)) continue;
         const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
         for (int t = t0; t < t1; ++t) {
