@@ -295,3 +295,33 @@ def test_hierarchical_winding_touching_contact(dev, full_assets):
     assert torch.equal(a['exterior'][away], b['exterior'][away])
     n_int = (~a['exterior']).sum(1)
     assert int(n_int.min()) != int(n_int.max())          # the sweep really crosses the surface
+
+
+def test_contact_query_batch64_properties(dev, full_assets):
+    """Size-independent properties on a bench-sized batch (64 SMPL-sized bodies): the product path
+    (hierarchical winding + pruned nearest) against the all-faces / dense kernels on every body,
+    determinism, and invariance to where a body sits in the batch."""
+    from oracle import lbs as olbs
+    from tuch_b200 import synthetic as syn
+    tm = olbs.to_torch_model(full_assets['model'])
+    B = 64
+    pose = torch.tensor(np.concatenate([syn.fold_arms_pose(8, seed=40 + k, fold=0.6 + 0.06 * k) for k in range(8)]))
+    betas = torch.tensor(np.random.default_rng(40).normal(0, 0.5, size=(B, 10)).astype(np.float32))
+    verts = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev).contiguous()
+    ex = make_topology(full_assets, dev, regions=False)
+    fa = make_topology(full_assets, dev, regions=False, exact=False)
+    a = ex.contact_query(verts, use_segments=True)
+    b = fa.contact_query(verts, use_segments=True)
+    assert torch.equal(a['argmin'], b['argmin']) and torch.equal(a['min_sq'], b['min_sq'])
+    assert (a['winding'] - b['winding']).abs().max() < 5e-3
+    away = (a['winding'] - 0.99).abs() > 1e-4
+    assert torch.equal(a['exterior'][away], b['exterior'][away])
+    assert int((~b['exterior']).sum()) > 1000
+    b2 = fa.contact_query(verts, use_segments=True)
+    for k in ('argmin', 'min_sq', 'winding', 'exterior'):
+        assert torch.equal(b[k], b2[k])
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(dev)
+    c = fa.contact_query(verts[perm].contiguous(), use_segments=True)
+    for k in ('argmin', 'min_sq', 'exterior'):
+        assert torch.equal(b[k][perm], c[k])
+    assert (b['winding'][perm] - c['winding']).abs().max() < 5e-6
