@@ -277,3 +277,43 @@ def test_eft_contact_loss_against_oracle(ctx):
     got.backward()
     assert abs(got.item() - total.item()) < 1e-4 * abs(total.item())
     assert rel(v.grad, v64.grad.numpy()) < 2e-4
+
+
+def test_contact_fit_cuda_graph_replay_equals_eager(ctx):
+    """ContactFit.capture(): the iteration replayed as a CUDA graph gives bit-identical parameters and
+    losses to the eager iteration, capture() itself does not advance the optimisation, and load() re-uses
+    the captured graph for a new batch like a fresh begin_contact_fit()."""
+    from tuch_b200 import synthetic as syn
+    from tuch_b200.smplify.smplifydc import SMPLifyDC
+    g = ctx['g']
+    ign = [syn.JOINT_IDS[n] for n in syn.IGN_JOINTS]
+    opt = SMPLifyDC(step_size=1e-2, batch_size=3, num_iters=4, focal_length=5000.0, geodistssmpl=ctx['geod'],
+                    geothres=float(g['geothres']), euclthres=0.02, device=torch.device(DEV),
+                    smpl=ctx['smpl'], pose_prior=ctx['prior'], ign_joints=ign)
+
+    def begin(pose):
+        kp = t(g['keypoints_2d'])
+        conf = kp[:, :, 2].clone()
+        conf[:, ign] = 0.0
+        return opt.begin_contact_fit(pose[:, 3:].clone(), pose[:, :3].clone(), t(g['init_betas']), t(g['init_cam_t']),
+                                     t(g['camera_center']), kp[:, :, :2].contiguous(), conf, ctx['a']['regions'],
+                                     [t(g['gt_contact']), None], torch.zeros(3, dtype=torch.bool, device=DEV),
+                                     t(g['has_discrete_contact']), 2000.0, 'sum', ctx['segments'])
+    pose0 = t(g['init_pose'])
+    eager = begin(pose0)
+    le = [float(eager.step()) for _ in range(4)]
+    graph = begin(pose0).capture()
+    assert torch.equal(graph.body_pose.detach(), pose0[:, 3:])          # capture() restored the state
+    lg = [float(graph.step()) for _ in range(4)]
+    assert le == lg
+    assert torch.equal(eager.body_pose.detach(), graph.body_pose.detach())
+    assert torch.equal(eager.global_orient.detach(), graph.global_orient.detach())
+    assert torch.equal(eager.vertices, graph.vertices)
+    # a new batch through the same graph
+    pose1 = pose0 + 0.05 * torch.randn(pose0.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
+    eager1 = begin(pose1)
+    le1 = [float(eager1.step()) for _ in range(3)]
+    graph.load(pose1, t(g['init_betas']), t(g['init_cam_t']), t(g['camera_center']), t(g['keypoints_2d']),
+               t(g['gt_contact']), torch.zeros(3, dtype=torch.bool, device=DEV), t(g['has_discrete_contact']))
+    lg1 = [float(graph.step()) for _ in range(3)]
+    assert le1 == lg1 and torch.equal(eager1.body_pose.detach(), graph.body_pose.detach())

@@ -67,8 +67,9 @@ class ContactFit:
                          contact_loss_weight=contact_loss_weight, output=contact_loss_return, segments=segments)
         self.vertices = None
         self.loss = None
+        self._graph = None
 
-    def step(self):
+    def _step_eager(self):
         out = self.owner._forward(self.global_orient, self.body_pose, self.betas)
         self.vertices = out.vertices
         self.loss = contact_fitting_loss(self.body_pose, self.global_orient, self.loop1_pose, self.loop1_orient,
@@ -78,6 +79,74 @@ class ContactFit:
         self.loss.backward()
         self.opt.step()
         return self.loss
+
+    def step(self):
+        """One iteration: SMPL forward -> contact_fitting_loss -> backward -> Adam.  Returns the loss (a
+        0-d device tensor; after capture() the same tensor object every time)."""
+        if self._graph is not None:
+            self._graph.replay()
+            return self.loss
+        return self._step_eager()
+
+    def capture(self, warmup=2):
+        """Captures one iteration into a CUDA graph: every later step() is a single graph launch (no
+        per-kernel launch latency, no Python between the ~60 kernels).  The iteration has no host
+        synchronisation and the library's scratch arenas only grow outside captures, so the warm-up
+        iterations run on the capture stream first; parameters and optimiser state are restored
+        afterwards, i.e. capture() does not advance the optimisation.  `vertices` and `loss` become static
+        tensors that every replay overwrites."""
+        if self._graph is not None:
+            return self
+        params = [self.body_pose, self.global_orient]
+        saved = [p.detach().clone() for p in params]
+        saved_state = [[t.clone() for t in st] for st in self.opt.state]
+        s = torch.cuda.Stream(device=self.body_pose.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):
+                self._step_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.no_grad():
+            for p, v in zip(params, saved):
+                p.copy_(v)
+            for st, sv in zip(self.opt.state, saved_state):
+                for t, v in zip(st, sv):
+                    t.copy_(v)
+        self.opt.zero_grad()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            self._step_eager()
+        self._graph = g
+        return self
+
+    def load(self, init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, gt_contact_l3=None,
+             ignore_idxs=None, has_discrete_contact=None):
+        """Re-uses this fit (and its captured graph) for a new batch of the same size: copies the inputs
+        -- device tensors or pinned host tensors -- into the tensors the iteration reads and resets the
+        optimiser state, like a fresh begin_contact_fit()."""
+        dev = self.body_pose.device
+        to = lambda t: t.to(dev, non_blocking=True)
+        with torch.no_grad():
+            pose = to(init_pose)
+            self.global_orient.copy_(pose[:, :3])
+            self.body_pose.copy_(pose[:, 3:])
+            self.betas.copy_(to(init_betas))
+            self.args['camera_t'].copy_(to(init_cam_t))
+            self.args['camera_center'].copy_(to(camera_center))
+            kp = to(keypoints_2d)
+            self.args['joints_2d'].copy_(kp[:, :, :2])
+            self.args['joints_conf'].copy_(kp[:, :, 2])
+            self.args['joints_conf'][:, self.owner.ign_joints] = 0.0
+            if gt_contact_l3 is not None:
+                self.args['gt_contact'][0].copy_(to(gt_contact_l3))
+            if ignore_idxs is not None:
+                self.args['ignore_idxs'].copy_(to(ignore_idxs))
+            if has_discrete_contact is not None:
+                self.args['has_discrete_contact'].copy_(to(has_discrete_contact))
+            for st in self.opt.state:
+                for t in st:
+                    t.zero_()
+        return self
 
 
 class SMPLifyDC():
