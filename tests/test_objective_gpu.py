@@ -213,8 +213,9 @@ def test_adam_kernel_matches_torch_optim():
     assert (p - p_ref.detach()).abs().max() < 2e-6
 
 
-@pytest.mark.parametrize('tag,use_contact,eu', [('contact', True, 0.02), ('spin', False, 0.0)])
-def test_smplify_dc_matches_reference_golden(ctx, tag, use_contact, eu):
+@pytest.mark.parametrize('tag,use_contact,eu,graph', [('contact', True, 0.02, False), ('contact', True, 0.02, True),
+                                                     ('spin', False, 0.0, False)])
+def test_smplify_dc_matches_reference_golden(ctx, tag, use_contact, eu, graph):
     """SMPLifyDC.__call__ / get_fitting_loss against the reference's own loop (6 iterations per stage)."""
     from tuch_b200 import synthetic as syn
     from tuch_b200.smplify.smplifydc import SMPLifyDC
@@ -222,7 +223,7 @@ def test_smplify_dc_matches_reference_golden(ctx, tag, use_contact, eu):
     ign = [syn.JOINT_IDS[n] for n in syn.IGN_JOINTS]
     opt = SMPLifyDC(step_size=1e-2, batch_size=3, num_iters=6, focal_length=5000.0, geodistssmpl=ctx['geod'],
                     geothres=float(g['geothres']), euclthres=eu, device=torch.device(DEV),
-                    smpl=ctx['smpl'], pose_prior=ctx['prior'], ign_joints=ign)
+                    smpl=ctx['smpl'], pose_prior=ctx['prior'], ign_joints=ign, use_cuda_graph=graph)
     assert opt.ign_joints == list(s['ign_joints'])
     kp = t(g['keypoints_2d'])
     outs = opt(t(g['init_pose']), t(g['init_betas']), t(g['init_cam_t']), t(g['camera_center']), kp,

@@ -162,8 +162,11 @@ class SMPLifyDC():
                  geothres=0.0,
                  euclthres=0.0,
                  device=torch.device('cuda'),
-                 smpl=None, pose_prior=None, ign_joints=None):
+                 smpl=None, pose_prior=None, ign_joints=None, use_cuda_graph=False):
         self.device = torch.device(device)
+        # stage-2 iterations replayed as one CUDA graph launch each (ContactFit.capture); pays off when the
+        # iteration is launch-bound (small batches)
+        self.use_cuda_graph = bool(use_cuda_graph)
         if self.device.type != 'cuda':
             raise ops.TuchError('SMPLifyDC needs a CUDA device: tuch_b200 has no CPU fallback')
         self.focal_length = focal_length
@@ -248,9 +251,11 @@ class SMPLifyDC():
             fit = self.begin_contact_fit(body_pose, global_orient, betas, camera_translation, camera_center,
                                          joints_2d, joints_conf, contactlist, gt_contact, ignore_idxs,
                                          has_discrete_contact, contact_loss_weight, contact_loss_return, segments)
+            if self.use_cuda_graph and self.num_iters > 2:
+                fit.capture()
             for _ in range(self.num_iters):
                 fit.step()
-                optiverts.append(fit.vertices)
+                optiverts.append(fit.vertices.clone() if self.use_cuda_graph else fit.vertices)
         else:
             body_pose.requires_grad_(True)
             betas.requires_grad_(True)
