@@ -567,9 +567,11 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     if (want_w && t->winding_mode == TUCH_WINDING_FAST && !t->has_clusters) {
         // no template was given: cluster the faces on the first body seen (one blocking copy, once);
         // inside a CUDA-graph capture the exact kernel is used instead
+        static std::mutex lazy_mu;                        // two threads may race to the first query
+        std::lock_guard<std::mutex> lk(lazy_mu);
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         TUCH_CUDA(cudaStreamIsCapturing(st, &cs));
-        if (cs == cudaStreamCaptureStatusNone) {
+        if (cs == cudaStreamCaptureStatusNone && !t->has_clusters) {
             std::vector<float> h((size_t)V * 3);
             TUCH_CUDA(cudaMemcpyAsync(h.data(), verts, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
             TUCH_CUDA(cudaStreamSynchronize(st));
