@@ -13,6 +13,8 @@
 #include "api_internal.h"
 #include "smpl_internal.h"
 
+#include <algorithm>
+
 namespace tuch {
 
 
@@ -408,6 +410,69 @@ lbs_bwd_contract_kernel(const float* __restrict__ M, int n_rows, int n_coords,
     }
 }
 
+// Tiled variant for the 207-row pose-blend contraction (a [B, 3V] x [3V, 207] GEMM, K = 20,670): a CTA owns
+// a 64-body x 64-row output tile over one K split, streams 32-wide K slabs of both operands through shared
+// memory ([k][row] so that a thread reads its 8 rows / 4 bodies as vectors) and keeps a 4 x 8 register
+// tile; the K splits are summed in a fixed order by lbs_contract_reduce_kernel.  Every operand
+// element is read 4 times from L2 instead of 32 (M) / 26 (G).
+constexpr int GT_B = 64, GT_R = 64, GT_K = 32, GT_THREADS = 128;
+
+__global__ void __launch_bounds__(GT_THREADS)
+lbs_contract_tiled_kernel(const float* __restrict__ M, const float* __restrict__ G, int n_rows, int n_coords, int B,
+                          int k_per_split, float* __restrict__ partial) {
+    __shared__ __align__(16) float sM[GT_K][GT_R + 4];
+    __shared__ __align__(16) float sG[GT_K][GT_B + 4];
+    const int r0 = blockIdx.x * GT_R, b0 = blockIdx.y * GT_B, split = blockIdx.z;
+    const int k0 = split * k_per_split, k1 = min(n_coords, k0 + k_per_split);
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;         // rows tx*8.., bodies ty*4..
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int kk = k0; kk < k1; kk += GT_K) {
+#pragma unroll
+        for (int i = 0; i < GT_R * GT_K / GT_THREADS; ++i) {
+            const int e = threadIdx.x + GT_THREADS * i, row = e / GT_K, k = e % GT_K;
+            sM[k][row] = (r0 + row < n_rows && kk + k < k1) ? __ldg(M + (size_t)(r0 + row) * n_coords + kk + k) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < GT_B * GT_K / GT_THREADS; ++i) {
+            const int e = threadIdx.x + GT_THREADS * i, bb = e / GT_K, k = e % GT_K;
+            sG[k][bb] = (b0 + bb < B && kk + k < k1) ? G[(size_t)(b0 + bb) * n_coords + kk + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < GT_K; ++k) {
+            const float4 m0 = *reinterpret_cast<const float4*>(&sM[k][tx * 8]);
+            const float4 m1 = *reinterpret_cast<const float4*>(&sM[k][tx * 8 + 4]);
+            const float4 g = *reinterpret_cast<const float4*>(&sG[k][ty * 4]);
+            const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gv[i], mv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int bb = b0 + ty * 4 + i, r = r0 + tx * 8 + j;
+            if (bb < B && r < n_rows) partial[((size_t)split * B + bb) * n_rows + r] = acc[i][j];
+        }
+}
+
+__global__ void lbs_contract_reduce_kernel(const float* __restrict__ partial, int n, int S, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = 0.f;
+    for (int s = 0; s < S; ++s) x += partial[(size_t)s * n + i];
+    out[i] = x;
+}
+
 // ------------------------------------------------------------------------------------------
 // backward 3/4: per (body, joint) reduction gA[b][k] = sum_{v in list(k)} w_vk g_v [v_posed; 1]^T.
 // One warp per (body, joint), no atomics (deterministic).
@@ -603,9 +668,23 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
     lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed);
     TUCH_LAUNCH_CHECK(); count_launch();
-    dim3 g2(cdiv(207, CT_ROWS), cdiv(B, CT_NB));
-    lbs_bwd_contract_kernel<<<g2, CT_THREADS, 0, st>>>(m.posedirs, 207, m.V * 3, w.g_vposed, B, w.g_pf);
-    TUCH_LAUNCH_CHECK(); count_launch();
+    {
+        // split K so that the grid fills the machine: tiles x splits >= ~3 CTAs per SM
+        const int tiles = cdiv(207, GT_R) * cdiv(B, GT_B);
+        int S = std::max(1, std::min(64, cdiv(6 * sm_count(), tiles)));
+        const int n_coords = m.V * 3;
+        int per = cdiv(cdiv(n_coords, S), GT_K) * GT_K;
+        S = cdiv(n_coords, per);
+        Scratch sc;
+        const size_t h_part = sc.plan(sizeof(float) * (size_t)S * B * 207);
+        if (int rc = sc.commit_slot(st, 2)) return rc;
+        float* partial = sc.get<float>(h_part);
+        dim3 g2(cdiv(207, GT_R), cdiv(B, GT_B), S);
+        lbs_contract_tiled_kernel<<<g2, GT_THREADS, 0, st>>>(m.posedirs, w.g_vposed, 207, n_coords, B, per, partial);
+        TUCH_LAUNCH_CHECK(); count_launch();
+        lbs_contract_reduce_kernel<<<cdiv(B * 207, 256), 256, 0, st>>>(partial, B * 207, S, w.g_pf);
+        TUCH_LAUNCH_CHECK(); count_launch();
+    }
     if (g_betas != nullptr) {
         dim3 g3(cdiv(m.L, CT_ROWS), cdiv(B, CT_NB));
         lbs_bwd_contract_kernel<<<g3, CT_THREADS, 0, st>>>(m.shapedirsT, m.L, m.V * 3, w.g_vposed, B, w.g_beta_vert);
