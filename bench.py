@@ -170,6 +170,7 @@ def run_ours(args):
     wind_ms, wind_n = ops.kernel_time('winding_kernel')
     near_ms, near_n = ops.kernel_time('nearest_kernel')
     seg_ms, seg_n = ops.kernel_time('winding_kernel_segments')
+    kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(ops.kernel_times().items()) if v[1]}
     ops.kernel_timing(enable=False)
     final_loss = float(loss.item())
     assert np.isfinite(final_loss), 'objective diverged'
@@ -225,7 +226,7 @@ def run_ours(args):
                     share_of_step=(wind_ms / ms) if ms > 0 else None,
                     equivalent_pair_evals_per_s=(pairs / (wind_avg_ms * 1e-3)) if wind_n else None,
                     nearest_kernel_avg_ms=near_ms / max(near_n, 1), segment_winding_ms_per_step=seg_ms / args.steps,
-                    clusters=fit.topo.cluster_stats(),
+                    clusters=fit.topo.cluster_stats(), kernel_ms_per_step=kernel_ms,
                     note='the winding numbers never touch HBM as a [V,F] tensor: the kernel is bound by fp32 issue slots '
                          '(see roofline_compute), not by HBM; its algorithmic bytes are the vertices in, the faces and '
                          'the winding numbers out.  See DESIGN.md section 5 and profiles/')

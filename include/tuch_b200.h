@@ -41,6 +41,8 @@ long long tuch_launch_count(void);
  * their launch stream.  tuch_kernel_timing_read synchronises on the recorded events and returns the
  * accumulated device time and launch count since the last reset. */
 int tuch_kernel_timing_enable(int on);
+/* comma-separated names of everything timed since the library was loaded (kernels or launch groups) */
+int tuch_kernel_timing_names(char* buf, int capacity);
 int tuch_kernel_timing_reset(void);
 int tuch_kernel_timing_read(const char* name, double* total_ms, long long* launches);
 /* releases every scratch arena of the current device (synchronises the device) */

@@ -68,6 +68,7 @@ def _declare(lib):
     lib.tuch_topology_set_hd.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.tuch_topology_num_hd.argtypes = [vp]
     lib.tuch_regressor_contact_loss.argtypes = [vp, vp, i32, vp, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tuch_kernel_timing_names.argtypes = [C.c_char_p, i32]
     lib.tuch_estimate_translation.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp]
     lib.tuch_rotmat_to_angle_axis.argtypes = [vp, i32, i32, vp, vp]
     lib.tuch_fits_pose_transform.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]

@@ -159,6 +159,16 @@ TUCH_EXPORT int tuch_kernel_timing_reset(void) {
     return 0;
 }
 
+TUCH_EXPORT int tuch_kernel_timing_names(char* buf, int capacity) {
+    TUCH_REQUIRE(buf != nullptr && capacity > 0, "tuch_kernel_timing_names: need a buffer");
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    std::string all;
+    for (auto& k : g_timed) all += (all.empty() ? "" : ",") + k.name;
+    TUCH_REQUIRE((int)all.size() < capacity, "tuch_kernel_timing_names: buffer of %d bytes is too small (%zu needed)", capacity, all.size() + 1);
+    std::memcpy(buf, all.c_str(), all.size() + 1);
+    return 0;
+}
+
 TUCH_EXPORT int tuch_kernel_timing_read(const char* name, double* total_ms, long long* launches) {
     TUCH_REQUIRE(name != nullptr, "tuch_kernel_timing_read: name is null");
     std::lock_guard<std::mutex> lk(g_timing_mu);
@@ -270,8 +280,21 @@ TUCH_EXPORT int tuch_topology_create(int V, int F, const int32_t* faces_host, tu
 
 static void free_regions(tuch_topology* t) {
     free_dev(t->d_region_off); free_dev(t->d_region_ids); free_dev(t->d_pair_a); free_dev(t->d_pair_b);
+    free_dev(t->d_pair_mask); free_dev(t->d_pair_word_off);
     t->d_region_off = t->d_region_ids = t->d_pair_a = t->d_pair_b = nullptr;
+    t->d_pair_mask = nullptr; t->d_pair_word_off = nullptr;
+    t->h_pair_word_off.clear(); t->max_pair_words = 0; t->has_pair_mask = false;
     t->n_regions = t->n_pairs = 0;
+}
+
+// (re)builds the per-pair sub-masks once the regions and the geodesic mask both exist
+static int refresh_pair_mask(tuch_topology* t, cudaStream_t st) {
+    t->has_pair_mask = false;
+    if (!t->has_mask || t->n_pairs == 0 || t->d_pair_word_off == nullptr) return 0;
+    if (int rc = launch_pair_mask(t->d_maskT, t->Vq, t->d_region_ids, t->d_region_off, t->d_pair_a, t->d_pair_b,
+                                  t->d_pair_word_off, t->n_pairs, t->max_pair_words, t->d_pair_mask, st)) return rc;
+    t->has_pair_mask = true;
+    return 0;
 }
 static void free_segments(tuch_topology* t) {
     free_dev(t->d_seg_vidx); free_dev(t->d_seg_faces); free_dev(t->d_slot_face); free_dev(t->d_slot_band0);
@@ -420,6 +443,7 @@ TUCH_EXPORT int tuch_topology_set_geodist(tuch_topology* t, const float* geodist
     if (int rc = ensure_mask(t)) return rc;
     if (int rc = launch_pack_mask(nullptr, geodist, geothres, t->V, t->Vq, t->W, t->d_maskT, (cudaStream_t)stream)) return rc;
     t->has_mask = true;
+    if (int rc = refresh_pair_mask(t, (cudaStream_t)stream)) return rc;
     return refresh_permuted_mask(t, (cudaStream_t)stream);
 }
 TUCH_EXPORT int tuch_topology_set_geomask(tuch_topology* t, const uint8_t* geomask, void* stream) {
@@ -427,6 +451,7 @@ TUCH_EXPORT int tuch_topology_set_geomask(tuch_topology* t, const uint8_t* geoma
     if (int rc = ensure_mask(t)) return rc;
     if (int rc = launch_pack_mask(geomask, nullptr, 0.f, t->V, t->Vq, t->W, t->d_maskT, (cudaStream_t)stream)) return rc;
     t->has_mask = true;
+    if (int rc = refresh_pair_mask(t, (cudaStream_t)stream)) return rc;
     return refresh_permuted_mask(t, (cudaStream_t)stream);
 }
 
@@ -450,7 +475,18 @@ TUCH_EXPORT int tuch_topology_set_regions(tuch_topology* t, int n_regions, const
     if (int rc = upload(pa, (size_t)n_pairs, &t->d_pair_a)) return rc;
     if (int rc = upload(pb, (size_t)n_pairs, &t->d_pair_b)) return rc;
     t->n_regions = n_regions; t->n_pairs = n_pairs;
-    return 0;
+    t->h_pair_word_off.assign(1, 0);
+    for (int p = 0; p < n_pairs; ++p) {
+        const long long na = off[pa[p] + 1] - off[pa[p]], nb = off[pb[p] + 1] - off[pb[p]];
+        const long long words = na * ((nb + 31) / 32);
+        t->max_pair_words = std::max(t->max_pair_words, words);
+        t->h_pair_word_off.push_back(t->h_pair_word_off.back() + words);
+    }
+    if (n_pairs > 0) {
+        if (int rc = upload(t->h_pair_word_off.data(), t->h_pair_word_off.size(), &t->d_pair_word_off)) return rc;
+        TUCH_CUDA(cudaMalloc((void**)&t->d_pair_mask, sizeof(uint32_t) * (size_t)std::max<long long>(1, t->h_pair_word_off.back())));
+    }
+    return refresh_pair_mask(t, nullptr);
 }
 
 TUCH_EXPORT int tuch_topology_set_segments(tuch_topology* t, int n_segments, const int32_t* vidx_off,
@@ -686,7 +722,8 @@ TUCH_EXPORT int tuch_region_min(const tuch_topology* t, const float* verts, int 
     float4* v4 = sc.get<float4>(h_v4);
     if (int rc = launch_pack_mesh(verts, t->d_faces, B, t->V, t->F, t->Fp, t->Vp, nullptr, v4, st)) return rc;
     return launch_region_min(v4, t->Vp, masked ? t->d_maskT : nullptr, t->Vq, t->d_region_ids, t->d_region_off,
-                             t->d_pair_a, t->d_pair_b, active, t->n_pairs, B, min_sq,
+                             t->d_pair_a, t->d_pair_b, active, t->n_pairs, B,
+                             t->has_pair_mask ? t->d_pair_mask : nullptr, t->d_pair_word_off, min_sq,
                              arg_i ? arg_i : sc.get<int>(h_i), arg_j ? arg_j : sc.get<int>(h_j), st);
 }
 

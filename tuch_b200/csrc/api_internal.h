@@ -25,6 +25,12 @@ struct tuch_topology {
     // DSC regions (CSR) and annotated pairs
     int n_regions = 0, n_pairs = 0;
     int *d_region_off = nullptr, *d_region_ids = nullptr, *d_pair_a = nullptr, *d_pair_b = nullptr;
+    // per-pair bit-packed sub-masks of the geodesic mask (valid when regions and mask both exist)
+    uint32_t* d_pair_mask = nullptr;
+    long long* d_pair_word_off = nullptr;
+    std::vector<long long> h_pair_word_off;   // [n_pairs + 1]
+    long long max_pair_words = 0;
+    bool has_pair_mask = false;
     // closed body segments
     int n_segments = 0, n_bands = 0, n_sv = 0, n_slots = 0;
     std::vector<int> h_vidx_off;       // [S+1] member-vertex ranges

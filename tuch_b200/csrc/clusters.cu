@@ -694,6 +694,7 @@ int cluster_splits(int B, int T, int NT, int sm_count) {
 
 int launch_cluster_pack(const ClusterJob& j, cudaStream_t st) {
     if (j.B == 0) return 0;
+    KernelTimer timer("cluster_pack_kernel", st);
     dim3 grid(cdiv(j.NT + j.NM + j.K, 4), j.B);
     // development knobs (scripts/sweep_beta.sh sweeps them); the shipped values are the constants
     static const float env_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : 0.f;

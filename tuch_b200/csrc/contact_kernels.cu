@@ -338,11 +338,37 @@ __global__ void solid_angles_kernel(const float* __restrict__ points, const floa
 // expansion-form distance, first flat index on ties (losses.py:113-116, train_module.py:83-90).
 // grid (pair slots, bodies); one block per (body, pair).
 // ------------------------------------------------------------------------------------------
+// The geodesic mask restricted to one annotated pair, bit-packed per row of region A:
+// pmask[pair_word_off[p] + a * ceil(nb / 32) + w] bit k = geomask[ia[a]][ib[32 w + k]].  Static per topology
+// (regions + mask), so the region minimum reads nb / 32 words per row instead of nb scattered mask words.
+__global__ void pair_mask_kernel(const uint32_t* __restrict__ maskT, int Vq, const int* __restrict__ region_ids,
+                                 const int* __restrict__ region_off, const int* __restrict__ pair_a,
+                                 const int* __restrict__ pair_b, const long long* __restrict__ pair_word_off,
+                                 uint32_t* __restrict__ pmask) {
+    const int p = blockIdx.y;
+    const int ra = pair_a[p], rb = pair_b[p];
+    const int* ia = region_ids + region_off[ra];
+    const int* ib = region_ids + region_off[rb];
+    const int na = region_off[ra + 1] - region_off[ra], nb = region_off[rb + 1] - region_off[rb];
+    const int nw = (nb + 31) / 32;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)na * nw) return;
+    const int a = (int)(e / nw), w = (int)(e % nw);
+    const int i = ia[a];
+    uint32_t bits = 0;
+    for (int k = 0; k < 32 && 32 * w + k < nb; ++k) {
+        const int j = ib[32 * w + k];
+        bits |= ((maskT[(size_t)(i >> 5) * Vq + j] >> (i & 31)) & 1u) << k;
+    }
+    pmask[pair_word_off[p] + e] = bits;
+}
+
 __global__ void __launch_bounds__(RM_THREADS)
 region_min_kernel(const float4* __restrict__ vert4, int Vp, const uint32_t* __restrict__ maskT, int Vq,
                   const int* __restrict__ region_ids, const int* __restrict__ region_off,
                   const int* __restrict__ pair_a, const int* __restrict__ pair_b,
-                  const uint8_t* __restrict__ active, int n_pairs,
+                  const uint8_t* __restrict__ active, int n_pairs, const uint32_t* __restrict__ pmask,
+                  const long long* __restrict__ pair_word_off,
                   float* __restrict__ min_out, int* __restrict__ arg_i, int* __restrict__ arg_j) {
     const int b = blockIdx.y, pidx = blockIdx.x;
     const size_t o = (size_t)b * n_pairs + pidx;
@@ -376,13 +402,20 @@ region_min_kernel(const float4* __restrict__ vert4, int Vp, const uint32_t* __re
             const float4 x = v[i];
             const uint32_t* mrow = maskT != nullptr ? maskT + (size_t)(i >> 5) * Vq : nullptr;
             const int sh = i & 31;
+            // packed row of the pair mask when the topology has it (c0 is a multiple of 32)
+            const uint32_t* prow = (maskT != nullptr && pmask != nullptr)
+                                       ? pmask + pair_word_off[pidx] + (long long)a * ((nb + 31) / 32) + c0 / 32 : nullptr;
             float rbest = INFINITY;
             int rc = -1;
+            uint32_t bits = 0;
             for (int c = 0; c < nc; ++c) {
                 const float4 y = s_vb[c];
                 const float zz = fmaf(x.z, y.z, fmaf(x.y, y.y, x.x * y.x));
                 float p = fmaf(-2.f, zz, x.w + y.w);
-                if (mrow != nullptr && !((mrow[s_jb[c]] >> sh) & 1u)) p = INFINITY;      // geomask[i][j]
+                if (prow != nullptr) {
+                    if ((c & 31) == 0) bits = prow[c >> 5];
+                    if (!((bits >> (c & 31)) & 1u)) p = INFINITY;                             // geomask[i][j]
+                } else if (mrow != nullptr && !((mrow[s_jb[c]] >> sh) & 1u)) p = INFINITY;
                 if (rc < 0 || p < rbest) { rbest = p; rc = c; }
             }
             const unsigned long long flat = (unsigned long long)a * nb + (unsigned long long)(c0 + rc);
@@ -515,13 +548,25 @@ int launch_solid_angles(const float* points, const float* tris, int bs, int Q, i
     return 0;
 }
 
+int launch_pair_mask(const uint32_t* maskT, int Vq, const int* region_ids, const int* region_off, const int* pair_a,
+                     const int* pair_b, const long long* pair_word_off, int n_pairs, long long max_words_per_pair,
+                     uint32_t* pmask, cudaStream_t st) {
+    if (n_pairs == 0 || max_words_per_pair == 0) return 0;
+    dim3 grid(cdiv(max_words_per_pair, 128), n_pairs);
+    pair_mask_kernel<<<grid, 128, 0, st>>>(maskT, Vq, region_ids, region_off, pair_a, pair_b, pair_word_off, pmask);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
 int launch_region_min(const float4* vert4, int Vp, const uint32_t* maskT, int Vq, const int* region_ids,
                       const int* region_off, const int* pair_a, const int* pair_b, const uint8_t* active,
-                      int n_pairs, int B, float* min_out, int* arg_i, int* arg_j, cudaStream_t st) {
+                      int n_pairs, int B, const uint32_t* pmask, const long long* pair_word_off, float* min_out,
+                      int* arg_i, int* arg_j, cudaStream_t st) {
     if (n_pairs == 0 || B == 0) return 0;
+    KernelTimer timer("region_min_kernel", st);
     dim3 grid(n_pairs, B);
     region_min_kernel<<<grid, RM_THREADS, 0, st>>>(vert4, Vp, maskT, Vq, region_ids, region_off, pair_a,
-                                                   pair_b, active, n_pairs, min_out, arg_i, arg_j);
+                                                   pair_b, active, n_pairs, pmask, pair_word_off, min_out, arg_i, arg_j);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

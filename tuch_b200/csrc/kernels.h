@@ -45,9 +45,15 @@ int launch_pairwise_dist_bwd(const float* x, const float* y, const float* P, con
                              int ny, int squared, float* gx, float* gy, cudaStream_t st);
 int launch_solid_angles(const float* points, const float* tris, int bs, int Q, int F, float* out,
                         cudaStream_t st);
+int launch_pair_mask(const uint32_t* maskT, int Vq, const int* region_ids, const int* region_off, const int* pair_a,
+                     const int* pair_b, const long long* pair_word_off, int n_pairs, long long max_words_per_pair,
+                     uint32_t* pmask, cudaStream_t st);
+// pmask / pair_word_off: optional per-pair bit-packed geodesic sub-masks (launch_pair_mask), NULL = look the
+// mask up entry by entry
 int launch_region_min(const float4* vert4, int Vp, const uint32_t* maskT, int Vq, const int* region_ids,
                       const int* region_off, const int* pair_a, const int* pair_b, const uint8_t* active,
-                      int n_pairs, int B, float* min_out, int* arg_i, int* arg_j, cudaStream_t st);
+                      int n_pairs, int B, const uint32_t* pmask, const long long* pair_word_off, float* min_out,
+                      int* arg_i, int* arg_j, cudaStream_t st);
 
 int sm_count();
 void count_launch();

@@ -649,6 +649,7 @@ lbs_bwd_chain_kernel(SmplDev m, const float* __restrict__ pose, int pose_is_rotm
 int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, int pose_is_rotmat, int B,
                        const LbsBuffers& w, float* verts, float* joints, cudaStream_t st) {
     if (B == 0) return 0;
+    KernelTimer timer("lbs_forward_kernels", st);
     lbs_pose_kernel<<<cdiv(B, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(m, betas, pose, pose_is_rotmat, B, w.R, w.Jrest,
                                                                    w.G, w.A, w.pf);
     TUCH_LAUNCH_CHECK(); count_launch();
@@ -665,6 +666,7 @@ int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, 
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
                         const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st) {
     if (B == 0) return 0;
+    KernelTimer timer("lbs_backward_kernels", st);
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
     lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed);
     TUCH_LAUNCH_CHECK(); count_launch();

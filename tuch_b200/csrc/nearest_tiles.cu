@@ -224,6 +224,7 @@ int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* v
                          cudaStream_t st) {
     if (B == 0) return 0;
     {
+        KernelTimer timer("nearest_pack_kernels", st);
         dim3 grid(cdiv(T, 4), B);
         pack_tiles_kernel<<<grid, 128, 0, st>>>(verts, V, vtile, T, NG, vert4p, tinfo);
         TUCH_LAUNCH_CHECK(); count_launch();

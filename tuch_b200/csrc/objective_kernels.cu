@@ -368,6 +368,7 @@ int launch_reprojection(const float* joints, const float* cam_t, const float* ce
                         const float* conf, int B, int J, float focal, float sigma, const float* cam_t_est,
                         float depth_weight, const float* g_loss, float* loss, float* extra, float* g_joints,
                         float* g_cam_t, cudaStream_t st) {
+    KernelTimer timer("objective_kernels", st);
     if (B == 0) return 0;
     reprojection_kernel<<<B, 64, 0, st>>>(joints, cam_t, center, joints_2d, conf, J, focal, sigma, cam_t_est,
                                           depth_weight, g_loss, loss, extra, g_joints, g_cam_t);
@@ -379,6 +380,7 @@ int launch_pose_terms(const float* means, const float* precisions, const float* 
                       const float* pose, const float* betas, int L, int B, float wp, float wa, float ws,
                       float* value, float* prior_value, int* which, float* g_pose, float* g_betas,
                       cudaStream_t st) {
+    KernelTimer timer("objective_kernels", st);
     if (B == 0) return 0;
     TUCH_REQUIRE(D <= PT_MAXD && M <= PT_MAXM, "pose prior: D=%d (max %d) or M=%d (max %d) too large", D, PT_MAXD, M, PT_MAXM);
     TUCH_REQUIRE(wa == 0.f || D >= 56, "angle prior needs a 69-dimensional body pose (got D=%d)", D);
@@ -392,6 +394,7 @@ int launch_contact_loss(const float* points, const int* argmin, const uint8_t* e
                         const uint8_t* body_active, const int* counts, int B, int N, float euclthres,
                         int pull_mode, int reduce_mode, float weight, const float* g_loss, float* loss,
                         float* parts, float* g_points, cudaStream_t st) {
+    KernelTimer timer("objective_kernels", st);
     if (B == 0) return 0;
     contact_loss_kernel<<<B, CL_THREADS, 0, st>>>(points, argmin, exterior, body_active, counts, N, euclthres,
                                                   pull_mode, reduce_mode, weight, g_loss, loss, parts, g_points);
@@ -402,6 +405,7 @@ int launch_contact_loss(const float* points, const int* argmin, const uint8_t* e
 int launch_region_sum(const float* verts, int B, int V, int n_pairs, const float* min_sq, const int* arg_i,
                       const int* arg_j, const uint8_t* body_active, float weight, const float* g_loss,
                       float* r2r, float* g_verts, cudaStream_t st) {
+    KernelTimer timer("objective_kernels", st);
     if (B == 0) return 0;
     region_sum_kernel<<<B, 128, 0, st>>>(verts, V, n_pairs, min_sq, arg_i, arg_j, body_active, weight, g_loss,
                                          r2r, g_verts);
@@ -411,6 +415,7 @@ int launch_region_sum(const float* verts, int B, int V, int n_pairs, const float
 
 int launch_adam(float* param, const float* grad, float* m, float* v, long long n, const int* step_dev,
                 int step_add, double lr, double beta1, double beta2, double eps, cudaStream_t st) {
+    KernelTimer timer("adam_kernels", st);
     if (n == 0) return 0;
     adam_kernel<<<cdiv(n, 256), 256, 0, st>>>(param, grad, m, v, n, step_dev, step_add, lr, beta1, beta2, eps);
     TUCH_LAUNCH_CHECK(); count_launch();

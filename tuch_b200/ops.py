@@ -59,6 +59,14 @@ def kernel_timing(enable=None, reset=False):
         check(lib().tuch_kernel_timing_enable(int(bool(enable))), 'tuch_kernel_timing_enable')
 
 
+def kernel_times():
+    """-> {name: (total device ms, launches)} of everything timed since the last reset."""
+    buf = C.create_string_buffer(4096)
+    check(lib().tuch_kernel_timing_names(buf, len(buf)), 'tuch_kernel_timing_names')
+    names = [n for n in buf.value.decode().split(',') if n]
+    return {n: kernel_time(n) for n in names}
+
+
 def kernel_time(name):
     """-> (total device ms, launches) of a timed kernel since the last reset."""
     ms, n = C.c_double(), C.c_longlong()
