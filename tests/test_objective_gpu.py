@@ -318,3 +318,43 @@ def test_contact_fit_cuda_graph_replay_equals_eager(ctx):
                t(g['gt_contact']), torch.zeros(3, dtype=torch.bool, device=DEV), t(g['has_discrete_contact']))
     lg1 = [float(graph.step()) for _ in range(3)]
     assert le1 == lg1 and torch.equal(eager1.body_pose.detach(), graph.body_pose.detach())
+
+
+def test_contact_fitting_loss_full_size_matches_reference_golden(full_assets):
+    """BASELINE config 1 at the real size (V=6890, F=13776): the product path (fused LBS, hierarchical
+    winding, pruned nearest vertex, analytic gradients) against the value and gradients the reference's own
+    contact_fitting_loss produced for the same body (tests/golden/make_golden_full.py)."""
+    from tuch_b200.models.smpl import SMPL
+    from tuch_b200.smplify.prior import MaxMixturePrior
+    from tuch_b200.smplify import losses as L
+    from tuch_b200.utils.segmentation import BatchBodySegment
+    g = golden('contact_full_size.npz')
+    a = full_assets
+    smpl = SMPL(model_arrays=a['model'], batch_size=1).to(DEV)
+    prior = MaxMixturePrior(gmm=a['gmm'], num_gaussians=8).to(DEV)
+    faces = t(a['model']['faces'])
+    segments = BatchBodySegment(list(a['segs'].keys()), faces, segment_data=a['segs'])
+    geomask = t(a['geo']) > float(g['geothres'])
+    pose = t(g['init_pose'])
+    bp = pose[:, 3:].clone().requires_grad_(True)
+    go = pose[:, :3].clone().requires_grad_(True)
+    out = smpl(global_orient=go, body_pose=bp, betas=t(g['init_betas']))
+    assert np.abs(out.vertices.detach().cpu().numpy() - g['verts']).max() < 2e-6
+    kp = t(g['keypoints_2d'])
+    loss, aux = L.contact_fitting_loss(
+        bp, go, bp.detach(), go.detach(), t(g['init_betas']), out.joints, geomask, 0.02, t(g['init_cam_t']),
+        t(g['camera_center']), kp[:, :, :2], kp[:, :, 2], prior, cdict=a['regions'],
+        gt_contact=[t(g['gt_contact']), None], ignore_idxs=t(g['ignore_idxs']),
+        has_discrete_contact=t(g['has_discrete_contact']), verts=out.vertices, face_tensor=faces[None],
+        focal_length=5000.0, contact_loss_weight=2000.0, segments=segments, return_parts=True)
+    loss.backward()
+    ref = float(g['loss'])
+    assert abs(loss.item() - ref) < 1e-4 * abs(ref), (loss.item(), ref)
+    assert rel(bp.grad, g['g_body_pose']) < 2e-4
+    assert rel(go.grad, g['g_orient']) < 2e-4
+    w = aux['winding'].cpu().numpy()[0]
+    assert np.abs(w - g['winding']).max() < 5e-3              # hierarchical mode: far-field error
+    safe = np.abs(g['winding'] - 0.99) > 1e-4
+    assert np.array_equal((w <= 0.99)[safe], (g['winding'] <= 0.99)[safe])
+    am = aux['argmin'].cpu().numpy()[0]
+    assert (am != g['argmin']).sum() <= 3                     # fp32 near-ties only
