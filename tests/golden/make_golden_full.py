@@ -1,6 +1,7 @@
 """BASELINE config 1 at the real size: batch=1 self-contact push/pull loss of one SMPL-sized body
 (V=6890, F=13776, lattice body) computed by EXECUTING the reference's own tuch/smplify/losses.py
-(contact_fitting_loss, CPU-patched as in make_golden.py) and tuch/utils/contact.py.  Needs ~8 GB of RAM
+(contact_fitting_loss, CPU-patched as in make_golden.py), tuch/utils/contact.py and, for two more bodies,
+tuch/train/loss.py (RegressorLoss.contact_loss with a 20k-point HD model -> regressor_full_size.npz).  Needs ~8 GB of RAM
 for the reference's [Q, F, 3, 3] solid-angle tensor.  Run in the build container:
     python tests/golden/make_golden_full.py   ->   tests/golden/contact_full_size.npz
 """
@@ -23,13 +24,16 @@ from oracle import lbs as olbs              # noqa: E402
 import make_golden as mg                    # noqa: E402
 
 
+N_HD = 20000          # HD points of the regressor-loss golden (the paper's HD model has ~20 k)
+
+
 def main():
     model = syn.make_lattice_body_model(seed=0)
     geo = syn.make_geodesics(model['v_template'], model['faces'], cache_dir='/tmp/tuch_b200_cache')
     regions = syn.make_regions(model)
     segs = syn.make_segments(model)
     gmm = syn.make_gmm()
-    hd_reg, hd_fidx = syn.make_hd_regressor(model, n_hd=16)
+    hd_reg, hd_fidx = syn.make_hd_regressor(model, n_hd=N_HD)
     cwd = os.getcwd()
     work = tempfile.mkdtemp(prefix='tuch_golden_full_')
     tmodel = mg.install_stubs(work, model, segs, hd_reg, hd_fidx, gmm)
@@ -75,7 +79,23 @@ def main():
         P[:, ~geomask] = float('inf')
         am = torch.argmin(P, axis=1)[0]
         mn = P.min(1)[0][0]
+    # ---- RegressorLoss.contact_loss with the HD path (tuch/train/loss.py:240-317) on two bodies
+    import tuch.train.loss as rtl
+    from collections import namedtuple
+    rtl.batch_pairwise_dist = cpu_pd
+    Opt = namedtuple('Opt', ['contact_loss_weight'])
+    crit = rtl.RegressorLoss(Opt(1.0), torch.device('cpu'), len(model['v_template']), face_tensor.repeat(2, 1, 1),
+                             torch.tensor(geo), geothres=geothres, euclthres=0.02,
+                             face_tensor=face_tensor.repeat(2, 1, 1), use_hd=True)
+    pose2 = torch.tensor(syn.fold_arms_pose(2, seed=78))
+    verts2 = olbs.smpl_forward(tmodel, torch.zeros(2, 10), pose2[:, 3:], pose2[:, :3])[0].detach()
+    pv = verts2.clone().requires_grad_(True)
+    rval = crit.contact_loss(pv, torch.tensor([True, True]))
+    rval.backward()
     os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, 'regressor_full_size.npz'), verts=verts2.numpy(), loss=rval.item(),
+                        g_verts=pv.grad.numpy().astype(np.float32), n_hd=N_HD, geothres=geothres)
+    print('regressor loss', rval.item(), 'file KB', os.path.getsize(os.path.join(HERE, 'regressor_full_size.npz')) // 1024)
     np.savez_compressed(os.path.join(HERE, 'contact_full_size.npz'),
                         init_pose=inp['init_pose'], init_betas=inp['init_betas'], init_cam_t=inp['init_cam_t'],
                         camera_center=inp['camera_center'], keypoints_2d=inp['keypoints_2d'],

@@ -160,3 +160,21 @@ def test_hd_inside_test_hierarchical_vs_all_faces(full_assets):
         n_int += int((df['hd_exterior'][b, :n] == 0).sum())
     assert n_int > 100
     assert torch.equal(le, lf) and (ge - gf).abs().max() <= 1e-6 * ge.abs().max()
+
+
+def test_contact_loss_full_size_matches_reference_golden(full_assets):
+    """The fused regressor contact loss (HD path, hierarchical inside test) against the value and gradient
+    the reference's own RegressorLoss.contact_loss produced for the same two SMPL-sized bodies."""
+    from tuch_b200 import synthetic as syn
+    r = golden('regressor_full_size.npz')
+    a = dict(full_assets)
+    a['hd_reg'], a['hd_fidx'] = syn.make_hd_regressor(a['model'], n_hd=int(r['n_hd']))
+    crit = make_criterion(a, True, geothres=float(r['geothres']), B=2)
+    pv = torch.tensor(r['verts'], device=DEV, requires_grad=True)
+    val = crit.contact_loss(pv, torch.tensor([True, True], device=DEV))
+    val.backward()
+    ref = float(r['loss'])
+    assert abs(val.item() - ref) < 2e-3 * abs(ref), (val.item(), ref)
+    g, gr = pv.grad.cpu().double().flatten(), torch.tensor(r['g_verts']).double().flatten()
+    assert float((g * gr).sum() / (g.norm() * gr.norm())) > 0.9995
+    assert rel(pv.grad, r['g_verts']) < 5e-2
