@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <numeric>
+#include <type_traits>
 #include <unordered_map>
 
 #include "api_internal.h"
@@ -248,6 +249,19 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// the same over aligned groups of W lanes (W = 16: the two half-warps reduce independently)
+template <int W>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 
 // One warp per node; nodes are laid out [tops | mids | leaves].  The two half-warps walk alternate leaves
 // of the node, one lane per face slot.  Record layout (all moments pre-scaled so that the kernel's sum is
@@ -409,15 +423,16 @@ struct NodeMoments {
         tzzx += 2.f * nz * sxz + nx * szz; tzzy += 2.f * nz * syz + ny * szz;
         txyz += 2.f * (nx * syz + ny * sxz + nz * sxy);
     }
+    template <int W>
     __device__ __forceinline__ void reduce() {
-        r2 = warp_max(r2);
-        m0x = warp_sum(m0x); m0y = warp_sum(m0y); m0z = warp_sum(m0z); tr = warp_sum(tr);
-        qxx = warp_sum(qxx); qyy = warp_sum(qyy); qzz = warp_sum(qzz);
-        qxy = warp_sum(qxy); qxz = warp_sum(qxz); qyz = warp_sum(qyz);
-        uvx = warp_sum(uvx); uvy = warp_sum(uvy); uvz = warp_sum(uvz);
-        txxx = warp_sum(txxx); tyyy = warp_sum(tyyy); tzzz = warp_sum(tzzz);
-        txxy = warp_sum(txxy); txxz = warp_sum(txxz); tyyx = warp_sum(tyyx); tyyz = warp_sum(tyyz);
-        tzzx = warp_sum(tzzx); tzzy = warp_sum(tzzy); txyz = warp_sum(txyz);
+        r2 = group_max<W>(r2);
+        m0x = group_sum<W>(m0x); m0y = group_sum<W>(m0y); m0z = group_sum<W>(m0z); tr = group_sum<W>(tr);
+        qxx = group_sum<W>(qxx); qyy = group_sum<W>(qyy); qzz = group_sum<W>(qzz);
+        qxy = group_sum<W>(qxy); qxz = group_sum<W>(qxz); qyz = group_sum<W>(qyz);
+        uvx = group_sum<W>(uvx); uvy = group_sum<W>(uvy); uvz = group_sum<W>(uvz);
+        txxx = group_sum<W>(txxx); tyyy = group_sum<W>(tyyy); tzzz = group_sum<W>(tzzz);
+        txxy = group_sum<W>(txxy); txxz = group_sum<W>(txxz); tyyx = group_sum<W>(tyyx); tyyz = group_sum<W>(tyyz);
+        tzzx = group_sum<W>(tzzx); tzzy = group_sum<W>(tzzy); txyz = group_sum<W>(txyz);
     }
     __device__ __forceinline__ void write(float4* o, float px, float py, float pz, float beta) const {
         o[0] = make_float4(px, py, pz, r2 * (beta * beta * 1.0002f));
@@ -468,16 +483,13 @@ cluster_pack_top_kernel(const float* __restrict__ verts, int V, const int* __res
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nm = m1 - m0, nl = l1 - l0;
-    for (int n = warp; n < 1 + nm + nl; n += 8) {
-        int s0, s1, node;
-        float beta = beta_group;
-        if (n == 0) { s0 = 0; s1 = n_slots; node = t; }
-        else if (n <= nm) { s0 = (mid_off[m0 + n - 1] - l0) * WC_LEAF; s1 = (mid_off[m0 + n] - l0) * WC_LEAF; node = NT + m0 + n - 1; }
-        else { s0 = (n - 1 - nm) * WC_LEAF; s1 = s0 + WC_LEAF; node = NT + NM + l0 + (n - 1 - nm); beta = beta_leaf; }
-        // pass 1: area-weighted centre (plain centroid mean for zero-area nodes)
+    // one node at a time: W = 32 lanes stride over the slots [s0, s1) of a group node, W = 16 lanes own the
+    // 16 slots of a leaf (the two half-warps take two leaves at once)
+    auto reduce_node = [&](auto width, int s0, int s1, int sub, int node, float beta, bool live) {
+        constexpr int W = decltype(width)::value;
         float wsum = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f, cnt = 0.f;
-        for (int i = s0 + lane; i < s1; i += 32) {
-            if (s_ok[i] == 0.f) continue;
+        for (int i = s0 + sub; i < s1; i += W) {
+            if (!live || s_ok[i] == 0.f) continue;
             const float* c = s_c + (size_t)i * 9;
             const float e1x = c[3] - c[0], e1y = c[4] - c[1], e1z = c[5] - c[2];
             const float e2x = c[6] - c[0], e2y = c[7] - c[1], e2z = c[8] - c[2];
@@ -488,24 +500,32 @@ cluster_pack_top_kernel(const float* __restrict__ verts, int V, const int* __res
             wsum += area; cx += area * gx; cy += area * gy; cz += area * gz;
             ux += gx; uy += gy; uz += gz; cnt += 1.f;
         }
-        wsum = warp_sum(wsum); cnt = warp_sum(cnt);
-        float px, py, pz;
-        if (wsum > 1e-30f) {
-            const float inv = 1.f / wsum;
-            px = warp_sum(cx) * inv; py = warp_sum(cy) * inv; pz = warp_sum(cz) * inv;
-        } else {
-            const float inv = 1.f / fmaxf(cnt, 1.f);
-            px = warp_sum(ux) * inv; py = warp_sum(uy) * inv; pz = warp_sum(uz) * inv;
-        }
-        // pass 2: radius and moments about p
+        wsum = group_sum<W>(wsum); cnt = group_sum<W>(cnt);
+        // area-weighted centre (plain centroid mean for zero-area nodes); both candidates are reduced so that
+        // the shuffles stay convergent when the two half-warps disagree
+        const float ax_ = group_sum<W>(cx), ay_ = group_sum<W>(cy), az_ = group_sum<W>(cz);
+        const float bx_ = group_sum<W>(ux), by_ = group_sum<W>(uy), bz_ = group_sum<W>(uz);
+        const bool weighted = wsum > 1e-30f;
+        const float inv = weighted ? 1.f / wsum : 1.f / fmaxf(cnt, 1.f);
+        const float px = (weighted ? ax_ : bx_) * inv, py = (weighted ? ay_ : by_) * inv, pz = (weighted ? az_ : bz_) * inv;
         NodeMoments mo;
-        for (int i = s0 + lane; i < s1; i += 32) {
-            if (s_ok[i] == 0.f) continue;
+        for (int i = s0 + sub; i < s1; i += W) {
+            if (!live || s_ok[i] == 0.f) continue;
             const float* c = s_c + (size_t)i * 9;
             mo.add(c[0] - px, c[1] - py, c[2] - pz, c[3] - px, c[4] - py, c[5] - pz, c[6] - px, c[7] - py, c[8] - pz);
         }
-        mo.reduce();
-        if (lane == 0) mo.write(nodes + ((size_t)b * (NT + NM + K) + node) * WC_NODE_F4, px, py, pz, beta);
+        mo.template reduce<W>();
+        if (live && sub == 0) mo.write(nodes + ((size_t)b * (NT + NM + K) + node) * WC_NODE_F4, px, py, pz, beta);
+    };
+    for (int n = warp; n < 1 + nm; n += 8) {                     // the top and its mids: full warps
+        if (n == 0) reduce_node(std::integral_constant<int, 32>(), 0, n_slots, lane, t, beta_group, true);
+        else reduce_node(std::integral_constant<int, 32>(), (mid_off[m0 + n - 1] - l0) * WC_LEAF,
+                         (mid_off[m0 + n] - l0) * WC_LEAF, lane, NT + m0 + n - 1, beta_group, true);
+    }
+    for (int pair = warp; 2 * pair < nl; pair += 8) {            // leaves: one per half-warp
+        const int j = 2 * pair + (lane >> 4);
+        reduce_node(std::integral_constant<int, 16>(), j * WC_LEAF, (j + 1) * WC_LEAF, lane & 15, NT + NM + l0 + j, beta_leaf,
+                    j < nl);
     }
 }
 
