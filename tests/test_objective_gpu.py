@@ -358,3 +358,42 @@ def test_contact_fitting_loss_full_size_matches_reference_golden(full_assets):
     assert np.array_equal((w <= 0.99)[safe], (g['winding'] <= 0.99)[safe])
     am = aux['argmin'].cpu().numpy()[0]
     assert (am != g['argmin']).sum() <= 3                     # fp32 near-ties only
+
+
+def test_smplify_dc_full_size_resolves_penetration(full_assets):
+    """End to end at the real size: SMPLifyDC.__call__ on 8 SMPL-sized bodies with folded-in arms; the contact
+    term must pull vertices out of the body (fewer interior vertices than at the start), everything stays
+    finite, and the 7-tuple has the reference's shapes (smplifydc.py:234)."""
+    from oracle import lbs as olbs
+    from tuch_b200 import ops, synthetic as syn
+    from tuch_b200.models.smpl import SMPL
+    from tuch_b200.smplify.prior import MaxMixturePrior
+    from tuch_b200.smplify.smplifydc import SMPLifyDC
+    from tuch_b200.utils.segmentation import BatchBodySegment
+    a = full_assets
+    model, B, iters = a['model'], 8, 15
+    tm = olbs.to_torch_model(model)
+    inp = syn.make_smplify_inputs(model, a['regions'], B, seed=9,
+                                  joints_fn=lambda p, b: olbs.smpl_forward(tm, torch.tensor(b), torch.tensor(p[:, 3:]),
+                                                                           torch.tensor(p[:, :3]))[1].numpy())
+    faces = t(model['faces'])
+    segments = BatchBodySegment(list(a['segs'].keys()), faces, segment_data=a['segs'])
+    opt = SMPLifyDC(step_size=1e-2, batch_size=B, num_iters=iters, focal_length=syn.FOCAL_LENGTH, geodistssmpl=t(a['geo']),
+                    geothres=0.3, euclthres=0.02, device=torch.device(DEV), smpl=SMPL(model_arrays=model, batch_size=B).to(DEV),
+                    pose_prior=MaxMixturePrior(gmm=a['gmm'], num_gaussians=8).to(DEV),
+                    ign_joints=[syn.JOINT_IDS[n] for n in syn.IGN_JOINTS])
+    out = opt(t(inp['init_pose']), t(inp['init_betas']), t(inp['init_cam_t']), t(inp['camera_center']),
+              t(inp['keypoints_2d']), use_contact=True, contactlist=a['regions'], gt_contact=[t(inp['gt_contact']), None],
+              ignore_idxs=t(inp['ignore_idxs']), has_discrete_contact=t(inp['has_discrete_contact']),
+              has_gt_keypoints=None, contact_loss_weight=2000.0, contact_loss_return='sum', segments=segments)
+    verts, joints, pose, betas, cam_t, reproj, optiverts = out
+    V = len(model['v_template'])
+    assert verts.shape == (B, V, 3) and joints.shape == (B, 49, 3) and pose.shape == (B, 72) and betas.shape == (B, 10)
+    assert cam_t.shape == (B, 3) and reproj.shape == (B, 49) and len(optiverts) == iters
+    for x in (verts, joints, pose, betas, cam_t, reproj):
+        assert bool(torch.isfinite(x).all())
+    topo = ops.Topology(model['faces'], V, torch.device(DEV))
+    topo.set_template(model['v_template'])
+    n0 = int((~topo.contact_query(optiverts[0].detach(), use_segments=False, want_nearest=False)['exterior']).sum())
+    n1 = int((~topo.contact_query(verts, use_segments=False, want_nearest=False)['exterior']).sum())
+    assert n0 > 500 and n1 < 0.9 * n0, (n0, n1)
