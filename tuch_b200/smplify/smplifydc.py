@@ -21,6 +21,10 @@ from .prior import MaxMixturePrior
 
 IGNORED_JOINT_NAMES = ['OP Neck', 'OP RHip', 'OP LHip', 'Right Hip', 'Left Hip']
 
+# one capture stream per device: the library keeps one grow-only scratch arena per stream, so captures
+# share it instead of each bringing their own
+_CAPTURE_STREAMS = {}
+
 
 class _Adam:
     """torch.optim.Adam(params, lr, betas) semantics over the fused Adam kernel (tuch_adam_step);
@@ -100,7 +104,10 @@ class ContactFit:
         params = [self.body_pose, self.global_orient]
         saved = [p.detach().clone() for p in params]
         saved_state = [[t.clone() for t in st] for st in self.opt.state]
-        s = torch.cuda.Stream(device=self.body_pose.device)
+        dev = self.body_pose.device
+        s = _CAPTURE_STREAMS.get(dev)
+        if s is None:
+            s = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(max(1, warmup)):
