@@ -77,8 +77,7 @@ if rank == 0:
         print('  sharded vs single-GPU: max |pose diff| %.2e (median over bodies %.2e), max |vertex diff| %.2e'
               % (float(d.max()), float(d.median()), float((ref[0] - verts_all).abs().max())))
         d2 = (ref[2] - ref2[2]).abs().amax(dim=1)
-        print('  single-GPU run vs itself:  max |pose diff| %.2e (median %.2e) -- fp32 atomics in the gradient scatter '
-              'reorder sums at the 1e-7 level; an inside/outside flag at the 0.99 threshold then occasionally flips '
-              'and Adam amplifies it' % (float(d2.max()), float(d2.median())))
+        print('  single-GPU run vs itself:  max |pose diff| %.2e (median %.2e) -- every reduction has a fixed order and '
+              'the gradient scatters accumulate in fixed point' % (float(d2.max()), float(d2.median())))
 if world > 1:
     dist.destroy_process_group()

@@ -397,3 +397,48 @@ def test_smplify_dc_full_size_resolves_penetration(full_assets):
     n0 = int((~topo.contact_query(optiverts[0].detach(), use_segments=False, want_nearest=False)['exterior']).sum())
     n1 = int((~topo.contact_query(verts, use_segments=False, want_nearest=False)['exterior']).sum())
     assert n0 > 500 and n1 < 0.9 * n0, (n0, n1)
+
+
+def test_objective_and_gradients_are_reproducible(full_assets):
+    """Every reduction on the path has a fixed order and the gradient scatters accumulate in 64-bit fixed
+    point, so two evaluations of the same inputs agree bit for bit -- loss, flags and gradients (the
+    objective is discontinuous in the inside/outside flags: without this, 1e-7 noise occasionally flips one
+    and Adam amplifies it)."""
+    from oracle import lbs as olbs
+    from tuch_b200 import synthetic as syn
+    from tuch_b200.models.smpl import SMPL
+    from tuch_b200.smplify.prior import MaxMixturePrior
+    from tuch_b200.smplify import losses as L
+    from tuch_b200.utils.segmentation import BatchBodySegment
+    a = full_assets
+    model, B = a['model'], 6
+    tm = olbs.to_torch_model(model)
+    inp = syn.make_smplify_inputs(model, a['regions'], B, seed=13,
+                                  joints_fn=lambda p, b: olbs.smpl_forward(tm, torch.tensor(b), torch.tensor(p[:, 3:]),
+                                                                           torch.tensor(p[:, :3]))[1].numpy())
+    smpl = SMPL(model_arrays=model, batch_size=B).to(DEV)
+    prior = MaxMixturePrior(gmm=a['gmm'], num_gaussians=8).to(DEV)
+    faces = t(model['faces'])
+    segments = BatchBodySegment(list(a['segs'].keys()), faces, segment_data=a['segs'])
+    geomask = t(a['geo']) > 0.3
+    kp = t(inp['keypoints_2d'])
+
+    def run():
+        pose = t(inp['init_pose'])
+        bp = pose[:, 3:].clone().requires_grad_(True)
+        go = pose[:, :3].clone().requires_grad_(True)
+        out = smpl(global_orient=go, body_pose=bp, betas=t(inp['init_betas']))
+        loss, aux = L.contact_fitting_loss(
+            bp, go, bp.detach(), go.detach(), t(inp['init_betas']), out.joints, geomask, 0.02, t(inp['init_cam_t']),
+            t(inp['camera_center']), kp[:, :, :2], kp[:, :, 2], prior, cdict=a['regions'],
+            gt_contact=[t(inp['gt_contact']), None], ignore_idxs=t(inp['ignore_idxs']),
+            has_discrete_contact=t(inp['has_discrete_contact']), verts=out.vertices, face_tensor=faces[None].repeat(B, 1, 1),
+            focal_length=5000.0, contact_loss_weight=2000.0, segments=segments, return_parts=True)
+        loss.backward()
+        return loss.detach(), bp.grad.clone(), go.grad.clone(), aux['exterior'].clone()
+    r0 = run()
+    assert int((~r0[3]).sum()) > 100
+    for _ in range(3):
+        r = run()
+        for x, y in zip(r0, r):
+            assert torch.equal(x, y)

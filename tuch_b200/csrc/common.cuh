@@ -115,6 +115,18 @@ __device__ __forceinline__ float half_solid_angle_n(float px, float py, float pz
     return atan2_poly(den == 0.f ? 0.f : num, den);
 }
 
+// ---------------------------------------------------------------- order-independent accumulation
+// Gradient scatters add many terms into the same element from different threads.  fp32 atomics make the
+// sum depend on the arrival order (run-to-run differences at the 1e-7 level that a discontinuous objective
+// amplifies); 64-bit fixed-point atomics (2^-32 resolution, +-2^31 range) are exact and therefore
+// deterministic.  A non-finite term is stored as is (it has to poison the result either way).
+constexpr float FIX_SCALE = 4294967296.f;            // 2^32
+__device__ __forceinline__ void fix_add(long long* acc, float* fallback, float v) {
+    if (!isfinite(v)) { *fallback = v; return; }
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__float2ll_rn(v * FIX_SCALE));
+}
+__device__ __forceinline__ float fix_value(long long acc) { return (float)((double)acc * (1.0 / 4294967296.0)); }
+
 // ---------------------------------------------------------------- mbarrier + 1-D TMA bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

@@ -141,11 +141,13 @@ hd_nearest_kernel(const float4* __restrict__ hd4, const int* __restrict__ proxy,
     if (live) argmin_out[(size_t)b * N + j] = bi;
 }
 
-// backward of the regressor rows: g_verts[b][col_k] += w_k g_hd[b][i]
+// backward of the regressor rows: g_verts[b][col_k] += w_k g_hd[b][i], through 64-bit fixed-point
+// accumulators g_fix[B][V][3] (zeroed by the caller) so that the sum does not depend on the arrival order;
+// hd_fold_kernel adds them into g_verts
 __global__ void hd_scatter_kernel(const float* __restrict__ g_hd, int V, int N, const int* __restrict__ idx,
                                   const int* __restrict__ counts, const int* __restrict__ row_off,
                                   const int* __restrict__ cols, const float* __restrict__ vals,
-                                  float* __restrict__ g_verts) {
+                                  float* __restrict__ g_verts, long long* __restrict__ g_fix) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= counts[b]) return;
@@ -154,11 +156,20 @@ __global__ void hd_scatter_kernel(const float* __restrict__ g_hd, int V, int N, 
     if (gx == 0.f && gy == 0.f && gz == 0.f) return;
     const int k = idx[o];
     float* g = g_verts + (size_t)b * V * 3;
+    long long* gf = g_fix + (size_t)b * V * 3;
     for (int e = row_off[k]; e < row_off[k + 1]; ++e) {
         const float w = vals[e];
         const int c = cols[e];
-        atomicAdd(&g[3 * c], w * gx); atomicAdd(&g[3 * c + 1], w * gy); atomicAdd(&g[3 * c + 2], w * gz);
+        fix_add(&gf[3 * c], &g[3 * c], w * gx); fix_add(&gf[3 * c + 1], &g[3 * c + 1], w * gy);
+        fix_add(&gf[3 * c + 2], &g[3 * c + 2], w * gz);
     }
+}
+
+__global__ void hd_fold_kernel(const long long* __restrict__ g_fix, long long n, float* __restrict__ g_verts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long a = g_fix[i];
+    if (a != 0) g_verts[i] += fix_value(a);
 }
 
 int launch_hd_select(const float* min_sq, const uint8_t* exterior, const uint8_t* body_active, const int* faces,
@@ -191,8 +202,15 @@ int launch_hd_nearest(const float4* hd4, const int* proxy, const int* counts, in
 int launch_hd_scatter(const float* g_hd, int B, int V, int N, const int* idx, const int* counts, const int* row_off,
                       const int* cols, const float* vals, float* g_verts, cudaStream_t st) {
     if (B == 0 || N == 0) return 0;
+    void* p = nullptr;
+    const size_t n = 3 * (size_t)B * V;
+    if (int rc = arena_get(st, sizeof(long long) * n, &p, 3)) return rc;
+    long long* g_fix = (long long*)p;
+    TUCH_CUDA(cudaMemsetAsync(g_fix, 0, sizeof(long long) * n, st));
     dim3 grid(cdiv(N, 256), B);
-    hd_scatter_kernel<<<grid, 256, 0, st>>>(g_hd, V, N, idx, counts, row_off, cols, vals, g_verts);
+    hd_scatter_kernel<<<grid, 256, 0, st>>>(g_hd, V, N, idx, counts, row_off, cols, vals, g_verts, g_fix);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    hd_fold_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(g_fix, (long long)n, g_verts);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

@@ -202,8 +202,8 @@ pose_terms_kernel(const float* __restrict__ means, const float* __restrict__ pre
 //         mode PULL_ALL:       every exterior point                     loss.py:306-308
 //   reduce REDUCE_SUM:  loss = sum push + sum pull                      losses.py:105, loss.py:315
 //          REDUCE_MEAN: loss = mean push + mean pull (empty -> 0)        eft/loss.py:158-166
-// gradient (scaled by weight * g_loss[b]) is scattered into g_points with atomics (two rows per
-// term: the point and its nearest partner).  counts[b] (optional) = valid points of body b.
+// gradient (scaled by weight * g_loss[b]) is scattered into g_points (two rows per term: the point and its
+// nearest partner) through 64-bit fixed-point accumulators: exact sums, reproducible run to run.  counts[b] (optional) = valid points of body b.
 // ------------------------------------------------------------------------------------------
 constexpr int CL_THREADS = 512;
 
@@ -212,7 +212,7 @@ contact_loss_kernel(const float* __restrict__ points, const int* __restrict__ ar
                     const uint8_t* __restrict__ exterior, const uint8_t* __restrict__ body_active,
                     const int* __restrict__ counts, int N, float euclthres, int pull_mode, int reduce_mode,
                     float weight, const float* __restrict__ g_loss, float* __restrict__ loss,
-                    float* __restrict__ parts, float* __restrict__ g_points) {
+                    float* __restrict__ parts, float* __restrict__ g_points, long long* __restrict__ g_fix) {
     __shared__ float s_red[CL_THREADS / 32];
     const int b = blockIdx.x;
     if (body_active != nullptr && !body_active[b]) {
@@ -257,6 +257,11 @@ contact_loss_kernel(const float* __restrict__ points, const int* __restrict__ ar
     const float up = weight * (g_loss != nullptr ? g_loss[b] : 1.f);
     if (up == 0.f) return;
     float* g = g_points + (size_t)b * N * 3;
+    // the scatter goes through 64-bit fixed-point accumulators (exact, order-independent); this CTA owns the
+    // body, so it zeroes them, scatters, and folds them into g_points itself
+    long long* gf = g_fix + (size_t)b * N * 3;
+    for (int k = threadIdx.x; k < 3 * N; k += CL_THREADS) gf[k] = 0;      // partners may lie beyond counts[b]
+    __syncthreads();
     for (int i = threadIdx.x; i < n; i += CL_THREADS) {
         const int j = am[i];
         const float dx = p[3 * i] - p[3 * j], dy = p[3 * i + 1] - p[3 * j + 1], dz = p[3 * i + 2] - p[3 * j + 2];
@@ -270,8 +275,15 @@ contact_loss_kernel(const float* __restrict__ points, const int* __restrict__ ar
         // d/dd [a tanh(d/s)^2] = 2 a t (1 - t^2) / s ;  d d / d p_i = (p_i - p_j) / d
         const float c = up * w * 2.f * a * t * (1.f - t * t) / (s * d);
         if (c == 0.f) continue;
-        atomicAdd(&g[3 * i], c * dx); atomicAdd(&g[3 * i + 1], c * dy); atomicAdd(&g[3 * i + 2], c * dz);
-        atomicAdd(&g[3 * j], -c * dx); atomicAdd(&g[3 * j + 1], -c * dy); atomicAdd(&g[3 * j + 2], -c * dz);
+        fix_add(&gf[3 * i], &g[3 * i], c * dx); fix_add(&gf[3 * i + 1], &g[3 * i + 1], c * dy);
+        fix_add(&gf[3 * i + 2], &g[3 * i + 2], c * dz);
+        fix_add(&gf[3 * j], &g[3 * j], -c * dx); fix_add(&gf[3 * j + 1], &g[3 * j + 1], -c * dy);
+        fix_add(&gf[3 * j + 2], &g[3 * j + 2], -c * dz);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * N; k += CL_THREADS) {
+        const long long a = gf[k];
+        if (a != 0) g[k] += fix_value(a);
     }
 }
 
@@ -296,17 +308,22 @@ region_sum_kernel(const float* __restrict__ verts, int V, int n_pairs, const flo
     if (on) {
         for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
             const size_t o = (size_t)b * n_pairs + p;
-            const int i = arg_i[o], j = arg_j[o];
-            if (i < 0) continue;                        // pair not annotated for this body
-            const float m = min_sq[o];
-            acc += m;
-            if (g_verts != nullptr && up != 0.f && !isinf(m) && i != j) {
-                float* g = g_verts + (size_t)b * V * 3;
+            if (arg_i[o] < 0) continue;                 // pair not annotated for this body
+            acc += min_sq[o];
+        }
+        // gradient of the attaining entries: a handful of pairs per body, added by one thread in class
+        // order (two pairs may share a vertex; a fixed order keeps the sum reproducible)
+        if (threadIdx.x == 0 && g_verts != nullptr && up != 0.f) {
+            float* g = g_verts + (size_t)b * V * 3;
+            for (int p = 0; p < n_pairs; ++p) {
+                const size_t o = (size_t)b * n_pairs + p;
+                const int i = arg_i[o], j = arg_j[o];
+                if (i < 0 || i == j || isinf(min_sq[o])) continue;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float d = 2.f * vb[3 * i + k] - 2.f * vb[3 * j + k];
-                    atomicAdd(&g[3 * i + k], up * d);
-                    atomicAdd(&g[3 * j + k], -up * d);
+                    g[3 * i + k] += up * d;
+                    g[3 * j + k] -= up * d;
                 }
             }
         }
@@ -396,8 +413,14 @@ int launch_contact_loss(const float* points, const int* argmin, const uint8_t* e
                         float* parts, float* g_points, cudaStream_t st) {
     KernelTimer timer("objective_kernels", st);
     if (B == 0) return 0;
+    long long* g_fix = nullptr;
+    if (g_points != nullptr) {                                    // fixed-point scatter accumulators
+        void* p = nullptr;
+        if (int rc = arena_get(st, sizeof(long long) * 3 * (size_t)B * N, &p, 3)) return rc;
+        g_fix = (long long*)p;
+    }
     contact_loss_kernel<<<B, CL_THREADS, 0, st>>>(points, argmin, exterior, body_active, counts, N, euclthres,
-                                                  pull_mode, reduce_mode, weight, g_loss, loss, parts, g_points);
+                                                  pull_mode, reduce_mode, weight, g_loss, loss, parts, g_points, g_fix);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }
