@@ -9,7 +9,6 @@ from tuch_b200.models.smpl import SMPL
 from tuch_b200.smplify.prior import MaxMixturePrior
 from tuch_b200.smplify.smplifydc import SMPLifyDC
 from tuch_b200.utils.segmentation import BatchBodySegment
-from oracle import lbs as olbs
 
 B, ITERS = 64, 100
 use_graph = len(sys.argv) > 1 and sys.argv[1] == 'graph'
@@ -17,9 +16,18 @@ dev = torch.device('cuda:0')
 model = syn.make_lattice_body_model(seed=0)
 geo = syn.make_geodesics(model['v_template'], model['faces'], cache_dir='/tmp/tuch_b200_cache')
 regions, segs, gmm = syn.make_regions(model), syn.make_segments(model), syn.make_gmm()
-tm = olbs.to_torch_model(model)
+_smpl_cpu_free = SMPL(model_arrays=model, batch_size=B).to(dev)          # keypoint targets from the product SMPL
+
+
+def _joints(p, b):
+    with torch.no_grad():
+        o = _smpl_cpu_free(global_orient=torch.tensor(p[:, :3], device=dev), body_pose=torch.tensor(p[:, 3:], device=dev),
+                           betas=torch.tensor(b, device=dev))
+    return o.joints.cpu().numpy()
+
+
 inp = syn.make_smplify_inputs(model, regions, B, seed=2,
-                              joints_fn=lambda p, b: olbs.smpl_forward(tm, torch.tensor(b), torch.tensor(p[:, 3:]), torch.tensor(p[:, :3]))[1].numpy())
+                              joints_fn=_joints)
 t = lambda x: torch.tensor(np.asarray(x), device=dev)
 smpl = SMPL(model_arrays=model, batch_size=B).to(dev)
 prior = MaxMixturePrior(gmm=gmm, num_gaussians=8).to(dev)

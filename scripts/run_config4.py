@@ -18,7 +18,6 @@ from tuch_b200.models.smpl import SMPL
 from tuch_b200.smplify.prior import MaxMixturePrior
 from tuch_b200.smplify.smplifydc import SMPLifyDC
 from tuch_b200.utils.segmentation import BatchBodySegment
-from oracle import lbs as olbs
 
 PER_GPU = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 ITERS = int(sys.argv[2]) if len(sys.argv) > 2 else 10
@@ -32,9 +31,18 @@ N = PER_GPU * world
 model = syn.make_lattice_body_model(seed=0)
 geo = syn.make_geodesics(model['v_template'], model['faces'], cache_dir='/tmp/tuch_b200_cache')
 regions, segs, gmm = syn.make_regions(model), syn.make_segments(model), syn.make_gmm()
-tm = olbs.to_torch_model(model)
+_smpl_all = SMPL(model_arrays=model, batch_size=N).to(dev)                     # keypoint targets from the product SMPL
+
+
+def _joints(p, b):
+    with torch.no_grad():
+        o = _smpl_all(global_orient=torch.tensor(p[:, :3], device=dev), body_pose=torch.tensor(p[:, 3:], device=dev),
+                      betas=torch.tensor(b, device=dev))
+    return o.joints.cpu().numpy()
+
+
 inp = syn.make_smplify_inputs(model, regions, N, seed=4,
-                              joints_fn=lambda p, b: olbs.smpl_forward(tm, torch.tensor(b), torch.tensor(p[:, 3:]), torch.tensor(p[:, :3]))[1].numpy())
+                              joints_fn=_joints)
 t = lambda x: torch.tensor(np.asarray(x), device=dev)
 faces = t(model['faces'])
 segments = BatchBodySegment(list(segs.keys()), faces, segment_data=segs)

@@ -26,13 +26,14 @@ def timeit(fn, n=5):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
 
-# posed bodies with self-penetration (LBS of the CPU oracle), tiled to the batch
-from oracle import lbs as olbs
-tm = olbs.to_torch_model(m)
+# posed bodies with self-penetration (the product's fused LBS), tiled to the batch
+from tuch_b200.models.smpl import SMPL
 nb = min(B, 16)
 pose = torch.tensor(syn.fold_arms_pose(nb, seed=7))
 betas = torch.tensor(np.random.default_rng(7).normal(0, 0.5, size=(nb, 10)).astype(np.float32))
-pv = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev)
+with torch.no_grad():
+    pv = SMPL(model_arrays=m, batch_size=nb).to(dev)(global_orient=pose[:, :3].to(dev), body_pose=pose[:, 3:].to(dev),
+                                                       betas=betas.to(dev)).vertices
 verts = pv.repeat((B + nb - 1) // nb, 1, 1)[:B].contiguous()
 topo.set_template(m['v_template'])
 print('clusters', topo.cluster_stats())

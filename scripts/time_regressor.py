@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tuch_b200 import ops, synthetic as syn
 from tuch_b200.utils.segmentation import BatchBodySegment
-from oracle import lbs as olbs
+from tuch_b200.models.smpl import SMPL
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 dev = torch.device('cuda:0')
@@ -20,11 +20,12 @@ topo.set_geodist(torch.tensor(geo, device=dev), 0.3)
 bbs = BatchBodySegment(list(segs.keys()), torch.tensor(m['faces'], device=dev), segment_data=segs)
 topo.set_segments(bbs.topology_entries())
 topo.set_hd(hd_reg, hd_fidx)
-tm = olbs.to_torch_model(m)
 nb = min(B, 16)
 pose = torch.tensor(syn.fold_arms_pose(nb, seed=7))
 betas = torch.tensor(np.random.default_rng(7).normal(0, 0.5, size=(nb, 10)).astype(np.float32))
-pv = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev)
+with torch.no_grad():
+    pv = SMPL(model_arrays=m, batch_size=nb).to(dev)(global_orient=pose[:, :3].to(dev), body_pose=pose[:, 3:].to(dev),
+                                                       betas=betas.to(dev)).vertices
 verts = pv.repeat((B + nb - 1) // nb, 1, 1)[:B].contiguous()
 g = torch.zeros_like(verts)
 
