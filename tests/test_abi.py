@@ -47,3 +47,35 @@ def test_no_cpu_fallback():
         contact.winding_numbers(x, torch.zeros(1, 2, 3, 3))
     with pytest.raises(ops.TuchError):
         ops.Topology([[0, 1, 2]], 3, 'cpu')
+
+
+def test_host_entry_points_validate_their_arguments():
+    """Error convention of the ABI on the entry points that need no device: non-zero return code and a
+    message from tuch_last_error(); nothing is written on failure."""
+    import numpy as np
+    from tuch_b200 import build
+    lib = ctypes.CDLL(build.build())
+    lib.tuch_last_error.restype = ctypes.c_char_p
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    faces = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    verts = np.zeros((4, 3), np.float32)
+    n = [ctypes.c_int32(-7) for _ in range(4)]
+    refs = [ctypes.byref(x) for x in n]
+    fp, vp = faces.ctypes.data_as(ctypes.c_void_p), verts.ctypes.data_as(ctypes.c_void_p)
+    # a face index out of range
+    bad = faces.copy()
+    bad[1, 2] = 9
+    rc = lib.tuch_cluster_tree_host(bad.ctypes.data_as(ctypes.c_void_p), 2, 4, vp, None, 0, None, 0, None, 0, None, 0, *refs)
+    assert rc != 0 and b'out of range' in lib.tuch_last_error() and n[0].value == -7
+    # null mesh
+    assert lib.tuch_cluster_tree_host(None, 2, 4, vp, None, 0, None, 0, None, 0, None, 0, *refs) != 0
+    # output buffers that are too small
+    assert lib.tuch_cluster_tree_host(fp, 2, 4, vp, None, 0, None, 0, None, 0, None, 0, *refs) == 0
+    k = n[0].value
+    assert k >= 1
+    small = np.zeros((k, 16), np.int32)
+    rc = lib.tuch_cluster_tree_host(fp, 2, 4, vp, small.ctypes.data_as(ctypes.c_void_p), k - 1, None, 0, None, 0, None, 0, *refs)
+    assert rc != 0 and b'capacity' in lib.tuch_last_error()
+    # the strip builder rejects an empty face list
+    L = ctypes.c_int32(0)
+    assert lib.tuch_strip_stream_host(fp, 0, None, None, 0, ctypes.byref(L), None) != 0
