@@ -310,7 +310,7 @@ TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
     free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_vgroup_off);
-    free_dev(t->d_maskP);
+    free_dev(t->d_maskP); free_dev(t->d_maskG);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -346,6 +346,10 @@ static int refresh_permuted_mask(tuch_topology* t, cudaStream_t st) {
     t->d_maskP = nullptr;
     TUCH_CUDA(cudaMalloc((void**)&t->d_maskP, sizeof(uint32_t) * (size_t)T * T * 32));
     if (int rc = launch_permute_mask(t->d_maskT, t->Vq, t->d_vtile, T, t->d_maskP, st)) return rc;
+    free_dev(t->d_maskG);
+    t->d_maskG = nullptr;
+    TUCH_CUDA(cudaMalloc((void**)&t->d_maskG, sizeof(uint32_t) * (size_t)cdiv(t->NG, 32) * T * 32));
+    if (int rc = launch_group_mask(t->d_maskP, t->d_vgroup_off, T, t->NG, t->d_maskG, st)) return rc;
     t->has_maskP = true;
     return 0;
 }
@@ -674,7 +678,8 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         int* am = argmin ? argmin : sc.get<int>(h_am);
         float* mn = min_sq ? min_sq : sc.get<float>(h_mn);
         if (nn_tiles) {
-            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4, sc.get<float4>(h_tinfo), am, mn, st)) return rc;
+            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4,
+                                              sc.get<float4>(h_tinfo), am, mn, st)) return rc;
         } else {
             if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;
         }

@@ -17,6 +17,7 @@ struct tuch_topology {
     int K = 0, NM = 0, NT = 0, T = 0, NG = 0, max_top_leaves = 0;
     int *d_leaf_face = nullptr, *d_mid_off = nullptr, *d_top_off = nullptr, *d_vtile = nullptr, *d_vgroup_off = nullptr;
     bool has_clusters = false;
+    uint32_t* d_maskG = nullptr;       // per-group summary of d_maskP (any unmasked row in the tile group)
     uint32_t* d_maskP = nullptr;       // geodesic mask in cluster order (nearest_tiles.cu); valid when both
     bool has_maskP = false;            // the mask and the hierarchy exist
     int winding_mode = 1;              // TUCH_WINDING_FAST

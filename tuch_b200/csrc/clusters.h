@@ -60,9 +60,10 @@ struct ClusterJob {
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);
 // tinfo: [B][T + NG][2] float4 -- tile spheres, then group spheres
-int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, const int* vgroup_off, int B,
-                         int V, int T, int NG, float4* vert4p, float4* tinfo, int* argmin, float* minval,
-                         cudaStream_t st);
+int launch_group_mask(const uint32_t* maskP, const int* vgroup_off, int T, int NG, uint32_t* maskG, cudaStream_t st);
+int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32_t* maskG, const int* vtile,
+                         const int* vgroup_off, int B, int V, int T, int NG, float4* vert4p, float4* tinfo,
+                         int* argmin, float* minval, cudaStream_t st);
 
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles

@@ -5,9 +5,9 @@
 // ids inside a tile), so the 32 candidate rows of a tile -- exactly one word of the bit-packed mask --
 // have a small bounding sphere that is recomputed per body.  One warp owns the 32 query columns of one
 // tile (lane = query):
-//   pass 1: the tile with the smallest |q - c_t| + R_t among those with at least one unmasked row; the
-//           (few distinct) such tiles of the warp are evaluated first, which gives every query a tight
-//           running minimum `best`
+//   pass 1: the nearest tile GROUP with an unmasked row (a static per-group summary of the mask), then its tile
+//           with the smallest |q - c_t| + R_t; the (few distinct) such tiles of the warp are evaluated first,
+//           which gives every query a tight running minimum `best`
 //   pass 2: a tile survives for a query iff its mask word is non-zero and (|q - c_t| - R_t)^2 <= best
 //           (with fp32 slack that covers the rounding of the expansion-form distance); the warp evaluates
 //           the 32 candidates of every tile that survives for ANY of its queries.
@@ -38,6 +38,23 @@ __global__ void permute_mask_kernel(const uint32_t* __restrict__ maskT, int Vq, 
         }
     }
     maskP[(size_t)t * T * 32 + s] = bits;
+}
+
+// maskG [GW][T * 32], GW = ceil(NG / 32): bit (g & 31) of maskG[g >> 5][s] = group g holds at least one row that
+// is unmasked for column s (static per topology, like maskP)
+__global__ void group_mask_kernel(const uint32_t* __restrict__ maskP, const int* __restrict__ vgroup_off, int T,
+                                  int NG, uint32_t* __restrict__ maskG) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gw = blockIdx.y;
+    if (s >= T * 32) return;
+    uint32_t bits = 0;
+    for (int k = 0; k < 32 && gw * 32 + k < NG; ++k) {
+        const int g = gw * 32 + k;
+        uint32_t any = 0;
+        for (int t = vgroup_off[g]; t < vgroup_off[g + 1]; ++t) any |= maskP[(size_t)t * T * 32 + s];
+        bits |= (any != 0u ? 1u : 0u) << k;
+    }
+    maskG[(size_t)gw * T * 32 + s] = bits;
 }
 
 // one warp per vertex tile:
@@ -141,8 +158,8 @@ __device__ __forceinline__ void nearest_eval_tile(const float4* __restrict__ tv,
 // grid (groups of NT_WARPS query tiles, bodies)
 __global__ void __launch_bounds__(NT_WARPS * 32)
 nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
-                     const uint32_t* __restrict__ maskP, const int* __restrict__ vtile,
-                     const int* __restrict__ vgroup_off, int V, int T, int NG,
+                     const uint32_t* __restrict__ maskP, const uint32_t* __restrict__ maskG,
+                     const int* __restrict__ vtile, const int* __restrict__ vgroup_off, int V, int T, int NG,
                      int* __restrict__ argmin_out, float* __restrict__ min_out) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -156,23 +173,35 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     const uint32_t* mcol = maskP + slot;                               // mask words of this column, stride T*32
     const size_t mstride = (size_t)T * 32;
 
-    // pass 1: the tile whose sphere promises the smallest masked distance |q - c| + R.  A whole group of
-    // tiles is skipped when its sphere cannot beat the running bound of any query of the warp.
+    // pass 1 (a heuristic: pass 2 is exhaustive whatever it picks): the nearest group -- by the lower bound of
+    // its sphere -- that holds an unmasked row for this query, then the tile of that group whose sphere promises
+    // the smallest masked distance |q - c| + R.  Queries of a warp are neighbours: few distinct groups.
+    int gstar = -1;
+    {
+        float glo_best = INFINITY;
+        for (int g = 0; g < NG; ++g) {
+            const float4 gs = __ldg(ib + 2 * (T + g));
+            const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
+            const float glo = sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))) - gs.w;
+            const bool has = (maskG[(size_t)(g >> 5) * mstride + slot] >> (g & 31)) & 1u;
+            if (has && glo < glo_best) { glo_best = glo; gstar = g; }
+        }
+    }
     float ub = INFINITY;
     int tstar = -1;
-    for (int g = 0; g < NG; ++g) {
-        const float4 gs = __ldg(ib + 2 * (T + g));
-        const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
-        const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
-        if (!__any_sync(0xffffffffu, oc >= 0 && glo < ub)) continue;      // padding lanes never vote
+    unsigned gtodo = __ballot_sync(0xffffffffu, gstar >= 0);
+    while (gtodo != 0u) {
+        const int g = __shfl_sync(0xffffffffu, gstar, __ffs(gtodo) - 1);
+        const bool mine = gstar == g;
         const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
         for (int t = t0; t < t1; ++t) {
             const uint32_t m = mcol[(size_t)t * mstride];
             const float4 s = __ldg(ib + 2 * t);
             const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
             const float d = sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + s.w;
-            if (m != 0u && d < ub) { ub = d; tstar = t; }
+            if (mine && m != 0u && d < ub) { ub = d; tstar = t; }
         }
+        gtodo &= ~__ballot_sync(0xffffffffu, mine);
     }
     // evaluate those tiles first (a warp's queries are neighbours: few distinct ones): from here on
     // `best` is a tight bound for the sphere test
@@ -219,9 +248,16 @@ int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, 
     return 0;
 }
 
-int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* vtile, const int* vgroup_off, int B,
-                         int V, int T, int NG, float4* vert4p, float4* tinfo, int* argmin, float* minval,
-                         cudaStream_t st) {
+int launch_group_mask(const uint32_t* maskP, const int* vgroup_off, int T, int NG, uint32_t* maskG, cudaStream_t st) {
+    dim3 grid(cdiv(T * 32, 128), cdiv(NG, 32));
+    group_mask_kernel<<<grid, 128, 0, st>>>(maskP, vgroup_off, T, NG, maskG);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32_t* maskG, const int* vtile,
+                         const int* vgroup_off, int B, int V, int T, int NG, float4* vert4p, float4* tinfo,
+                         int* argmin, float* minval, cudaStream_t st) {
     if (B == 0) return 0;
     {
         KernelTimer timer("nearest_pack_kernels", st);
@@ -235,7 +271,8 @@ int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const int* v
     {
         dim3 grid(cdiv(T, NT_WARPS), B);
         KernelTimer timer("nearest_kernel", st);
-        nearest_tiles_kernel<<<grid, NT_WARPS * 32, 0, st>>>(vert4p, tinfo, maskP, vtile, vgroup_off, V, T, NG, argmin, minval);
+        nearest_tiles_kernel<<<grid, NT_WARPS * 32, 0, st>>>(vert4p, tinfo, maskP, maskG, vtile, vgroup_off, V, T, NG, argmin,
+                                                             minval);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
