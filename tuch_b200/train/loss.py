@@ -55,7 +55,7 @@ class _RegressorContact(torch.autograd.Function):
 
 class RegressorLoss(nn.Module):
     def __init__(self, options, device, num_verts, faces, geodistssmpl, geothres=0.2, euclthres=0.02,
-                 face_tensor=None, use_hd=True, hd_regressor=None, hd_faces=None, segments=None):
+                 face_tensor=None, use_hd=True, hd_regressor=None, hd_faces=None, segments=None, template=None):
         super().__init__()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -95,6 +95,8 @@ class RegressorLoss(nn.Module):
         self._topo = ops.Topology(self.face_tensor[0], num_verts, self.device)
         self._topo.set_geomask(self.geomask)
         self._topo.set_segments(self.segments.topology_entries())
+        if template is not None:                               # e.g. smpl.v_template: the face / vertex hierarchy of the
+            self._topo.set_template(template)                  # hierarchical kernels (else: first body seen)
         if self.use_hd:
             self._topo.set_hd(hd_regressor, hd_faces)
 
