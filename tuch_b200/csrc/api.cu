@@ -594,6 +594,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st) {
     TUCH_REQUIRE(t != nullptr, "tuch_contact_query: null topology");
     TUCH_REQUIRE(B >= 0, "tuch_contact_query: negative batch");
+    TUCH_REQUIRE(B <= 65535, "tuch_contact_query: at most 65535 bodies per call (the batch is a grid dimension), got %d", B);
     if (B == 0) return 0;
     TUCH_REQUIRE(verts != nullptr, "tuch_contact_query: verts is null");
     const bool want_w = winding != nullptr || exterior != nullptr;
