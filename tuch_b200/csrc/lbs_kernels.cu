@@ -417,7 +417,7 @@ lbs_bwd_contract_kernel(const float* __restrict__ M, int n_rows, int n_coords,
 // element is read 4 times from L2 instead of 32 (M) / 26 (G).
 constexpr int GT_B = 64, GT_R = 64, GT_K = 32, GT_THREADS = 128;
 
-__global__ void __launch_bounds__(GT_THREADS)
+__global__ void __launch_bounds__(GT_THREADS, 6)
 lbs_contract_tiled_kernel(const float* __restrict__ M, const float* __restrict__ G, int n_rows, int n_coords, int B,
                           int k_per_split, float* __restrict__ partial) {
     __shared__ __align__(16) float sM[GT_K][GT_R + 4];
@@ -431,12 +431,12 @@ lbs_contract_tiled_kernel(const float* __restrict__ M, const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int kk = k0; kk < k1; kk += GT_K) {
-#pragma unroll
+#pragma unroll 8
         for (int i = 0; i < GT_R * GT_K / GT_THREADS; ++i) {
             const int e = threadIdx.x + GT_THREADS * i, row = e / GT_K, k = e % GT_K;
             sM[k][row] = (r0 + row < n_rows && kk + k < k1) ? __ldg(M + (size_t)(r0 + row) * n_coords + kk + k) : 0.f;
         }
-#pragma unroll
+#pragma unroll 8
         for (int i = 0; i < GT_B * GT_K / GT_THREADS; ++i) {
             const int e = threadIdx.x + GT_THREADS * i, bb = e / GT_K, k = e % GT_K;
             sG[k][bb] = (b0 + bb < B && kk + k < k1) ? G[(size_t)(b0 + bb) * n_coords + kk + k] : 0.f;
