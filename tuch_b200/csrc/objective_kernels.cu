@@ -287,6 +287,79 @@ contact_loss_kernel(const float* __restrict__ points, const int* __restrict__ ar
     }
 }
 
+// REDUCE_SUM form spread over gridDim.x CTAs per body (the per-point weights do not depend on the body's
+// totals): chunk x of body y adds its terms into partials[y][x][4] and scatters its gradient rows into the
+// fixed-point accumulators (zeroed by the launcher); contact_loss_fold_kernel then sums the partials in chunk
+// order and folds the accumulators into g_points.  Same values as contact_loss_kernel up to the order of the
+// fp32 loss sum; the gradient is bit-identical (exact accumulation).
+__global__ void __launch_bounds__(CL_THREADS)
+contact_loss_chunk_kernel(const float* __restrict__ points, const int* __restrict__ argmin,
+                          const uint8_t* __restrict__ exterior, const uint8_t* __restrict__ body_active,
+                          const int* __restrict__ counts, int N, float euclthres, int pull_mode, float weight,
+                          const float* __restrict__ g_loss, float* __restrict__ partials,
+                          float* __restrict__ g_points, long long* __restrict__ g_fix) {
+    __shared__ float s_red[CL_THREADS / 32];
+    const int b = blockIdx.y;
+    float* part = partials + ((size_t)b * gridDim.x + blockIdx.x) * 4;
+    if (body_active != nullptr && !body_active[b]) {
+        if (threadIdx.x < 4) part[threadIdx.x] = 0.f;
+        return;
+    }
+    const int n = counts != nullptr ? min(counts[b], N) : N;
+    const float* p = points + (size_t)b * N * 3;
+    const float up = g_points != nullptr ? weight * (g_loss != nullptr ? g_loss[b] : 1.f) : 0.f;
+    float* g = g_points != nullptr ? g_points + (size_t)b * N * 3 : nullptr;
+    long long* gf = g_fix != nullptr ? g_fix + (size_t)b * N * 3 : nullptr;
+
+    float push = 0.f, pull = 0.f, n_push = 0.f, n_pull = 0.f;
+    for (int i = blockIdx.x * CL_THREADS + threadIdx.x; i < n; i += gridDim.x * CL_THREADS) {
+        const int j = argmin[(size_t)b * N + i];
+        const float dx = p[3 * i] - p[3 * j], dy = p[3 * i + 1] - p[3 * j + 1], dz = p[3 * i + 2] - p[3 * j + 2];
+        const float d = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        float a, s, t;
+        if (!exterior[(size_t)b * N + i]) {
+            a = 1.f; s = 0.04f; t = tanhf(d / 0.04f);
+            push += t * t; n_push += 1.f;
+        } else if (pull_mode == PULL_ALL || d < euclthres) {
+            a = 0.005f; s = 0.005f; t = tanhf(d / 0.005f);
+            pull += 0.005f * (t * t); n_pull += 1.f;
+        } else continue;
+        if (up == 0.f || !(d > 0.f)) continue;          // torch.norm backward is 0 at 0
+        const float c = up * 2.f * a * t * (1.f - t * t) / (s * d);
+        if (c == 0.f) continue;
+        fix_add(&gf[3 * i], &g[3 * i], c * dx); fix_add(&gf[3 * i + 1], &g[3 * i + 1], c * dy);
+        fix_add(&gf[3 * i + 2], &g[3 * i + 2], c * dz);
+        fix_add(&gf[3 * j], &g[3 * j], -c * dx); fix_add(&gf[3 * j + 1], &g[3 * j + 1], -c * dy);
+        fix_add(&gf[3 * j + 2], &g[3 * j + 2], -c * dz);
+    }
+    push = block_sum(push, s_red);
+    pull = block_sum(pull, s_red);
+    n_push = block_sum(n_push, s_red);
+    n_pull = block_sum(n_pull, s_red);
+    if (threadIdx.x == 0) { part[0] = push; part[1] = pull; part[2] = n_push; part[3] = n_pull; }
+}
+
+__global__ void __launch_bounds__(CL_THREADS)
+contact_loss_fold_kernel(const float* __restrict__ partials, int chunks, int N, float* __restrict__ loss,
+                         float* __restrict__ parts, float* __restrict__ g_points,
+                         const long long* __restrict__ g_fix) {
+    const int b = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        float v = 0.f;
+        for (int c = 0; c < chunks; ++c) v += partials[((size_t)b * chunks + c) * 4 + threadIdx.x];
+        if (parts != nullptr) parts[4 * b + threadIdx.x] = v;
+        const float other = __shfl_xor_sync(0xfu, v, 1);
+        if (threadIdx.x == 0 && loss != nullptr) loss[b] = v + other;
+    }
+    if (g_points == nullptr) return;
+    float* g = g_points + (size_t)b * N * 3;
+    const long long* gf = g_fix + (size_t)b * N * 3;
+    for (int k = blockIdx.x * CL_THREADS + threadIdx.x; k < 3 * N; k += gridDim.x * CL_THREADS) {
+        const long long a = gf[k];
+        if (a != 0) g[k] += fix_value(a);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // region-to-region: r2r[b] = sum over active pairs of min_sq[b,p] (losses.py:116-117) and the
 // gradient of the attaining entry P[i,j] = |x_i|^2 + |x_j|^2 - 2 x_i.x_j (contact.py:42):
@@ -413,11 +486,26 @@ int launch_contact_loss(const float* points, const int* argmin, const uint8_t* e
                         float* parts, float* g_points, cudaStream_t st) {
     KernelTimer timer("objective_kernels", st);
     if (B == 0) return 0;
-    long long* g_fix = nullptr;
-    if (g_points != nullptr) {                                    // fixed-point scatter accumulators
+    const size_t fix_bytes = g_points != nullptr ? sizeof(long long) * 3 * (size_t)B * N : 0;
+    const int chunks = reduce_mode == REDUCE_SUM ? std::min((N + CL_THREADS - 1) / CL_THREADS, 16) : 1;
+    const size_t part_bytes = chunks > 1 ? sizeof(float) * 4 * (size_t)B * chunks : 0;
+    char* scratch = nullptr;
+    if (fix_bytes + part_bytes > 0) {
         void* p = nullptr;
-        if (int rc = arena_get(st, sizeof(long long) * 3 * (size_t)B * N, &p, 3)) return rc;
-        g_fix = (long long*)p;
+        if (int rc = arena_get(st, fix_bytes + part_bytes, &p, 3)) return rc;
+        scratch = (char*)p;
+    }
+    long long* g_fix = g_points != nullptr ? (long long*)scratch : nullptr;   // fixed-point scatter accumulators
+    if (chunks > 1) {
+        float* partials = (float*)(scratch + fix_bytes);
+        if (g_fix != nullptr) TUCH_CUDA(cudaMemsetAsync(g_fix, 0, fix_bytes, st));
+        contact_loss_chunk_kernel<<<dim3(chunks, B), CL_THREADS, 0, st>>>(points, argmin, exterior, body_active, counts, N,
+                                                                          euclthres, pull_mode, weight, g_loss, partials,
+                                                                          g_points, g_fix);
+        TUCH_LAUNCH_CHECK(); count_launch();
+        contact_loss_fold_kernel<<<dim3(chunks, B), CL_THREADS, 0, st>>>(partials, chunks, N, loss, parts, g_points, g_fix);
+        TUCH_LAUNCH_CHECK(); count_launch();
+        return 0;
     }
     contact_loss_kernel<<<B, CL_THREADS, 0, st>>>(points, argmin, exterior, body_active, counts, N, euclthres,
                                                   pull_mode, reduce_mode, weight, g_loss, loss, parts, g_points, g_fix);
