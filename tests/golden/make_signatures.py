@@ -20,7 +20,8 @@ TARGETS = {
     'tuch/smplify/smplifydc.py': ['SMPLifyDC.__init__', 'SMPLifyDC.__call__', 'SMPLifyDC.get_fitting_loss'],
     'tuch/train/loss.py': ['batch_face_normals', 'RegressorLoss.__init__', 'RegressorLoss.forward', 'RegressorLoss.contact_loss'],
     'tuch/train/fits_dict.py': ['FitsDict.flip_pose', 'FitsDict.rotate_pose', 'FitsDict.__getitem__', 'FitsDict.__setitem__'],
-    'tuch/train/train_module.py': ['TUCH.contact_from_verts'],
+    'tuch/train/train_module.py': ['TUCH.contact_from_verts', 'TUCH.__init__', 'TUCH.get_verts_in_contact',
+                                   'TUCH.forward_train_step'],
     'tuch/eft/loss.py': ['EFTLoss.contact_loss'],
 }
 

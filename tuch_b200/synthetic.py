@@ -547,3 +547,85 @@ def make_smplify_inputs(model, regions, batch: int, seed: int = 0, joints_fn=Non
     return dict(init_pose=init_pose, init_betas=init_betas, init_cam_t=cam_t.astype(np.float32),
                 camera_center=center, keypoints_2d=kp, gt_contact=gt,
                 has_discrete_contact=np.ones(batch, bool), ignore_idxs=np.zeros(batch, bool))
+
+
+# ---------------------------------------------------------------------------------------------
+# train-step inputs (the keys of tuch/datasets/base_dataset.py:310-331 that
+# tuch/train/train_module.py:120-141 reads) and a stand-in for the image regressor
+# ---------------------------------------------------------------------------------------------
+def make_train_batch(model, regions, batch: int, seed: int = 0, joints_fn=None, img_hw: int = IMG_RES,
+                     n_store=None, dataset='dsc'):
+    """-> (batch dict of numpy arrays + 'dataset_name' list, fits store [n_store,82]).  Even rows are "dsc"
+    rows (discrete contact labels, no SMPL ground truth), odd rows "mtp" rows (pseudo ground-truth SMPL),
+    as in the reference's mixed batches (README.md:122-124)."""
+    rng = np.random.default_rng(seed + 307)
+    n_store = 2 * batch if n_store is None else n_store
+    tgt_pose = fold_arms_pose(batch, seed=seed + 1, fold=1.1)
+    tgt_betas = rng.normal(0, 0.5, size=(batch, 10)).astype(np.float32)
+    cam_t = np.tile(np.array([[0.0, 0.0, 2 * FOCAL_LENGTH / (IMG_RES * 0.9)]], np.float32), (batch, 1))
+    cam_t = cam_t + rng.normal(0, 0.05, size=(batch, 3)).astype(np.float32)
+    kp = np.zeros((batch, 49, 3), np.float32)
+    pose_3d = np.zeros((batch, 24, 4), np.float32)
+    if joints_fn is not None:
+        j = joints_fn(tgt_pose, tgt_betas)
+        p = j + cam_t[:, None, :]
+        px = FOCAL_LENGTH * p[:, :, :2] / p[:, :, 2:3] + rng.normal(0, 2.0, size=(batch, 49, 2))   # centred pixels
+        kp[:, :, :2] = px / (IMG_RES / 2.0)
+        pose_3d[:, :, :3] = j[:, 25:, :]
+    else:
+        kp[:, :, :2] = rng.uniform(-0.6, 0.6, size=(batch, 49, 2))
+        pose_3d[:, :, :3] = rng.normal(0, 0.3, size=(batch, 24, 3))
+    kp[:, :, 2] = rng.uniform(0.5, 1.0, size=(batch, 49))
+    pose_3d[:, :, 3] = 1.0
+    is_dsc = (np.arange(batch) % 2) == 0
+    n_cls = len(regions['classes'])
+    contact_vec = np.zeros((batch, n_cls), np.float32)
+    for b in np.where(is_dsc)[0]:
+        contact_vec[b, rng.choice(n_cls, size=rng.integers(1, 4), replace=False)] = 1.0
+    store = np.zeros((n_store, 82), np.float32)
+    store[:, :72] = fold_arms_pose(n_store, seed=seed + 2, fold=0.8)
+    store[:, 72:] = rng.normal(0, 0.5, size=(n_store, 10))
+    out = dict(
+        img=rng.normal(0, 1, size=(batch, 3, img_hw, img_hw)).astype(np.float32),
+        keypoints=kp, pose_3d=pose_3d,
+        pose=np.where(is_dsc[:, None], 0, tgt_pose).astype(np.float32),
+        betas=np.where(is_dsc[:, None], 0, tgt_betas).astype(np.float32),
+        contact_vec=contact_vec,
+        has_smpl=np.zeros(batch, np.float32), has_pgt_smpl=(~is_dsc).astype(np.float32),
+        has_disc_contact=is_dsc.astype(np.float32),
+        has_gt_kpts=(is_dsc & (rng.uniform(size=batch) < 0.5)).astype(np.float32),
+        has_pose_3d=(~is_dsc & (np.arange(batch) % 4 == 3)).astype(np.float32),
+        is_flipped=(rng.uniform(size=batch) < 0.5).astype(np.int64),
+        rot_angle=np.where(rng.uniform(size=batch) < 0.6, rng.normal(0, 30, size=batch), 0).astype(np.float32),
+        sample_index=rng.permutation(n_store)[:batch].astype(np.int64),
+        dataset_name=[dataset] * batch)
+    return out, store
+
+
+def make_stand_in_regressor(seed: int = 0, spread: float = 0.15):
+    """A few-hundred-parameter stand-in for the image regressor (HMR is outside this path): pooled image ->
+    linear -> (rotmat[B,24,3,3], betas[B,10], camera[B,3]) around a folded-arm pose, so that the predicted
+    meshes self-intersect like early-training predictions do.  Plain torch; runs on either device."""
+    import torch
+    from torch import nn
+    from .utils.geometry import batch_rodrigues, rot6d_to_rotmat
+
+    class StandInRegressor(nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.pool = nn.AdaptiveAvgPool2d(4)
+            self.fc = nn.Linear(48, 24 * 6 + 10 + 3)
+            with torch.no_grad():
+                self.fc.weight.copy_(torch.randn(self.fc.weight.shape, generator=g) * 0.5)
+                self.fc.bias.zero_()
+            base = batch_rodrigues(torch.tensor(fold_arms_pose(1, seed=seed + 5, fold=1.0)).view(24, 3))
+            self.register_buffer('base6', base[:, :, :2].reshape(1, 24 * 6).clone())
+
+        def forward(self, img):
+            x = torch.tanh(self.fc(self.pool(img).flatten(1)))
+            rotmat = rot6d_to_rotmat(self.base6 + spread * x[:, :144]).view(-1, 24, 3, 3)
+            cam = torch.stack([0.9 + 0.05 * x[:, 154], 0.05 * x[:, 155], 0.05 * x[:, 156]], dim=-1)
+            return rotmat, 0.5 * x[:, 144:154], cam
+
+    return StandInRegressor()
