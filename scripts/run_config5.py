@@ -28,6 +28,9 @@ from tuch_b200.utils.segmentation import BatchBodySegment
 PER_GPU = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 ITERS = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 STEPS = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+PROFILE = len(sys.argv) > 4 and sys.argv[4] == 'profile'       # synchronised per-phase wall times (dev aid)
+SEED = int(os.environ.get('TUCH_BATCH_SEED', 5))
+GRAPH = os.environ.get('TUCH_FIT_GRAPH', '1') != '0'          # fitting iterations as CUDA graphs (captured once)
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 local = int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(local)
@@ -56,7 +59,7 @@ face_tensor = faces[None].expand(PER_GPU, -1, -1)
 crit = RegressorLoss(o, dev, V, face_tensor, geod, geothres=0.3, euclthres=0.02, face_tensor=face_tensor, use_hd=True,
                      hd_regressor=hd_reg, hd_faces=hd_fidx, segments=segments, template=model['v_template'])
 smplify = SMPLifyDC(step_size=1e-2, batch_size=PER_GPU, num_iters=max(ITERS, 1), focal_length=syn.FOCAL_LENGTH,
-                    geodistssmpl=geod, geothres=0.3, euclthres=0.02, device=dev,
+                    geodistssmpl=geod, geothres=0.3, euclthres=0.02, device=dev, use_cuda_graph=GRAPH,
                     smpl=SMPL(model_arrays=model, batch_size=PER_GPU).to(dev),
                     pose_prior=MaxMixturePrior(gmm=gmm, num_gaussians=8).to(dev),
                     ign_joints=[syn.JOINT_IDS[n] for n in syn.IGN_JOINTS])
@@ -67,7 +70,7 @@ def _joints(p, b):
         return smpl(global_orient=t(p[:, :3]), body_pose=t(p[:, 3:]), betas=t(b)).joints.cpu().numpy()
 
 
-batch, store = syn.make_train_batch(model, regions, PER_GPU, seed=5 + rank, joints_fn=_joints, img_hw=64)
+batch, store = syn.make_train_batch(model, regions, PER_GPU, seed=SEED + rank, joints_fn=_joints, img_hw=64)
 fits = FitsDict(device=dev, dataset_sizes={'dsc': len(store)})
 fits.fits_dict['dsc'] = torch.tensor(store)
 net = syn.make_stand_in_regressor(seed=0).to(dev)
@@ -89,8 +92,39 @@ def step():
     return losses, out
 
 
+if PROFILE:
+    import time
+    phases = {}
+
+    def timed(name, fn):
+        def wrapper(*a, **k):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            torch.cuda.synchronize()
+            phases[name] = phases.get(name, 0.0) + time.perf_counter() - t0
+            return r
+        return wrapper
+    tuch.smplify = type('Fit', (), {'__call__': staticmethod(timed('smplify.__call__', smplify.__call__)),
+                                    'get_fitting_loss': staticmethod(timed('get_fitting_loss', smplify.get_fitting_loss))})()
+    tuch.criterion_cospin = type('Crit', (), {'__call__': staticmethod(timed('criterion', crit.__call__)),
+                                              'segments': crit.segments})()
+    tuch.smpl = timed('smpl forwards', smpl)
+    tuch.model = type('Net', (), {'__call__': staticmethod(timed('regressor', net.__call__)), 'train': net.train})()
+    fits.__class__ = type('TimedFits', (FitsDict,), {'__getitem__': timed('fits get', FitsDict.__getitem__),
+                                                     '__setitem__': timed('fits set', FitsDict.__setitem__)})
+    tuch.contact_from_verts = timed('contact_from_verts', tuch.contact_from_verts)
+    import tuch_b200.train.train_module as tmod
+    tmod.estimate_translation = timed('estimate_translation', tmod.estimate_translation)
+    tmod.rotation_matrix_to_angle_axis = timed('rotmat_to_angle_axis', tmod.rotation_matrix_to_angle_axis)
+    _step, _bwd = tuch.forward_train_step, torch.Tensor.backward
+    tuch.forward_train_step = timed('forward_train_step (all)', _step)
+    torch.Tensor.backward = timed('backward', _bwd)
+
 step()                                                 # warm-up: scratch arenas, hierarchy, cuBLAS handles
 torch.cuda.synchronize()
+if PROFILE:
+    phases.clear()
 if world > 1:
     dist.barrier()
 n0 = ops.launch_count()
@@ -106,11 +140,15 @@ if world > 1:
 if rank == 0:
     ms = float(ms)
     print('config %s: %d bodies/GPU x %d GPU(s), %d SMPLify-DC iterations per stage in the loop: %.1f ms per train step '
-          '(max over ranks) = %.0f bodies/s; %d of our kernel launches per step'
+          '(max over ranks) = %.0f bodies/s; %d host-side launches of our kernels per step (graph replays excluded)'
           % ('5' if ITERS > 0 else '3', PER_GPU, world, ITERS, ms, PER_GPU * world / ms * 1e3,
              (ops.launch_count() - n0) // STEPS))
     print('  losses:', {k: round(float(v), 5) for k, v in losses.items()})
     print('  valid fits %d / %d, fits-store rows rewritten so far: %d' % (
         int(out['valid_kpts_anno'].sum()), PER_GPU, int((fits.fits_dict['dsc'] != torch.tensor(store)).any(dim=1).sum())))
+    if PROFILE:
+        print('  phases, ms per step (synchronised, so they add up to more than the pipelined step):')
+        for k, v in sorted(phases.items(), key=lambda kv: -kv[1]):
+            print('    %-28s %.2f' % (k, v * 1e3 / STEPS))
 if world > 1:
     dist.destroy_process_group()

@@ -243,6 +243,46 @@ def test_smplify_dc_matches_reference_golden(ctx, tag, use_contact, eu, graph):
     assert np.array_equal(kp2.cpu().numpy(), s[tag + '/kp_after'])      # in-place side effect of the reference
 
 
+def test_smplify_dc_graphed_calls_reuse_captures(ctx):
+    """use_cuda_graph=True keeps the captured stage-1 / stage-2 iterations between calls (a training loop fits
+    every step): a second call with another batch of the same size replays them on the new data and returns
+    what the eager path returns, bit for bit."""
+    from tuch_b200 import synthetic as syn
+    from tuch_b200.smplify.smplifydc import SMPLifyDC
+    g = ctx['g']
+    ign = [syn.JOINT_IDS[n] for n in syn.IGN_JOINTS]
+    mk = lambda graph: SMPLifyDC(step_size=1e-2, batch_size=3, num_iters=5, focal_length=5000.0,
+                                 geodistssmpl=ctx['geod'], geothres=float(g['geothres']), euclthres=0.02,
+                                 device=torch.device(DEV), smpl=ctx['smpl'], pose_prior=ctx['prior'], ign_joints=ign,
+                                 use_cuda_graph=graph)
+    eager, graphed = mk(False), mk(True)
+    gen = torch.Generator().manual_seed(11)
+    gt_b = torch.roll(t(g['gt_contact']), 1, dims=0)
+    batches = [
+        dict(pose=t(g['init_pose']), betas=t(g['init_betas']), cam=t(g['init_cam_t']), kp=t(g['keypoints_2d']),
+             gt=t(g['gt_contact']), ign=torch.zeros(3, dtype=torch.bool, device=DEV),
+             dc=t(g['has_discrete_contact']), hk=t(np.array([True, False, False]))),
+        dict(pose=t(g['init_pose']) + 0.05 * torch.randn(3, 72, generator=gen).to(DEV),
+             betas=t(g['init_betas']) + 0.1 * torch.randn(3, 10, generator=gen).to(DEV),
+             cam=t(g['init_cam_t']) + 0.02 * torch.randn(3, 3, generator=gen).to(DEV),
+             kp=t(g['keypoints_2d']) + torch.cat([torch.randn(3, 49, 2, generator=gen), torch.zeros(3, 49, 1)], -1).to(DEV),
+             gt=gt_b, ign=torch.tensor([False, True, False], device=DEV),
+             dc=torch.tensor([True, True, False], device=DEV), hk=t(np.array([False, False, True]))),
+    ]
+    for rnd in range(3):
+        b = batches[rnd % 2]
+        outs = []
+        for opt in (eager, graphed):
+            outs.append(opt(b['pose'], b['betas'], b['cam'], t(g['camera_center']), b['kp'], use_contact=True,
+                            contactlist=ctx['a']['regions'], gt_contact=[b['gt'], None], ignore_idxs=b['ign'],
+                            has_discrete_contact=b['dc'], has_gt_keypoints=b['hk'], contact_loss_weight=2000.0,
+                            contact_loss_return='sum', segments=ctx['segments']))
+        for x, y in zip(outs[0][:6], outs[1][:6]):
+            assert torch.equal(x, y), rnd
+        assert len(outs[1][6]) == 5 and all(torch.equal(x, y) for x, y in zip(outs[0][6], outs[1][6]))
+    assert len(graphed._camera_fits) == 1 and len(graphed._contact_fits) == 1
+
+
 def test_contact_from_verts_mirror_matches_reference_golden(ctx):
     from tuch_b200.train.train_module import contact_from_verts
     c = golden('contact_from_verts.npz')

@@ -48,6 +48,91 @@ class _Adam:
                 ops.adam_step(p, p.grad.contiguous(), m, v, t, self.lr, self.betas[0], self.betas[1], self.eps)
 
 
+def _capture_iteration(step_eager, params, opt, warmup=2):
+    """Captures one optimisation iteration (forward, loss, backward, Adam) into a CUDA graph.  The library's
+    scratch arenas only grow outside captures, so `warmup` iterations run on the capture stream first;
+    parameters and optimiser state are restored afterwards, i.e. capturing does not advance the optimisation."""
+    saved = [p.detach().clone() for p in params]
+    saved_state = [[t.clone() for t in st] for st in opt.state]
+    dev = params[0].device
+    s = _CAPTURE_STREAMS.get(dev)
+    if s is None:
+        s = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(max(1, warmup)):
+            step_eager()
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.no_grad():
+        for p, v in zip(params, saved):
+            p.copy_(v)
+        for st, sv in zip(opt.state, saved_state):
+            for t, v in zip(st, sv):
+                t.copy_(v)
+    opt.zero_grad()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        step_eager()
+    return g
+
+
+class CameraFit:
+    """Stage 1 in flight (smplifydc.py:100-134): camera translation + shape (contact mode) or + global
+    orientation, pose fixed.  Exists so that a training loop that calls SMPLifyDC every step with the same
+    batch size can replay the iteration as a CUDA graph: load() swaps the batch in."""
+
+    def __init__(self, owner, global_orient, body_pose, betas, camera_translation, init_cam_t, camera_center,
+                 joints_2d, joints_conf, use_contact):
+        self.owner = owner
+        self.global_orient, self.body_pose, self.betas = global_orient, body_pose, betas
+        self.camera_translation, self.init_cam_t, self.camera_center = camera_translation, init_cam_t, camera_center
+        self.joints_2d, self.joints_conf = joints_2d, joints_conf
+        camera_translation.requires_grad_(True)
+        if use_contact:
+            betas.requires_grad_(True)
+            self.params = [betas, camera_translation]
+        else:
+            global_orient.requires_grad_(True)
+            self.params = [global_orient, camera_translation]
+        self.spw = 1.0 if use_contact else 0.0
+        self.opt = _Adam(self.params, lr=owner.step_size, betas=(0.9, 0.999))
+        self._graph = None
+
+    def _step_eager(self):
+        out = self.owner._forward(self.global_orient, self.body_pose, self.betas)
+        loss = camera_fitting_loss(out, self.camera_translation, self.init_cam_t, self.camera_center, self.joints_2d,
+                                   self.joints_conf, focal_length=self.owner.focal_length, shape_prior_weight=self.spw)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+
+    def step(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._step_eager()
+
+    def capture(self, warmup=2):
+        if self._graph is None:
+            self._graph = _capture_iteration(self._step_eager, self.params, self.opt, warmup)
+        return self
+
+    def load(self, init_pose, init_betas, init_cam_t, camera_center, joints_2d, joints_conf):
+        with torch.no_grad():
+            self.global_orient.copy_(init_pose[:, :3])
+            self.body_pose.copy_(init_pose[:, 3:])
+            self.betas.copy_(init_betas)
+            self.camera_translation.copy_(init_cam_t)
+            self.init_cam_t.copy_(init_cam_t)
+            self.camera_center.copy_(camera_center)
+            self.joints_2d.copy_(joints_2d)
+            self.joints_conf.copy_(joints_conf)
+            for st in self.opt.state:
+                for t in st:
+                    t.zero_()
+        return self
+
+
 class ContactFit:
     """One stage-2 optimisation in flight; see SMPLifyDC.begin_contact_fit."""
 
@@ -99,31 +184,8 @@ class ContactFit:
         iterations run on the capture stream first; parameters and optimiser state are restored
         afterwards, i.e. capture() does not advance the optimisation.  `vertices` and `loss` become static
         tensors that every replay overwrites."""
-        if self._graph is not None:
-            return self
-        params = [self.body_pose, self.global_orient]
-        saved = [p.detach().clone() for p in params]
-        saved_state = [[t.clone() for t in st] for st in self.opt.state]
-        dev = self.body_pose.device
-        s = _CAPTURE_STREAMS.get(dev)
-        if s is None:
-            s = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(max(1, warmup)):
-                self._step_eager()
-        torch.cuda.current_stream().wait_stream(s)
-        with torch.no_grad():
-            for p, v in zip(params, saved):
-                p.copy_(v)
-            for st, sv in zip(self.opt.state, saved_state):
-                for t, v in zip(st, sv):
-                    t.copy_(v)
-        self.opt.zero_grad()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
-            self._step_eager()
-        self._graph = g
+        if self._graph is None:
+            self._graph = _capture_iteration(self._step_eager, [self.body_pose, self.global_orient], self.opt, warmup)
         return self
 
     def load(self, init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, gt_contact_l3=None,
@@ -171,9 +233,10 @@ class SMPLifyDC():
                  device=torch.device('cuda'),
                  smpl=None, pose_prior=None, ign_joints=None, use_cuda_graph=False):
         self.device = torch.device(device)
-        # stage-2 iterations replayed as one CUDA graph launch each (ContactFit.capture); pays off when the
-        # iteration is launch-bound (small batches)
+        # iterations of both stages replayed as one CUDA graph launch each (_call_graphed); pays off when the
+        # iteration is launch-bound (small batches, or a training loop that fits every step)
         self.use_cuda_graph = bool(use_cuda_graph)
+        self._camera_fits, self._contact_fits = {}, {}
         if self.device.type != 'cuda':
             raise ops.TuchError('SMPLifyDC needs a CUDA device: tuch_b200 has no CPU fallback')
         self.focal_length = focal_length
@@ -224,6 +287,10 @@ class SMPLifyDC():
                  contact_loss_return='sum', segments=None):
         """Perform body fitting.  Returns (vertices, joints, pose, betas, camera_translation,
         reprojection_loss, optiverts) exactly as smplifydc.py:234."""
+        if self.use_cuda_graph and use_contact and self.num_iters > 2:
+            return self._call_graphed(init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, contactlist,
+                                      gt_contact, ignore_idxs, has_discrete_contact, has_gt_keypoints,
+                                      contact_loss_weight, contact_loss_return, segments)
         camera_translation = init_cam_t.clone()
         joints_2d = keypoints_2d[:, :, :2].contiguous()
         joints_conf = keypoints_2d[:, :, -1].clone()
@@ -258,11 +325,9 @@ class SMPLifyDC():
             fit = self.begin_contact_fit(body_pose, global_orient, betas, camera_translation, camera_center,
                                          joints_2d, joints_conf, contactlist, gt_contact, ignore_idxs,
                                          has_discrete_contact, contact_loss_weight, contact_loss_return, segments)
-            if self.use_cuda_graph and self.num_iters > 2:
-                fit.capture()
             for _ in range(self.num_iters):
                 fit.step()
-                optiverts.append(fit.vertices.clone() if self.use_cuda_graph else fit.vertices)
+                optiverts.append(fit.vertices)
         else:
             body_pose.requires_grad_(True)
             betas.requires_grad_(True)
@@ -293,6 +358,62 @@ class SMPLifyDC():
         pose = torch.cat([global_orient, body_pose], dim=-1).detach()
         betas = betas.detach()
         return vertices, joints, pose, betas, camera_translation, reprojection_loss, optiverts
+
+    def _call_graphed(self, init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, contactlist, gt_contact,
+                      ignore_idxs, has_discrete_contact, has_gt_keypoints, contact_loss_weight, contact_loss_return,
+                      segments):
+        """The contact branch of __call__ with both stages replayed as CUDA graphs (one launch per iteration).
+        The captured iterations are kept per batch size and contact configuration, so a training loop that calls
+        this every step pays for the capture once; later calls copy their batch into the tensors the graphs
+        read.  Same kernels in the same order as the eager branch: identical results."""
+        B = init_pose.shape[0]
+        n = lambda t: None if t is None else t.detach().clone()
+        joints_2d = keypoints_2d[:, :, :2].contiguous()
+        joints_conf = keypoints_2d[:, :, -1].clone()
+        cam = self._camera_fits.get(B)
+        if cam is None:
+            cam = CameraFit(self, n(init_pose[:, :3]), n(init_pose[:, 3:]), n(init_betas), n(init_cam_t), n(init_cam_t),
+                            n(camera_center), joints_2d, joints_conf, use_contact=True).capture()
+            self._camera_fits[B] = cam
+        else:
+            cam.load(init_pose, init_betas, init_cam_t, camera_center, joints_2d, joints_conf)
+        for _ in range(self.num_iters):
+            cam.step()
+        betas = cam.betas.detach().clone()
+        camera_translation = cam.camera_translation.detach().clone()
+
+        gt_l3 = gt_contact[0] if gt_contact is not None else None
+        key = (B, id(contactlist), id(segments), float(contact_loss_weight), contact_loss_return, gt_l3 is None,
+               ignore_idxs is None, has_discrete_contact is None)
+        hit = self._contact_fits.get(key)
+        if hit is None:
+            conf2 = joints_conf.clone()
+            conf2[:, self.ign_joints] = 0.0
+            fit = self.begin_contact_fit(n(cam.body_pose), n(cam.global_orient), betas.clone(), camera_translation.clone(),
+                                         n(camera_center), joints_2d.clone(), conf2, contactlist,
+                                         None if gt_contact is None else [n(gt_l3)] + list(gt_contact[1:]),
+                                         n(ignore_idxs), n(has_discrete_contact), contact_loss_weight,
+                                         contact_loss_return, segments).capture()
+            self._contact_fits[key] = (fit, contactlist, segments)      # the keyed objects stay alive with the entry
+        else:
+            fit = hit[0]
+            fit.load(torch.cat([cam.global_orient, cam.body_pose], dim=-1).detach(), betas, camera_translation,
+                     camera_center, keypoints_2d, gt_l3, ignore_idxs, has_discrete_contact)
+        optiverts = []
+        for _ in range(self.num_iters):
+            fit.step()
+            optiverts.append(fit.vertices.clone())
+        body_pose, global_orient = fit.body_pose.detach().clone(), fit.global_orient.detach().clone()
+        with torch.no_grad():
+            out = self._forward(global_orient, body_pose, betas, return_full_pose=True)
+            conf = fit.args['joints_conf'].clone()
+            if has_gt_keypoints is not None:
+                conf[has_gt_keypoints, :25] = 0
+            reprojection_loss = body_fitting_loss(body_pose, betas, out.joints, camera_translation, camera_center,
+                                                  joints_2d, conf, self.pose_prior, focal_length=self.focal_length,
+                                                  output='reprojection')
+        pose = torch.cat([global_orient, body_pose], dim=-1)
+        return out.vertices.detach(), out.joints.detach(), pose, betas, camera_translation, reprojection_loss, optiverts
 
     def get_fitting_loss(self, pose, betas, cam_t, camera_center, keypoints_2d, has_gt_keypoints=None):
         """Reprojection loss [B,49] of given body and camera parameters (smplifydc.py:238-276).  As in

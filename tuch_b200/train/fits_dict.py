@@ -54,7 +54,11 @@ class FitsDict():
     def __getitem__(self, x):
         """ Retrieve dictionary entries: (pose[B,72], betas[B,10]) with rotation and flipping applied """
         dataset_name, ind, rot, is_flipped = x
-        params = torch.stack([self.fits_dict[ds][int(i)] for ds, i in zip(dataset_name, ind)]).to(self.device)
+        ind = torch.as_tensor(ind, dtype=torch.long).cpu()
+        params = torch.empty(len(dataset_name), 82)
+        for ds, pos in self._rows_by_dataset(dataset_name).items():       # one gather per dataset, not per sample
+            params[pos] = self.fits_dict[ds][ind[pos]].float()
+        params = params.to(self.device)
         pose = ops.fits_pose_transform(params[:, :72], rot, is_flipped, self._perm_dev, flip_first=False)
         return pose, params[:, 72:].clone()
 
@@ -66,9 +70,19 @@ class FitsDict():
         pose = ops.fits_pose_transform(pose.to(self.device), -rot.to(self.device, torch.float32), is_flipped,
                                        self._perm_dev, flip_first=True)
         params = torch.cat((pose, betas.to(self.device)), dim=-1).cpu()
-        for n, (ds, i) in enumerate(zip(dataset_name, ind)):
-            if update[n]:
-                self.fits_dict[ds][int(i)] = params[n]
+        ind = torch.as_tensor(ind, dtype=torch.long).cpu()
+        update = torch.as_tensor(update).cpu().bool()
+        for ds, pos in self._rows_by_dataset(dataset_name).items():
+            sel = pos[update[pos]]
+            if len(sel):
+                self.fits_dict[ds][ind[sel]] = params[sel].to(self.fits_dict[ds].dtype)
+
+    @staticmethod
+    def _rows_by_dataset(dataset_name):
+        rows = {}
+        for n, ds in enumerate(dataset_name):
+            rows.setdefault(ds, []).append(n)
+        return {ds: torch.tensor(r, dtype=torch.long) for ds, r in rows.items()}
 
     def flip_pose(self, pose, is_flipped):
         """flip SMPL pose parameters"""
