@@ -135,23 +135,62 @@ pack_groups_kernel(const int* __restrict__ vgroup_off, int T, int NG, float4* __
     }
 }
 
-// the 32 candidate rows of tile t against this lane's query: first minimum inside the tile (its rows are
-// in ascending original order), merged into (best, bi) with the lowest-original-index tie-break
-__device__ __forceinline__ void nearest_eval_tile(const float4* __restrict__ tv, const int* __restrict__ tid,
-                                                  uint32_t m, const float4& q, float& best, int& bi) {
-    float lbest = INFINITY;
+// fp32 expansion-form squared distance of contact.py:42, in the FMA order of nearest_kernel
+__device__ __forceinline__ float row_value(const float4& v, const float4& q) {
+    const float zz = fmaf(v.z, q.z, fmaf(v.y, q.y, v.x * q.x));
+    return fmaf(-2.f, zz, v.w + q.w);
+}
+
+// smallest unmasked value among the 32 candidate rows of a tile for this lane's query.  Only the VALUE is
+// tracked in the hot loop (one FMNMX per row instead of compare + two selects); the row that attains the final
+// minimum is looked up once per query at the end (tile_first_row).  FULL: every lane's mask word is all ones.
+template <bool FULL>
+__device__ __forceinline__ float tile_min(const float4* __restrict__ tv, uint32_t m, const float4& q) {
+    float lb = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        float p = row_value(__ldg(tv + k), q);
+        if (!FULL) p = ((m >> k) & 1u) ? p : INFINITY;
+        lb = fminf(lb, p);
+    }
+    return lb;
+}
+
+// original id of the first row of the tile (rows are in ascending original order) whose value equals target
+__device__ __forceinline__ int tile_first_row(const float4* __restrict__ tv, const int* __restrict__ tid, uint32_t m,
+                                              const float4& q, float target) {
     int lk = 0;
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        const float4 v = __ldg(tv + k);
-        const float zz = fmaf(v.z, q.z, fmaf(v.y, q.y, v.x * q.x));
-        float p = fmaf(-2.f, zz, v.w + q.w);
-        p = ((m >> k) & 1u) ? p : INFINITY;
-        if (p < lbest) { lbest = p; lk = k; }
+    for (int k = 31; k >= 0; --k) {
+        const float p = row_value(__ldg(tv + k), q);
+        if (((m >> k) & 1u) && p == target) lk = k;
     }
-    if (lbest < INFINITY) {
-        const int r = __ldg(tid + lk);
-        if (lbest < best || (lbest == best && r < bi)) { best = lbest; bi = r; }
+    return __ldg(tid + lk);
+}
+
+// running minimum of one query: value, the tile that attains it, and the attaining row's original id once it
+// had to be resolved (-1 = not yet).  Exact ties between two tiles go to the lowest original id, as in
+// nearest_kernel; they are rare, so both tiles are re-scanned on the spot.
+struct NearestState {
+    float best = INFINITY;
+    int btile = -1;
+    int bi = -1;
+};
+
+__device__ __forceinline__ void nearest_visit_tile(const float4* __restrict__ vb, const int* __restrict__ vtile,
+                                                   const uint32_t* __restrict__ mcol, size_t mstride, int t, uint32_t m,
+                                                   bool pad, const float4& q, NearestState& st) {
+    const bool full = __all_sync(0xffffffffu, m == 0xffffffffu || pad);
+    const float lb = full ? tile_min<true>(vb + t * 32, m, q) : tile_min<false>(vb + t * 32, m, q);
+    const bool tie = lb == st.best && lb < INFINITY && t != st.btile;
+    if (lb < st.best) { st.best = lb; st.btile = t; st.bi = -1; }
+    if (__any_sync(0xffffffffu, tie)) {
+        if (tie) {
+            if (st.bi < 0)
+                st.bi = tile_first_row(vb + st.btile * 32, vtile + st.btile * 32, mcol[(size_t)st.btile * mstride], q, st.best);
+            const int r = tile_first_row(vb + t * 32, vtile + t * 32, m, q, lb);
+            if (r < st.bi) { st.bi = r; st.btile = t; }
+        }
     }
 }
 
@@ -205,12 +244,12 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     }
     // evaluate those tiles first (a warp's queries are neighbours: few distinct ones): from here on
     // `best` is a tight bound for the sphere test
-    float best = INFINITY;
-    int bi = 0x7fffffff;
+    NearestState st;
+    const bool pad = oc < 0;
     unsigned todo = __ballot_sync(0xffffffffu, tstar >= 0);
     while (todo != 0u) {
         const int ts = __shfl_sync(0xffffffffu, tstar, __ffs(todo) - 1);
-        nearest_eval_tile(vb + ts * 32, vtile + ts * 32, mcol[(size_t)ts * mstride], q, best, bi);
+        nearest_visit_tile(vb, vtile, mcol, mstride, ts, mcol[(size_t)ts * mstride], pad, q, st);
         todo &= ~__ballot_sync(0xffffffffu, tstar == ts);
     }
     // pass 2: every tile whose sphere can still hold a row at or below the running minimum; groups of
@@ -221,7 +260,7 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
         const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
         // lanes without any unmasked row (padding slots, fully masked columns) never vote
-        const bool gneed = tstar >= 0 && (glo <= 0.f || glo * glo <= fmaf(best, 1.00001f, 4e-6f * (q.w + gs2.x)));
+        const bool gneed = tstar >= 0 && (glo <= 0.f || glo * glo <= fmaf(st.best, 1.00001f, 4e-6f * (q.w + gs2.x)));
         if (!__any_sync(0xffffffffu, gneed)) continue;
         const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
         for (int t = t0; t < t1; ++t) {
@@ -229,15 +268,25 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
             const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
             const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
             const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
-            const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(best, 1.00001f, 4e-6f * (q.w + s2.x)));
+            const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(st.best, 1.00001f, 4e-6f * (q.w + s2.x)));
             if (!__any_sync(0xffffffffu, need)) continue;
-            nearest_eval_tile(vb + t * 32, vtile + t * 32, m, q, best, bi);
+            if (__any_sync(0xffffffffu, tstar == t)) continue;          // evaluated for the whole warp above
+            nearest_visit_tile(vb, vtile, mcol, mstride, t, m, pad, q, st);
         }
     }
+    // the attaining rows: one scan per distinct attaining tile of the warp (its queries are neighbours: a few)
+    todo = __ballot_sync(0xffffffffu, st.bi < 0 && st.btile >= 0);
+    while (todo != 0u) {
+        const int ts = __shfl_sync(0xffffffffu, st.btile, __ffs(todo) - 1);
+        const bool mine = st.bi < 0 && st.btile == ts;
+        const int r = tile_first_row(vb + ts * 32, vtile + ts * 32, mcol[(size_t)ts * mstride], q, st.best);
+        if (mine) st.bi = r;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
     if (oc >= 0) {
-        const bool none = bi == 0x7fffffff;                            // fully masked column
-        argmin_out[(size_t)b * V + oc] = none ? 0 : bi;
-        min_out[(size_t)b * V + oc] = none ? INFINITY : best;
+        const bool none = st.btile < 0;                                // fully masked column
+        argmin_out[(size_t)b * V + oc] = none ? 0 : st.bi;
+        min_out[(size_t)b * V + oc] = none ? INFINITY : st.best;
     }
 }
 
