@@ -52,3 +52,9 @@ print('selected HD points per body', n.tolist()[:8], 'interior frac %.3f' % floa
 print('HD exterior flag mismatches fast vs exact: %d of %d; loss rel diff %.2e' % (mism, int(n.sum()), float(((le - lf).abs() / le.abs().clamp_min(1e-9)).max())))
 for k in ('winding_kernel_points', 'winding_refine_kernel'):
     print(' ', k, ops.kernel_time(k))
+
+# device time of every timed kernel group over one more HD call
+ops.kernel_timing(enable=True, reset=True)
+run(True); torch.cuda.synchronize()
+for k, v in sorted(ops.kernel_times().items(), key=lambda kv: -kv[1][0]):
+    print('  %-28s %8.3f ms  (%d launches)' % (k, v[0], v[1]))

@@ -175,6 +175,7 @@ __global__ void hd_fold_kernel(const long long* __restrict__ g_fix, long long n,
 int launch_hd_select(const float* min_sq, const uint8_t* exterior, const uint8_t* body_active, const int* faces,
                      int B, int V, int N, const int* hd_face, float thres_sq, int* idx, int* counts, cudaStream_t st) {
     if (B == 0) return 0;
+    KernelTimer timer("hd_select_kernel", st);
     hd_select_kernel<<<B, HS_THREADS, 0, st>>>(min_sq, exterior, body_active, faces, V, N, hd_face, thres_sq, idx, counts);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
@@ -184,6 +185,7 @@ int launch_hd_gather(const float* verts, int B, int V, int N, const int* idx, co
                      const int* cols, const float* vals, const int* hd_face, const int* faces, float4* hd4,
                      float* hd, float* off, int* proxy, cudaStream_t st) {
     if (B == 0 || N == 0) return 0;
+    KernelTimer timer("hd_gather_kernel", st);
     dim3 grid(cdiv(N, 256), B);
     hd_gather_kernel<<<grid, 256, 0, st>>>(verts, V, N, idx, counts, row_off, cols, vals, hd_face, faces, hd4, hd, off, proxy);
     TUCH_LAUNCH_CHECK(); count_launch();
@@ -193,6 +195,7 @@ int launch_hd_gather(const float* verts, int B, int V, int N, const int* idx, co
 int launch_hd_nearest(const float4* hd4, const int* proxy, const int* counts, int B, int N, const uint32_t* maskT,
                       int Vq, int* argmin, cudaStream_t st) {
     if (B == 0 || N == 0) return 0;
+    KernelTimer timer("hd_nearest_kernel", st);
     dim3 grid(cdiv(N, HN_THREADS), B);
     hd_nearest_kernel<<<grid, HN_THREADS, 0, st>>>(hd4, proxy, counts, N, maskT, Vq, argmin);
     TUCH_LAUNCH_CHECK(); count_launch();
@@ -202,6 +205,7 @@ int launch_hd_nearest(const float4* hd4, const int* proxy, const int* counts, in
 int launch_hd_scatter(const float* g_hd, int B, int V, int N, const int* idx, const int* counts, const int* row_off,
                       const int* cols, const float* vals, float* g_verts, cudaStream_t st) {
     if (B == 0 || N == 0) return 0;
+    KernelTimer timer("hd_scatter_kernels", st);
     void* p = nullptr;
     const size_t n = 3 * (size_t)B * V;
     if (int rc = arena_get(st, sizeof(long long) * n, &p, 3)) return rc;
