@@ -591,7 +591,8 @@ static int run_segments(const tuch_topology* t, const float* verts, int B, Scrat
 }
 
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
-                       float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st) {
+                       float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
+                       PackedClusters* packed_out) {
     TUCH_REQUIRE(t != nullptr, "tuch_contact_query: null topology");
     TUCH_REQUIRE(B >= 0, "tuch_contact_query: negative batch");
     TUCH_REQUIRE(B <= 65535, "tuch_contact_query: at most 65535 bodies per call (the batch is a grid dimension), got %d", B);
@@ -657,6 +658,10 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                          sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
             j.max_top_leaves = t->max_top_leaves;
             if (int rc = launch_winding_clusters(j, st)) return rc;
+            if (packed_out != nullptr) {
+                packed_out->ctri = strip4; packed_out->nodes = info;
+                cluster_pack_betas(j, &packed_out->beta_leaf, &packed_out->beta_group);
+            }
         } else {
             if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
             StripJob j{strip4, info, verts, (long long)V * 3, sc.get<float>(h_par), w, (long long)V, nullptr, B, V, Lp, S};

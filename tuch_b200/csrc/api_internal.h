@@ -81,8 +81,18 @@ int launch_exterior_init(const float* winding, int B, int V, uint8_t* exterior, 
 int launch_segment_apply(const float* seg_winding, const int* seg_vidx, int n_sv, int B, int V,
                          uint8_t* exterior, uint8_t* seg_ext_out, const uint8_t* body_active, cudaStream_t st);
 
+// the face hierarchy of this batch as packed by the hierarchical winding path (leaf triangles + node records);
+// lives in the stream's shared scratch arena: valid until the next call that commits that arena
+struct PackedClusters {
+    const float4* ctri = nullptr;
+    const float4* nodes = nullptr;
+    float beta_leaf = 0.f, beta_group = 0.f;      // opening radii baked into the node records
+};
+
 // vert4_out: optional caller-owned [B][Vp] float4 buffer that receives the packed vertices
+// packed_out: optional, receives the packed hierarchy when the hierarchical winding path ran (else stays null)
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
-                       float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st);
+                       float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
+                       PackedClusters* packed_out = nullptr);
 
 }  // namespace tuch

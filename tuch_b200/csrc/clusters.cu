@@ -558,7 +558,9 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
                        const float4* __restrict__ ctri, const float4* __restrict__ nodes,
                        const int* __restrict__ mid_off, const int* __restrict__ top_off,
                        float* __restrict__ partial, int Q, int T, int K, int NM, int NT, int tops_per_split, int S,
-                       const int* __restrict__ q_counts, const uint8_t* __restrict__ body_active) {
+                       const int* __restrict__ q_counts, const uint8_t* __restrict__ body_active, float open_leaf,
+                       float open_group) {
+    // open_leaf / open_group scale the squared opening radii baked into the node records (1 = as packed)
     __shared__ float s_acc[WC_WARPS][32 * (WC_LEAF + 1)];
     const int b = blockIdx.z, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -592,7 +594,7 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
         const float4 tc = __ldg(trec);
         const float tx = tc.x - px, ty = tc.y - py, tz = tc.z - pz;
         const float td2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-        if (!__any_sync(0xffffffffu, td2 < tc.w)) {
+        if (!__any_sync(0xffffffffu, td2 < tc.w * open_group)) {
             far += node_far_field(trec, tx, ty, tz, td2);
             continue;
         }
@@ -602,7 +604,7 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
             const float4 mc = __ldg(mrec);
             const float mx = mc.x - px, my = mc.y - py, mz = mc.z - pz;
             const float md2 = fmaf(mz, mz, fmaf(my, my, mx * mx));
-            if (!__any_sync(0xffffffffu, md2 < mc.w)) {
+            if (!__any_sync(0xffffffffu, md2 < mc.w * open_group)) {
                 far += node_far_field(mrec, mx, my, mz, md2);
                 continue;
             }
@@ -612,7 +614,7 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
                 const float4 lc = __ldg(lrec);
                 const float lx = lc.x - px, ly = lc.y - py, lz = lc.z - pz;
                 const float ld2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
-                const bool near = ld2 < lc.w;
+                const bool near = ld2 < lc.w * open_leaf;
                 unsigned nm = __ballot_sync(0xffffffffu, near);
                 if (nm != 0xffffffffu) {
                     const float v = node_far_field(lrec, lx, ly, lz, ld2);
@@ -712,14 +714,20 @@ int cluster_splits(int B, int T, int NT, int sm_count) {
     return cdiv(NT, per);
 }
 
+void cluster_pack_betas(const ClusterJob& j, float* beta_leaf, float* beta_group) {
+    // development knobs (scripts/sweep_beta.sh sweeps them); the shipped values are the constants
+    static const float env_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : 0.f;
+    static const float env_group = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : 0.f;
+    *beta_leaf = env_leaf > 0.f ? env_leaf : j.beta_leaf;
+    *beta_group = env_group > 0.f ? env_group : j.beta_group;
+}
+
 int launch_cluster_pack(const ClusterJob& j, cudaStream_t st) {
     if (j.B == 0) return 0;
     KernelTimer timer("cluster_pack_kernel", st);
     dim3 grid(cdiv(j.NT + j.NM + j.K, 4), j.B);
-    // development knobs (scripts/sweep_beta.sh sweeps them); the shipped values are the constants
-    static const float env_leaf = getenv("TUCH_WC_BETA") ? (float)atof(getenv("TUCH_WC_BETA")) : 0.f;
-    static const float env_group = getenv("TUCH_WC_BETA_SUPER") ? (float)atof(getenv("TUCH_WC_BETA_SUPER")) : 0.f;
-    const float beta_leaf = env_leaf > 0.f ? env_leaf : j.beta_leaf, beta_group = env_group > 0.f ? env_group : j.beta_group;
+    float beta_leaf, beta_group;
+    cluster_pack_betas(j, &beta_leaf, &beta_group);
     const size_t smem = (size_t)j.max_top_leaves * WC_LEAF * 10 * sizeof(float);
     if (j.max_top_leaves > 0 && smem <= 200 * 1024) {
         static size_t attr_smem = 0;
@@ -745,13 +753,16 @@ int launch_cluster_query(const ClusterJob& j, cudaStream_t st) {
     const int T = j.vtile != nullptr ? j.T : cdiv(Q, 32);
     if (j.B == 0 || Q == 0) return 0;
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
+    const float rl = j.packed_beta_leaf > 0.f ? j.beta_leaf / j.packed_beta_leaf : 1.f;
+    const float rg = j.packed_beta_group > 0.f ? j.beta_group / j.packed_beta_group : 1.f;
+    const float open_leaf = rl * rl, open_group = rg * rg;
     {
         const int per = cdiv(j.NT, j.S);
         dim3 grid(cdiv(T, WC_WARPS), j.S, j.B);
         KernelTimer timer(j.vtile != nullptr ? "winding_kernel" : "winding_kernel_points", st);
         winding_cluster_kernel<<<grid, WC_WARPS * 32, 0, st>>>(points, j.vtile, j.ctri, j.nodes, j.mid_off, j.top_off,
                                                                j.partial, Q, T, j.K, j.NM, j.NT, per, j.S, j.q_counts,
-                                                               j.body_active);
+                                                               j.body_active, open_leaf, open_group);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     {

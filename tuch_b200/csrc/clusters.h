@@ -55,6 +55,9 @@ struct ClusterJob {
     // 1.5).  Off-surface queries see near-integer winding numbers, i.e. interior points sit at 1.0, only
     // 0.01 above the threshold: they need a tighter far field and a narrower band (WC_*_POINTS).
     float beta_leaf = WC_BETA, beta_group = WC_BETA_GROUP, margin = WC_MARGIN;
+    // launch_cluster_query on node records another job packed (the opening radius is baked into them): the radii
+    // THAT job packed with (cluster_pack_betas); 0 = the records are this job's own
+    float packed_beta_leaf = 0.f, packed_beta_group = 0.f;
     int max_top_leaves = 0;          // largest top group in leaves (shared-memory staging of the pack kernel)
 };
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
@@ -67,6 +70,7 @@ int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32
 
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
+void cluster_pack_betas(const ClusterJob& job, float* beta_leaf, float* beta_group);   // the radii it bakes in
 int launch_cluster_query(const ClusterJob& job, cudaStream_t st);     // winding kernel + finalize + exact refine
 int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);  // both
 

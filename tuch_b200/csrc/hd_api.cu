@@ -68,10 +68,9 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     // (the default), else the all-faces strip kernel
     const bool fast = use_hd && t->winding_mode == TUCH_WINDING_FAST && t->has_clusters;
     const int S = !use_hd ? 1 : fast ? cluster_splits(B, cdiv(N, 32), t->NT, sm_count()) : strip_splits(B, N, Lp, sm_count());
-    const size_t h_tri = sc.plan(!use_hd ? 0 : fast ? sizeof(float4) * 3 * (size_t)B * t->K * WC_LEAF
-                                                    : sizeof(float4) * 2 * (size_t)B * Lp);
-    const size_t h_info = sc.plan(!use_hd ? 0 : fast ? sizeof(float4) * WC_NODE_F4 * (size_t)B * (t->NT + t->NM + t->K)
-                                                     : sizeof(float4) * (size_t)B * (Lp / WS_TILE));
+    // hierarchical: the point query re-uses the hierarchy the vertex query below packs for this batch
+    const size_t h_tri = sc.plan(!use_hd || fast ? 0 : sizeof(float4) * 2 * (size_t)B * Lp);
+    const size_t h_info = sc.plan(!use_hd || fast ? 0 : sizeof(float4) * (size_t)B * (Lp / WS_TILE));
     const size_t h_par = sc.plan(use_hd ? sizeof(float) * (size_t)B * S * N : 0);
     const size_t h_ref = sc.plan(fast ? sizeof(int) * (BN + 1) : 0);
     if (int rc = sc.commit_slot(st, 1)) return rc;
@@ -80,7 +79,8 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     uint8_t* ex = sc.get<uint8_t>(h_ex);
 
     // loss.py:251-270 -- exterior flags (winding + segment whitelist) and the masked nearest vertex
-    if (int rc = contact_query_impl(t, verts, B, 1, am, mn, nullptr, ex, nullptr, st)) return rc;
+    PackedClusters packed;
+    if (int rc = contact_query_impl(t, verts, B, 1, am, mn, nullptr, ex, nullptr, st, &packed)) return rc;
 
     if (!use_hd) {                                                    // loss.py:303-315
         return launch_contact_loss(verts, am, ex, valid, nullptr, B, V, 0.f, PULL_ALL, REDUCE_SUM, weight, g_loss,
@@ -100,15 +100,20 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
                                   t->d_faces, hd4, hd, off, proxy, st)) return rc;
     if (int rc = launch_hd_nearest(hd4, proxy, cnt, B, N, t->d_maskT, t->Vq, ham, st)) return rc;
     // loss.py:297 -- inside test of the offset HD points against the full mesh
-    float4* strip4 = sc.get<float4>(h_tri);
-    float4* info = sc.get<float4>(h_info);
     if (fast) {
-        ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, nullptr, strip4, info,
+        // nothing between the vertex query and here commits the shared arena, so its packed hierarchy is intact
+        TUCH_REQUIRE(packed.ctri != nullptr && packed.nodes != nullptr,
+                     "tuch_regressor_contact_loss: the vertex query did not leave a packed face hierarchy");
+        ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, nullptr,
+                     const_cast<float4*>(packed.ctri), const_cast<float4*>(packed.nodes),
                      sc.get<float>(h_par), hw, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
         j.points = off; j.Q = N; j.q_counts = cnt; j.body_active = valid; j.max_top_leaves = t->max_top_leaves;
         j.beta_leaf = WC_BETA_POINTS; j.beta_group = WC_BETA_GROUP_POINTS; j.margin = WC_MARGIN_POINTS;
-        if (int rc = launch_winding_clusters(j, st)) return rc;
+        j.packed_beta_leaf = packed.beta_leaf; j.packed_beta_group = packed.beta_group;
+        if (int rc = launch_cluster_query(j, st)) return rc;
     } else {
+        float4* strip4 = sc.get<float4>(h_tri);
+        float4* info = sc.get<float4>(h_info);
         if (int rc = launch_pack_strips(verts, B, V, t->d_faces, t->d_strip_vid, t->d_strip_fid, Lp, strip4, info, st)) return rc;
         StripJob j{strip4, info, off, (long long)N * 3, sc.get<float>(h_par), hw, (long long)N, valid, B, N, Lp, S};
         j.q_counts = cnt;
