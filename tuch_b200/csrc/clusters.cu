@@ -423,6 +423,19 @@ struct NodeMoments {
         tzzx += 2.f * nz * sxz + nx * szz; tzzy += 2.f * nz * syz + ny * szz;
         txyz += 2.f * (nx * syz + ny * sxz + nz * sxy);
     }
+    static constexpr int N_SUMS = 23;                            // every field but r2
+    __device__ __forceinline__ void store_sums(float* p) const {
+        const float v[N_SUMS] = {m0x, m0y, m0z, tr, qxx, qyy, qzz, qxy, qxz, qyz, uvx, uvy, uvz,
+                                 txxx, tyyy, tzzz, txxy, txxz, tyyx, tyyz, tzzx, tzzy, txyz};
+#pragma unroll
+        for (int k = 0; k < N_SUMS; ++k) p[k] = v[k];
+    }
+    __device__ __forceinline__ void add_sums(const float* p) {
+        m0x += p[0]; m0y += p[1]; m0z += p[2]; tr += p[3]; qxx += p[4]; qyy += p[5]; qzz += p[6]; qxy += p[7];
+        qxz += p[8]; qyz += p[9]; uvx += p[10]; uvy += p[11]; uvz += p[12]; txxx += p[13]; tyyy += p[14];
+        tzzz += p[15]; txxy += p[16]; txxz += p[17]; tyyx += p[18]; tyyz += p[19]; tzzx += p[20]; tzzy += p[21];
+        txyz += p[22];
+    }
     template <int W>
     __device__ __forceinline__ void reduce() {
         r2 = group_max<W>(r2);
@@ -517,11 +530,64 @@ cluster_pack_top_kernel(const float* __restrict__ verts, int V, const int* __res
         mo.template reduce<W>();
         if (live && sub == 0) mo.write(nodes + ((size_t)b * (NT + NM + K) + node) * WC_NODE_F4, px, py, pz, beta);
     };
-    for (int n = warp; n < 1 + nm; n += 8) {                     // the top and its mids: full warps
-        if (n == 0) reduce_node(std::integral_constant<int, 32>(), 0, n_slots, lane, t, beta_group, true);
-        else reduce_node(std::integral_constant<int, 32>(), (mid_off[m0 + n - 1] - l0) * WC_LEAF,
-                         (mid_off[m0 + n] - l0) * WC_LEAF, lane, NT + m0 + n - 1, beta_group, true);
+    // the top node spans every slot of the CTA (up to 64 leaves): all eight warps take a share -- one warp alone
+    // would be the critical path of the whole pack -- and their partial sums meet in shared memory in warp order
+    {
+        __shared__ float s_part[8][NodeMoments::N_SUMS + 1];
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // area, area * centroid, centroid, count
+        for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+            if (s_ok[i] == 0.f) continue;
+            const float* c = s_c + (size_t)i * 9;
+            const float e1x = c[3] - c[0], e1y = c[4] - c[1], e1z = c[5] - c[2];
+            const float e2x = c[6] - c[0], e2y = c[7] - c[1], e2z = c[8] - c[2];
+            const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+            const float area = 0.5f * sqrtf(nx * nx + ny * ny + nz * nz);
+            const float gx = (c[0] + c[3] + c[6]) * (1.f / 3.f), gy = (c[1] + c[4] + c[7]) * (1.f / 3.f),
+                        gz = (c[2] + c[5] + c[8]) * (1.f / 3.f);
+            acc[0] += area; acc[1] += area * gx; acc[2] += area * gy; acc[3] += area * gz;
+            acc[4] += gx; acc[5] += gy; acc[6] += gz; acc[7] += 1.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc[k] = group_sum<32>(acc[k]);
+            if (lane == 0) s_part[warp][k] = acc[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = 0.f;
+            for (int w = 0; w < 8; ++w) v += s_part[w][k];
+            acc[k] = v;
+        }
+        __syncthreads();
+        const bool weighted = acc[0] > 1e-30f;
+        const float inv = weighted ? 1.f / acc[0] : 1.f / fmaxf(acc[7], 1.f);
+        const float px = (weighted ? acc[1] : acc[4]) * inv, py = (weighted ? acc[2] : acc[5]) * inv,
+                    pz = (weighted ? acc[3] : acc[6]) * inv;
+        NodeMoments mo;
+        for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+            if (s_ok[i] == 0.f) continue;
+            const float* c = s_c + (size_t)i * 9;
+            mo.add(c[0] - px, c[1] - py, c[2] - pz, c[3] - px, c[4] - py, c[5] - pz, c[6] - px, c[7] - py, c[8] - pz);
+        }
+        mo.template reduce<32>();
+        if (lane == 0) {
+            mo.store_sums(s_part[warp]);
+            s_part[warp][NodeMoments::N_SUMS] = mo.r2;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            NodeMoments top;
+            for (int w = 0; w < 8; ++w) {
+                top.add_sums(s_part[w]);
+                top.r2 = fmaxf(top.r2, s_part[w][NodeMoments::N_SUMS]);
+            }
+            top.write(nodes + ((size_t)b * (NT + NM + K) + t) * WC_NODE_F4, px, py, pz, beta_group);
+        }
     }
+    for (int n = warp; n < nm; n += 8)                           // its mids: one full warp each
+        reduce_node(std::integral_constant<int, 32>(), (mid_off[m0 + n] - l0) * WC_LEAF,
+                    (mid_off[m0 + n + 1] - l0) * WC_LEAF, lane, NT + m0 + n, beta_group, true);
     for (int pair = warp; 2 * pair < nl; pair += 8) {            // leaves: one per half-warp
         const int j = 2 * pair + (lane >> 4);
         reduce_node(std::integral_constant<int, 16>(), j * WC_LEAF, (j + 1) * WC_LEAF, lane & 15, NT + NM + l0 + j, beta_leaf,
