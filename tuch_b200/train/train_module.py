@@ -106,125 +106,121 @@ class TUCH(ContactFromVertsMixin):
         return {b: [torch.where(close[b])[0], q['argmin'][b][close[b]].long()] for b in range(verts.shape[0])}
 
     # ------------------------------------------------------------------ train_module.py:112-336
+    # The step is written as five stages over a small per-step record; the statements they replace are cited.
+    class _Fit:
+        """The best-known body of every sample in the batch (the `opt_*` values of the reference)."""
+        __slots__ = ('pose', 'betas', 'vertices', 'joints', 'cam_t', 'joint_loss', 'contact')
+
+    def _body(self, pose, betas):
+        out = self.smpl(betas=betas, body_pose=pose[:, 3:], global_orient=pose[:, :3])
+        return out.vertices, out.joints
+
+    def _camera_from_weak_perspective(self, cam):
+        """(s, tx, ty) -> (tx, ty, 2 f / (res s))                                      :193-196, :213-216"""
+        depth = 2 * self.focal_length / (self.options.img_res * cam[:, 0] + 1e-9)
+        return torch.stack([cam[:, 1], cam[:, 2], depth], dim=-1)
+
+    def _stored_fits(self, key, kp_px, has_gt_kp, center):
+        """Fits-store lookup, their bodies, region distances, camera and reprojection score   :156-183"""
+        fit = self._Fit()
+        pose, betas = self.fits_dict[key]
+        fit.pose, fit.betas = pose.to(self.device), betas.to(self.device)
+        fit.vertices, fit.joints = self._body(fit.pose, fit.betas)
+        fit.contact = self.contact_from_verts(fit.vertices, mode='regions')
+        fit.cam_t = estimate_translation(fit.joints, kp_px, focal_length=self.focal_length,
+                                         img_size=self.options.img_res, has_2d_kp_anno=has_gt_kp)
+        fit.joint_loss = self.smplify.get_fitting_loss(fit.pose, fit.betas, fit.cam_t, center, kp_px,
+                                                       has_gt_kp).mean(dim=-1)
+        return fit
+
+    def _fit_in_the_loop(self, fit, key, start, kp_px, center, labels, flags):
+        """SMPLify-DC from the network's prediction; samples whose new fit scores at least as well -- and, with
+        contact labels, brings the labelled regions at least as close -- replace the stored one      :236-284"""
+        o = self.options
+        has_dc, has_gt_kp, has_smpl = flags
+        verts, joints, pose, betas, cam_t, joint_loss, optiverts = self.smplify(
+            *start, center, kp_px, use_contact=o.use_contact_in_the_loop, contactlist=self.contactlists,
+            gt_contact=[labels, None], ignore_idxs=has_smpl, has_discrete_contact=has_dc,
+            has_gt_keypoints=has_gt_kp, contact_loss_weight=o.contact_in_the_loop_loss_weight,
+            contact_loss_return='sum', segments=self.criterion_cospin.segments)
+        joint_loss = joint_loss.mean(dim=-1)
+        better = joint_loss <= fit.joint_loss
+        contact = self.contact_from_verts(verts, mode='regions')
+        closer = ((labels * contact) <= (labels * fit.contact)).sum(1) > 0
+        if o.use_contact_in_the_loop:
+            better[has_dc] = (closer * better)[has_dc]
+        for name, new in (('joint_loss', joint_loss), ('vertices', verts), ('contact', contact), ('joints', joints),
+                          ('pose', pose), ('betas', betas), ('cam_t', cam_t)):
+            getattr(fit, name)[better] = new[better]
+        self.fits_dict[key + (better.cpu(),)] = (fit.pose.cpu(), fit.betas.cpu())
+        return optiverts
+
     def forward_train_step(self, input_batch):
         o = self.options
-        camera_center = torch.zeros(o.batch_size, 2, device=self.device)
         self.model.train()
-
         images = input_batch['img']
-        batch_size = images.shape[0]
-        indices = input_batch['sample_index']
-        is_flipped = input_batch['is_flipped']
-        rot_angle = input_batch['rot_angle']
-        dataset_name = input_batch['dataset_name']
+        n = images.shape[0]
+        key = (input_batch['dataset_name'], input_batch['sample_index'].cpu(), input_batch['rot_angle'].cpu(),
+               input_batch['is_flipped'].cpu())
+        has_pose_3d, has_dc, has_gt_kp = (input_batch[k].bool() for k in ('has_pose_3d', 'has_disc_contact',
+                                                                          'has_gt_kpts'))
+        has_smpl = input_batch['has_smpl'].bool() | input_batch['has_pgt_smpl'].bool()
+        labels = input_batch['contact_vec']
+        gt_pose, gt_betas = input_batch['pose'], input_batch['betas']
 
-        has_pose_3d = input_batch['has_pose_3d'].bool()
-        has_disc_contact = input_batch['has_disc_contact'].bool()
-        has_2d_keypoints_gtanno = input_batch['has_gt_kpts'].bool()
-        has_smpl_ = input_batch['has_smpl'].bool() | input_batch['has_pgt_smpl'].bool()
+        # ---- ground truth (or mimicked) bodies, keypoints in pixels                                    :142-151
+        gt_vertices, gt_joints_model = self._body(gt_pose, gt_betas)
+        kp_px = input_batch['keypoints'].clone()
+        kp_px[:, :, :-1] = 0.5 * o.img_res * (kp_px[:, :, :-1] + 1)
+        center = 0.5 * o.img_res * torch.ones(n, 2, device=self.device)
 
-        gt_keypoints_2d = input_batch['keypoints']
-        gt_joints = input_batch['pose_3d']
-        gt_pose = input_batch['pose']
-        gt_betas = input_batch['betas']
-        gt_disc_contact = input_batch['contact_vec']
-        gt_out = self.smpl(betas=gt_betas, body_pose=gt_pose[:, 3:], global_orient=gt_pose[:, :3])
-        gt_model_joints, gt_verts = gt_out.joints, gt_out.vertices
+        # ---- the stored fits; the camera of the ground-truth body is estimated before get_fitting_loss
+        #      zeroes the ignored confidences in kp_px (the order of :171-183)
+        gt_cam_t = estimate_translation(gt_joints_model, kp_px, focal_length=self.focal_length, img_size=o.img_res,
+                                        has_2d_kp_anno=has_gt_kp)
+        fit = self._stored_fits(key, kp_px, has_gt_kp, center)
 
-        # keypoints from [-1,1] to pixels                                                    :148-151
-        gt_keypoints_2d_orig = gt_keypoints_2d.clone()
-        gt_keypoints_2d_orig[:, :, :-1] = 0.5 * o.img_res * (gt_keypoints_2d_orig[:, :, :-1] + 1)
-
-        # current best fits                                                                  :156-166
-        opt_pose, opt_betas = self.fits_dict[(dataset_name, indices.cpu(), rot_angle.cpu(), is_flipped.cpu())]
-        opt_pose, opt_betas = opt_pose.to(self.device), opt_betas.to(self.device)
-        opt_output = self.smpl(betas=opt_betas, body_pose=opt_pose[:, 3:], global_orient=opt_pose[:, :3])
-        opt_vertices, opt_joints = opt_output.vertices, opt_output.joints
-        opt_contact_l3 = self.contact_from_verts(opt_vertices, mode='regions')
-
-        # camera translations (one kernel per call, no host round trip)                      :171-183
-        gt_cam_t = estimate_translation(gt_model_joints, gt_keypoints_2d_orig, focal_length=self.focal_length,
-                                        img_size=o.img_res, has_2d_kp_anno=has_2d_keypoints_gtanno)
-        opt_cam_t = estimate_translation(opt_joints, gt_keypoints_2d_orig, focal_length=self.focal_length,
-                                         img_size=o.img_res, has_2d_kp_anno=has_2d_keypoints_gtanno)
-        center = 0.5 * o.img_res * torch.ones(batch_size, 2, device=self.device)
-        opt_joint_loss = self.smplify.get_fitting_loss(opt_pose, opt_betas, opt_cam_t, center, gt_keypoints_2d_orig,
-                                                       has_2d_keypoints_gtanno).mean(dim=-1)
-
-        # SPIN fits, for logging only                                                        :186-196
+        # ---- SPIN's own prediction, for logging only                                                   :186-196
         spin_vertices = spin_cam_t = None
         if self.modelspin is not None:
             with torch.no_grad():
                 rot_s, betas_s, cam_s = self.modelspin(images)
                 spin_vertices = self.smpl(betas=betas_s, body_pose=rot_s[:, 1:], global_orient=rot_s[:, 0].unsqueeze(1),
                                           pose2rot=False).vertices.clone()
-                spin_cam_t = torch.stack([cam_s[:, 1], cam_s[:, 2],
-                                          2 * self.focal_length / (o.img_res * cam_s[:, 0] + 1e-9)], dim=-1)
+                spin_cam_t = self._camera_from_weak_perspective(cam_s)
 
-        # regressor                                                                          :202-229
+        # ---- the regressor                                                                             :202-229
         pred_rotmat, pred_betas, pred_camera = self.model(images)
-        pred_output = self.smpl(betas=pred_betas, body_pose=pred_rotmat[:, 1:],
-                                global_orient=pred_rotmat[:, 0].unsqueeze(1), pose2rot=False)
-        pred_vertices, pred_joints = pred_output.vertices, pred_output.joints
-        pred_pose = rotation_matrix_to_angle_axis(pred_rotmat.detach().reshape(-1, 3, 3)).contiguous() \
-            .view(batch_size, -1)
+        pred = self.smpl(betas=pred_betas, body_pose=pred_rotmat[:, 1:], global_orient=pred_rotmat[:, 0].unsqueeze(1),
+                         pose2rot=False)
+        pred_pose = rotation_matrix_to_angle_axis(pred_rotmat.detach().reshape(-1, 3, 3)).contiguous().view(n, -1)
         pred_pose[torch.isnan(pred_pose)] = 0.0
-        pred_cam_t = torch.stack([pred_camera[:, 1], pred_camera[:, 2],
-                                  2 * self.focal_length / (o.img_res * pred_camera[:, 0] + 1e-9)], dim=-1)
-        pred_keypoints_2d = perspective_projection(
-            pred_joints, rotation=torch.eye(3, device=self.device).unsqueeze(0).expand(batch_size, -1, -1),
-            translation=pred_cam_t, focal_length=self.focal_length, camera_center=camera_center)
-        pred_keypoints_2d = pred_keypoints_2d / (o.img_res / 2.)
+        pred_cam_t = self._camera_from_weak_perspective(pred_camera)
+        pred_kp = perspective_projection(pred.joints, rotation=torch.eye(3, device=self.device).expand(n, -1, -1),
+                                         translation=pred_cam_t, focal_length=self.focal_length,
+                                         camera_center=torch.zeros(o.batch_size, 2, device=self.device))
+        pred_kp = pred_kp / (o.img_res / 2.)
 
-        # SMPLify-DC in the loop, starting from the prediction                              :236-284
-        smplifyoptiverts = None
+        # ---- optimisation in the loop                                                                  :236-284
+        optiverts = None
         if o.run_smplify:
-            new_opt_vertices, new_opt_joints, new_opt_pose, new_opt_betas, new_opt_cam_t, new_opt_joint_loss, \
-                smplifyoptiverts = self.smplify(
-                    pred_pose.detach(), pred_betas.detach(), pred_cam_t.detach(), center, gt_keypoints_2d_orig,
-                    use_contact=o.use_contact_in_the_loop, contactlist=self.contactlists,
-                    gt_contact=[gt_disc_contact, None], ignore_idxs=has_smpl_,
-                    has_discrete_contact=has_disc_contact, has_gt_keypoints=has_2d_keypoints_gtanno,
-                    contact_loss_weight=o.contact_in_the_loop_loss_weight, contact_loss_return='sum',
-                    segments=self.criterion_cospin.segments)
-            new_opt_joint_loss = new_opt_joint_loss.mean(dim=-1)
-            update = (new_opt_joint_loss <= opt_joint_loss)
-            # with discrete contact labels the new fit must also bring the labelled regions at least as close
-            new_opt_contact_l3 = self.contact_from_verts(new_opt_vertices, mode='regions')
-            update_contact_l3 = ((gt_disc_contact * new_opt_contact_l3) <= (gt_disc_contact * opt_contact_l3)).sum(1) > 0
-            if o.use_contact_in_the_loop:
-                update[has_disc_contact] = (update_contact_l3 * update)[has_disc_contact]
+            optiverts = self._fit_in_the_loop(fit, key, (pred_pose.detach(), pred_betas.detach(), pred_cam_t.detach()),
+                                              kp_px, center, labels, (has_dc, has_gt_kp, has_smpl))
 
-            opt_joint_loss[update] = new_opt_joint_loss[update]
-            opt_vertices[update, :] = new_opt_vertices[update, :]
-            opt_contact_l3[update, :] = new_opt_contact_l3[update, :]
-            opt_joints[update, :] = new_opt_joints[update, :]
-            opt_pose[update, :] = new_opt_pose[update, :]
-            opt_betas[update, :] = new_opt_betas[update, :]
-            opt_cam_t[update, :] = new_opt_cam_t[update, :]
-            self.fits_dict[(dataset_name, indices.cpu(), rot_angle.cpu(), is_flipped.cpu(), update.cpu())] = \
-                (opt_pose.cpu(), opt_betas.cpu())
+        # ---- ground truth wins where it exists; which fits may supervise the regressor                 :290-301
+        for name, gt in (('cam_t', gt_cam_t), ('joints', gt_joints_model), ('pose', gt_pose), ('betas', gt_betas),
+                         ('vertices', gt_vertices)):
+            getattr(fit, name)[has_smpl] = gt[has_smpl]
+        good_fit = (fit.joint_loss < o.smplify_threshold).to(self.device)
+        supervise = has_smpl | good_fit
 
-        # ground-truth parameters win where they exist                                       :290-301
-        opt_cam_t[has_smpl_, :] = gt_cam_t[has_smpl_, :]
-        opt_joints[has_smpl_, :, :] = gt_model_joints[has_smpl_, :, :]
-        opt_pose[has_smpl_, :] = gt_pose[has_smpl_, :]
-        opt_betas[has_smpl_, :] = gt_betas[has_smpl_, :]
-        opt_vertices[has_smpl_, :] = gt_verts[has_smpl_, :]
-        valid_fit = (opt_joint_loss < o.smplify_threshold).to(self.device)
-        valid_fit_pose = has_smpl_ | valid_fit
-        valid_fit_shape = has_smpl_ | valid_fit
-
-        loss, loss_dict = self.criterion_cospin(pred_rotmat, pred_betas, opt_pose, opt_betas, pred_keypoints_2d,
-                                                gt_keypoints_2d, pred_joints, gt_joints, has_pose_3d, pred_vertices,
-                                                opt_vertices, pred_camera, valid_fit_pose, valid_fit_shape)
-        losses = {'loss': loss.detach()}
-        for k, val in loss_dict.items():
-            losses[k] = val.detach()
-        output = {'pred_vertices': pred_vertices.detach(), 'spin_vertices': spin_vertices,
-                  'opt_vertices': opt_vertices.detach(), 'pred_cam_t': pred_cam_t.detach(), 'spin_cam_t': spin_cam_t,
-                  'opt_cam_t': opt_cam_t.detach(), 'smplifyoptiverts': smplifyoptiverts,
-                  'gt_contact_l3': gt_disc_contact, 'has_contact_pc': has_disc_contact,
-                  'has_contact': has_disc_contact, 'valid_kpts_anno': valid_fit | has_smpl_,
-                  'gt_keypoints': gt_keypoints_2d_orig}
+        # ---- losses and the logging dictionaries                                                       :303-336
+        loss, parts = self.criterion_cospin(pred_rotmat, pred_betas, fit.pose, fit.betas, pred_kp,
+                                            input_batch['keypoints'], pred.joints, input_batch['pose_3d'], has_pose_3d,
+                                            pred.vertices, fit.vertices, pred_camera, supervise, supervise)
+        losses = {'loss': loss.detach(), **{k: v.detach() for k, v in parts.items()}}
+        output = dict(pred_vertices=pred.vertices.detach(), spin_vertices=spin_vertices,
+                      opt_vertices=fit.vertices.detach(), pred_cam_t=pred_cam_t.detach(), spin_cam_t=spin_cam_t,
+                      opt_cam_t=fit.cam_t.detach(), smplifyoptiverts=optiverts, gt_contact_l3=labels,
+                      has_contact_pc=has_dc, has_contact=has_dc, valid_kpts_anno=supervise, gt_keypoints=kp_px)
         return loss, losses, output
