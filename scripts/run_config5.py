@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from tuch_b200 import ops, synthetic as syn
+from tuch_b200 import distributed as tdist, ops, synthetic as syn
 from tuch_b200.models.smpl import SMPL
 from tuch_b200.smplify.prior import MaxMixturePrior
 from tuch_b200.smplify.smplifydc import SMPLifyDC
@@ -84,10 +84,11 @@ def step():
     loss, losses, out = tuch.forward_train_step(gb)
     optim.zero_grad()
     loss.backward()
-    if world > 1:
-        for p in net.parameters():
-            dist.all_reduce(p.grad)
-            p.grad /= world
+    if world > 1:                                      # one flattened bucket over NCCL, then the mean
+        grads = [p.grad for p in net.parameters()]
+        tdist.all_reduce_sum_(grads)
+        for g in grads:
+            g /= world
     optim.step()
     return losses, out
 
