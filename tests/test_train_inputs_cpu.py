@@ -60,3 +60,28 @@ def test_train_step_mirror_reports_missing_data_tree():
     else:
         with pytest.raises(TuchError, match='focal_length'):
             TUCH(None, torch.device('cuda'), None, None, None, None, None, None, None)
+
+
+def test_oracle_train_step_runs_and_keeps_its_invariants(small_assets):
+    """The CPU restatement of TUCH.forward_train_step (oracle/train_step.py) on its own: finite losses with the
+    reference's keys, SMPLify-DC in the loop only ever rewrites rows of the fits store that belong to the batch,
+    ground-truth rows end up with their ground-truth parameters, and without fitting the store stays untouched."""
+    import test_train_step_gpu as T
+    from tuch_b200 import synthetic as syn
+    a = small_assets
+    tm, batch, store = T.make_inputs(a)
+    for run_smplify in (True, False):
+        net = syn.make_stand_in_regressor()
+        (loss, losses, out), st = T.run_oracle(a, tm, batch, store.copy(), T.options(run_smplify), net)
+        assert set(losses) == {'loss', 'loss_shape', 'loss_keypoints', 'loss_keypoints_3d', 'loss_regr_pose',
+                               'loss_regr_betas', 'loss_cam', 'loss_contact'}
+        assert all(bool(torch.isfinite(v).all()) for v in losses.values())
+        changed = np.where((st.numpy() != store).any(axis=1))[0]
+        assert set(changed.tolist()) <= set(batch['sample_index'].tolist())
+        assert (len(changed) > 0) == run_smplify
+        gt = batch['has_pgt_smpl'].astype(bool)
+        assert np.array_equal(out['opt_pose'].numpy()[gt], batch['pose'][gt])
+        assert np.array_equal(out['opt_betas'].numpy()[gt], batch['betas'][gt])
+        assert bool(out['valid_kpts_anno'][torch.tensor(gt)].all())
+        loss.backward()
+        assert bool(torch.isfinite(net.fc.weight.grad).all()) and float(net.fc.weight.grad.abs().max()) > 0
