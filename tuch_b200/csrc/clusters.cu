@@ -175,7 +175,109 @@ struct TreeBuilder {
         if (mid_off) mid_off->push_back(n_leaves);
         if (top_off) top_off->push_back(n_mids);
     }
+
+    // ---- optional second stage: rounder leaves (scripts/proto/leaf_refine.py) -------------------------
+    // The bisection above cuts along one principal axis per level, which leaves elongated leaves (bounding
+    // radius 1.55x that of the equal-area disc on the SMPL-sized body).  Here every pair of leaves that are
+    // neighbours in the item graph is pooled and re-split along the best of a fixed set of directions, sizes
+    // kept <= leaf, whenever that lowers R_a^3 + R_b^3 (the near set of a leaf grows with R^3).  Leaves keep
+    // their index, so the group structure above them is untouched.  `pts` holds ppi points per item that the
+    // radius has to cover (the corners of a face; the vertex itself).
+    std::vector<float> pts;
+    int ppi = 0;
+
+    double radius3(const int* items, int n) const {
+        double c[3] = {0, 0, 0};
+        for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) c[a] += cen[3 * items[i] + a];
+        for (int a = 0; a < 3; ++a) c[a] /= n;
+        double r2 = 0;
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < ppi; ++k) {
+                const float* q = &pts[((size_t)items[i] * ppi + k) * 3];
+                const double dx = q[0] - c[0], dy = q[1] - c[1], dz = q[2] - c[2];
+                r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+            }
+        return r2 * std::sqrt(r2);
+    }
+
+    void refine(int sweeps) {
+        if (ppi <= 0 || n_leaves < 2) return;
+        std::vector<int>& L = *leaf_items;
+        // 13 directions: the axes, the face diagonals and the body diagonals of the cube
+        static const double dirs[13][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, -1, 0}, {1, 0, 1}, {1, 0, -1},
+                                           {0, 1, 1}, {0, 1, -1}, {1, 1, 1}, {1, 1, -1}, {1, -1, 1}, {-1, 1, 1}};
+        std::vector<int> owner(N, -1);
+        // measured on B200: exchanging items across group boundaries makes the leaves rounder still (-28 % near
+        // pairs) but inflates the group spheres, more groups open per warp and the winding kernel gets SLOWER
+        // (2.77 vs 2.66 ms) -- so the leaves of different groups are left alone
+        std::vector<int> group_of_leaf;
+        if (mid_off != nullptr && (int)mid_off->size() == n_mids + 1) {
+            group_of_leaf.resize(n_leaves);
+            for (int m = 0; m < n_mids; ++m)
+                for (int l = (*mid_off)[m]; l < (*mid_off)[m + 1]; ++l) group_of_leaf[l] = m;
+        }
+        for (int sweep = 0; sweep < sweeps; ++sweep) {
+            for (int l = 0; l < n_leaves; ++l)
+                for (int i = 0; i < leaf; ++i) if (L[(size_t)l * leaf + i] >= 0) owner[L[(size_t)l * leaf + i]] = l;
+            std::vector<std::pair<int, int>> pairs;
+            for (int t = 0; t < N; ++t)
+                for (int k = adj_off[t]; k < adj_off[t + 1]; ++k)
+                    if (owner[t] < owner[adj[k]]) pairs.emplace_back(owner[t], owner[adj[k]]);
+            std::sort(pairs.begin(), pairs.end());
+            pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+            if (!group_of_leaf.empty())                          // exchanges stay inside one group: its item set,
+                pairs.erase(std::remove_if(pairs.begin(), pairs.end(),   // hence its sphere and moments, is unchanged
+                                           [&](const std::pair<int, int>& q) { return group_of_leaf[q.first] != group_of_leaf[q.second]; }),
+                            pairs.end());
+            int improved = 0;
+            std::vector<int> pool, best;
+            std::vector<std::pair<double, int>> key;
+            for (const auto& pr : pairs) {
+                int* la = &L[(size_t)pr.first * leaf];
+                int* lb = &L[(size_t)pr.second * leaf];
+                pool.clear();
+                int na = 0, nb = 0;
+                for (int i = 0; i < leaf; ++i) if (la[i] >= 0) { pool.push_back(la[i]); ++na; }
+                for (int i = 0; i < leaf; ++i) if (lb[i] >= 0) { pool.push_back(lb[i]); ++nb; }
+                const int n = na + nb;
+                double cost = radius3(pool.data(), na) + radius3(pool.data() + na, nb);
+                int best_k = -1;
+                key.resize(n);
+                for (const auto& d : dirs) {
+                    for (int i = 0; i < n; ++i) {
+                        const int f = pool[i];
+                        key[i] = {cen[3 * f] * d[0] + cen[3 * f + 1] * d[1] + cen[3 * f + 2] * d[2], f};
+                    }
+                    std::sort(key.begin(), key.end());
+                    std::vector<int> order(n);
+                    for (int i = 0; i < n; ++i) order[i] = key[i].second;
+                    for (int k = std::max(n - leaf, 1); k <= std::min(leaf, n - 1); ++k) {
+                        const double c = radius3(order.data(), k) + radius3(order.data() + k, n - k);
+                        if (c < cost * 0.999) { cost = c; best = order; best_k = k; }
+                    }
+                }
+                if (best_k < 0) continue;
+                ++improved;
+                std::sort(best.begin(), best.begin() + best_k);
+                std::sort(best.begin() + best_k, best.end());
+                for (int i = 0; i < leaf; ++i) {
+                    la[i] = i < best_k ? best[i] : -1;
+                    lb[i] = i < n - best_k ? best[best_k + i] : -1;
+                }
+                for (int i = 0; i < best_k; ++i) owner[best[i]] = pr.first;
+                for (int i = best_k; i < n; ++i) owner[best[i]] = pr.second;
+            }
+            if (improved == 0) break;
+        }
+    }
 };
+
+// development knob: sweeps of TreeBuilder::refine over the face leaves and the vertex tiles (0 = off, the default
+// until the refined trees have been through the GPU parity suite)
+static int tree_refine_sweeps() {
+    static const int n = getenv("TUCH_TREE_REFINE") ? atoi(getenv("TUCH_TREE_REFINE")) : 0;
+    return std::max(0, std::min(n, 16));
+}
 
 uint64_t edge_key(int u, int v) {
     const uint64_t a = (uint64_t)std::min(u, v), b = (uint64_t)std::max(u, v);
@@ -204,6 +306,14 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
             for (int x : kv.second) for (int y : kv.second) if (x != y) nb[x].push_back(y);
         tb.set_adjacency(nb);
         tb.run();
+        if (tree_refine_sweeps() > 0) {
+            tb.ppi = 3;
+            tb.pts.resize((size_t)F * 9);
+            for (int t = 0; t < F; ++t)
+                for (int e = 0; e < 3; ++e)
+                    for (int a = 0; a < 3; ++a) tb.pts[((size_t)t * 3 + e) * 3 + a] = verts[3 * faces[3 * t + e] + a];
+            tb.refine(tree_refine_sweeps());
+        }
         out.K = tb.n_leaves; out.NM = tb.n_mids; out.NT = tb.n_tops;
         for (int t = 0; t < out.NT; ++t)
             out.max_top_leaves = std::max(out.max_top_leaves, out.mid_off[out.top_off[t + 1]] - out.mid_off[out.top_off[t]]);
@@ -220,6 +330,11 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
         }
         tb.set_adjacency(nb);
         tb.run();
+        if (tree_refine_sweeps() > 0) {
+            tb.ppi = 1;
+            tb.pts = tb.cen;
+            tb.refine(tree_refine_sweeps());
+        }
         out.T = tb.n_leaves; out.NG = tb.n_mids;
     }
     // self-checks: partitions of the faces and of the vertices
