@@ -91,3 +91,42 @@ def test_far_field_expansion_matches_exact_solid_angles():
     # margin (WC_MARGIN); the actual error is a few 1e-3
     assert total_err.max() < 1e-2, total_err.max()
     assert np.abs(signed_err).max() < 4e-3, np.abs(signed_err).max()
+
+
+def test_refined_tree_is_a_valid_partition_with_rounder_leaves():
+    """TUCH_TREE_REFINE (off by default, read once per process -> a subprocess here): the refined hierarchy is
+    still a partition with ascending ids, keeps the leaf / group counts, and its leaves are rounder."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+sys.path.insert(0, %r)
+import numpy as np
+from tuch_b200 import ops, synthetic as syn
+m = syn.make_lattice_body_model(seed=0)
+v, f = m['v_template'].astype(np.float64), m['faces']
+t = ops.cluster_tree(f, v)
+leaf, vt = t['leaf_face'], t['vtile']
+assert np.array_equal(np.sort(leaf[leaf >= 0]), np.arange(len(f))) and np.array_equal(np.sort(vt[vt >= 0]), np.arange(len(v)))
+for row in list(leaf) + list(vt):
+    n = int((row >= 0).sum())
+    assert n >= 1 and np.all(row[:n] >= 0) and np.all(row[n:] < 0) and np.all(np.diff(row[:n]) > 0)
+tri = v[f]
+r3 = 0.0
+for row in leaf:
+    c = tri[row[row >= 0]].reshape(-1, 3)
+    r3 += np.linalg.norm(c - c.mean(0), axis=1).max() ** 3
+print(json.dumps(dict(K=len(leaf), NM=len(t['mid_off']) - 1, NT=len(t['top_off']) - 1, T=len(vt), r3=r3,
+                      mid_off=t['mid_off'].tolist())))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for tag, sweeps in (('plain', '0'), ('refined', '3')):
+        env = dict(os.environ, TUCH_TREE_REFINE=sweeps)
+        r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        import json
+        out[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ('K', 'NM', 'NT', 'T', 'mid_off'):
+        assert out['plain'][k] == out['refined'][k], k
+    assert out['refined']['r3'] < 0.85 * out['plain']['r3'], (out['refined']['r3'], out['plain']['r3'])
