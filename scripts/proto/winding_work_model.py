@@ -5,8 +5,9 @@ tops and mids opened for the whole warp as soon as one lane is inside the openin
 lane, the near pass two queries per step -- and counts node tests, far-field evaluations and near steps.  The
 weights are the SASS instruction counts of those pieces.  Use it to compare tree variants
 offline, e.g.
-    python scripts/proto/winding_work_model.py
-    TUCH_TREE_REFINE=4 python scripts/proto/winding_work_model.py
+    python scripts/proto/winding_work_model.py [leaves per sub-group, default 0 = the shipped three levels]
+    TUCH_TREE_REFINE=4 python scripts/proto/winding_work_model.py 2
+A sub-group is a hypothetical fourth level: runs of N consecutive leaves inside a mid, opened like a group.
 """
 import os
 import sys
@@ -38,6 +39,13 @@ def main():
     ls = [node_sphere(tri, area, cen, ids) for ids in leaf_ids]
     ms = [node_sphere(tri, area, cen, np.concatenate(leaf_ids[mid[m]:mid[m + 1]])) for m in range(len(mid) - 1)]
     ts = [node_sphere(tri, area, cen, np.concatenate(leaf_ids[mid[top[k]]:mid[top[k + 1]]])) for k in range(len(top) - 1)]
+    sub = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    subs = {}
+    if sub > 0:
+        for m in range(len(mid) - 1):
+            for l0 in range(mid[m], mid[m + 1], sub):
+                l1 = min(l0 + sub, mid[m + 1])
+                subs[l0] = (l1, node_sphere(tri, area, cen, np.concatenate(leaf_ids[l0:l1])))
     tests = far = near_steps = mids_open = 0
     for row in vt:
         q = v[row[row >= 0]]
@@ -52,17 +60,28 @@ def main():
                     far += 1
                     continue
                 mids_open += 1
-                for l in range(mid[m], mid[m + 1]):
-                    tests += 1
-                    n_near = int((np.linalg.norm(q - ls[l][0], axis=1) < BETA_LEAF * ls[l][1]).sum())
-                    if n_near < len(q):
-                        far += 1
-                    near_steps += (n_near + 1) // 2
+                l = mid[m]
+                while l < mid[m + 1]:
+                    l1 = l + 1
+                    if sub > 0:
+                        l1, (p, r) = subs[l]
+                        tests += 1
+                        if not (np.linalg.norm(q - p, axis=1) < BETA_GROUP * r).any():
+                            far += 1
+                            l = l1
+                            continue
+                    for ll in range(l, l1):
+                        tests += 1
+                        n_near = int((np.linalg.norm(q - ls[ll][0], axis=1) < BETA_LEAF * ls[ll][1]).sum())
+                        if n_near < len(q):
+                            far += 1
+                        near_steps += (n_near + 1) // 2
+                    l = l1
     n_warps = len(vt)
     total = W_TEST * tests + W_FAR * far + W_NEAR_STEP * near_steps
-    print('TUCH_TREE_REFINE=%s: per warp %.0f node tests, %.0f far fields, %.1f mids opened, %.0f near steps -> %.1f k '
+    print('TUCH_TREE_REFINE=%s, sub-groups of %d: per warp %.0f node tests, %.0f far fields, %.1f mids opened, %.0f near steps -> %.1f k '
           'warp instructions (tests %.0f %%, far %.0f %%, near %.0f %%)'
-          % (os.environ.get('TUCH_TREE_REFINE', '0'), tests / n_warps, far / n_warps, mids_open / n_warps,
+          % (os.environ.get('TUCH_TREE_REFINE', '0'), sub, tests / n_warps, far / n_warps, mids_open / n_warps,
              near_steps / n_warps, total / n_warps / 1e3, 100 * W_TEST * tests / total, 100 * W_FAR * far / total,
              100 * W_NEAR_STEP * near_steps / total))
 
