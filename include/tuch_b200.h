@@ -45,8 +45,14 @@ int tuch_kernel_timing_enable(int on);
 int tuch_kernel_timing_names(char* buf, int capacity);
 int tuch_kernel_timing_reset(void);
 int tuch_kernel_timing_read(const char* name, double* total_ms, long long* launches);
-/* releases every scratch arena of the current device (synchronises the device) */
+/* Scratch arenas: one grow-only block per (device, stream, purpose) inside the library, so that calls do not
+ * allocate after the first one at a size and can be captured into CUDA graphs.  A block that a capture has seen
+ * is never freed by growth (it is retired and kept for the graphs that point at it).  tuch_release_scratch()
+ * frees every block of the current device (synchronises the device) and INVALIDATES every graph captured over
+ * library calls before it: it increments tuch_scratch_generation(), which holders of captured graphs compare
+ * with the value they saw at capture time to know that they must capture again. */
 int tuch_release_scratch(void);
+long long tuch_scratch_generation(void);
 
 /* ------------------------------------------------------------------ a1  contact.py:23-47
  * batch_pairwise_dist(x, y, squared): P[b,i,j] = (|x_i|^2 + |y_j|^2) - 2 x_i.y_j, sqrt if !squared.

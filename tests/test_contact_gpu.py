@@ -81,6 +81,30 @@ def test_pairwise_dist_backward_matches_autograd(dev):
         assert (gy - yd.grad).abs().max() < 2e-4 * yd.grad.abs().max()
 
 
+def test_pairwise_dist_inplace_mask_idiom(dev):
+    """The reference's idiom (losses.py:76,92-93,115; eft/loss.py:155): build P with autograd, write inf into it in
+    place under no_grad, then differentiate a min of it.  The mirror must allow that and give torch's gradient."""
+    from tuch_b200.utils import contact
+    rng = np.random.default_rng(11)
+    xn = rng.normal(size=(1, 40, 3)).astype(np.float32)
+    mask = rng.uniform(size=(40, 40)) > 0.4
+    mask = mask & mask.T
+    np.fill_diagonal(mask, False)
+    x = torch.tensor(xn, device=dev, requires_grad=True)
+    P = contact.batch_pairwise_dist(x, x, squared=True)
+    with torch.no_grad():
+        P[:, ~torch.tensor(mask, device=dev)] = float('inf')
+    sub = P[:, [1, 5, 9], :][:, :, [2, 3, 30, 31]]
+    torch.min(sub).backward()
+    xd = torch.tensor(xn, dtype=torch.float64, requires_grad=True)
+    Pd = (xd * xd).sum(-1)[:, :, None] + (xd * xd).sum(-1)[:, None, :] - 2 * xd @ xd.transpose(1, 2)
+    with torch.no_grad():
+        Pd[:, ~torch.tensor(mask)] = float('inf')
+    torch.min(Pd[:, [1, 5, 9], :][:, :, [2, 3, 30, 31]]).backward()
+    assert torch.isfinite(x.grad).all()
+    assert (x.grad.cpu().double() - xd.grad).abs().max() < 2e-5 * xd.grad.abs().max()
+
+
 def test_winding_edge_cases(dev):
     from tuch_b200.utils import contact
     # empty triangle set -> zeros; empty query set -> empty

@@ -320,6 +320,27 @@ def test_eft_contact_loss_against_oracle(ctx):
     assert rel(v.grad, v64.grad.numpy()) < 2e-4
 
 
+def test_eft_contact_loss_matches_reference_golden(ctx):
+    """The EFT mirror against the value and gradient recorded from the reference's own tuch/eft/loss.py:129-181
+    (tests/golden/make_golden_eft.py): each body alone (the reference's setting) and the three as one batch."""
+    from tuch_b200.eft.loss import contact_loss
+    e = golden('eft_contact_loss.npz')
+    a = ctx['a']
+    face_tensor = ctx['faces'][None]
+    for b in range(3):
+        v = t(e['verts'][[b]]).requires_grad_(True)
+        got = contact_loss(t(e['gt_contact'][[b]]), v, ctx['geomask'], face_tensor, a['regions'], ctx['segments'])
+        got.backward()
+        ref = float(e['loss'][b])
+        assert abs(got.item() - ref) < 1e-4 * abs(ref), (b, got.item(), ref)
+        assert rel(v.grad[0], e['g_verts'][b]) < 2e-4
+    v = t(e['verts']).requires_grad_(True)
+    got = contact_loss(t(e['gt_contact']), v, ctx['geomask'], face_tensor.repeat(3, 1, 1), a['regions'], ctx['segments'])
+    got.backward()
+    assert abs(got.item() - float(e['loss'].sum())) < 1e-4 * float(e['loss'].sum())
+    assert rel(v.grad, e['g_verts']) < 2e-4
+
+
 def test_contact_fit_cuda_graph_replay_equals_eager(ctx):
     """ContactFit.capture(): the iteration replayed as a CUDA graph gives bit-identical parameters and
     losses to the eager iteration, capture() itself does not advance the optimisation, and load() re-uses
@@ -358,6 +379,55 @@ def test_contact_fit_cuda_graph_replay_equals_eager(ctx):
                t(g['gt_contact']), torch.zeros(3, dtype=torch.bool, device=DEV), t(g['has_discrete_contact']))
     lg1 = [float(graph.step()) for _ in range(3)]
     assert le1 == lg1 and torch.equal(eager1.body_pose.detach(), graph.body_pose.detach())
+
+
+def test_captured_graph_survives_scratch_growth_and_release(ctx):
+    """A graph captured at a small batch keeps working after (i) a later, larger capture on the same stream has
+    made the library's scratch arena grow -- the block the first graph points at is retired, not freed -- and
+    (ii) tuch_release_scratch(), after which step() notices the generation change and captures again."""
+    from tuch_b200 import ops, synthetic as syn
+    from tuch_b200.models.smpl import SMPL
+    from tuch_b200.smplify.smplifydc import SMPLifyDC
+    g = ctx['g']
+    ign = [syn.JOINT_IDS[n] for n in syn.IGN_JOINTS]
+
+    def make(B):
+        smpl = SMPL(model_arrays=ctx['a']['model'], batch_size=B).to(DEV)
+        opt = SMPLifyDC(step_size=1e-2, batch_size=B, num_iters=3, focal_length=5000.0, geodistssmpl=ctx['geod'],
+                        geothres=float(g['geothres']), euclthres=0.02, device=torch.device(DEV), smpl=smpl,
+                        pose_prior=ctx['prior'], ign_joints=ign)
+        rep = lambda x: t(np.concatenate([np.asarray(x)] * ((B + 2) // 3))[:B])
+        kp = rep(g['keypoints_2d'])
+        conf = kp[:, :, 2].clone()
+        conf[:, ign] = 0.0
+        pose = rep(g['init_pose'])
+        fit = opt.begin_contact_fit(pose[:, 3:].clone(), pose[:, :3].clone(), rep(g['init_betas']), rep(g['init_cam_t']),
+                                    rep(g['camera_center']), kp[:, :, :2].contiguous(), conf, ctx['a']['regions'],
+                                    [rep(g['gt_contact']), None], torch.zeros(B, dtype=torch.bool, device=DEV),
+                                    rep(g['has_discrete_contact']), 2000.0, 'sum', ctx['segments'])
+        args = (pose, rep(g['init_betas']), rep(g['init_cam_t']), rep(g['camera_center']), kp, rep(g['gt_contact']),
+                torch.zeros(B, dtype=torch.bool, device=DEV), rep(g['has_discrete_contact']))
+        return fit, args
+
+    ops.release_scratch()                         # start from empty arenas so that the second capture must grow them
+    small, sargs = make(2)
+    small.capture()
+    first = [float(small.step()) for _ in range(3)]
+    pose_first = small.body_pose.detach().clone()
+    big, _ = make(48)                             # 24x the scratch of the small fit on the same capture stream
+    big.capture()
+    for _ in range(2):
+        big.step()
+    small.load(*sargs)
+    again = [float(small.step()) for _ in range(3)]
+    assert again == first and torch.equal(small.body_pose.detach(), pose_first)
+    gen = ops.scratch_generation()
+    ops.release_scratch()
+    assert ops.scratch_generation() == gen + 1
+    small.load(*sargs)
+    third = [float(small.step()) for _ in range(3)]            # re-captured transparently
+    assert third == first and torch.equal(small.body_pose.detach(), pose_first)
+    torch.cuda.synchronize()
 
 
 def test_contact_fitting_loss_full_size_matches_reference_golden(full_assets):

@@ -22,6 +22,8 @@ def _declare(lib):
     lib.tuch_launch_count.restype = C.c_longlong
     lib.tuch_device_info.argtypes = [C.POINTER(i32)] * 3
     lib.tuch_release_scratch.argtypes = []
+    lib.tuch_scratch_generation.argtypes = []
+    lib.tuch_scratch_generation.restype = C.c_longlong
     lib.tuch_kernel_timing_enable.argtypes = [i32]
     lib.tuch_kernel_timing_reset.argtypes = []
     lib.tuch_kernel_timing_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]

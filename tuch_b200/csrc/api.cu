@@ -71,30 +71,43 @@ KernelTimer::~KernelTimer() {
 }
 
 // ---------------------------------------------------------------- scratch arenas
-struct Arena { void* ptr = nullptr; size_t cap = 0; };
+// One grow-only block per (device, slot, stream).  A CUDA graph captured over a call bakes the block's address
+// into its kernel nodes, so a block that a capture has seen is never freed while the library lives: when such an
+// arena has to grow (a later, larger eager call on the same stream) the old block is RETIRED -- kept allocated
+// for the graphs that still point at it -- and a new one serves the calls from then on.  tuch_release_scratch()
+// is the one call that frees everything; it bumps tuch_scratch_generation() so that holders of captured graphs
+// can tell that they must re-capture (tuch_b200/smplify/smplifydc.py does).
+struct Arena { void* ptr = nullptr; size_t cap = 0; bool captured = false; };
 static std::mutex g_arena_mu;
 static std::map<std::pair<std::pair<int, int>, cudaStream_t>, Arena> g_arenas;
+static std::vector<std::pair<int, void*>> g_retired;          // (device, block) kept alive for captured graphs
+static std::atomic<long long> g_scratch_generation{0};
 
 int arena_get(cudaStream_t st, size_t bytes, void** out, int slot) {
     int dev = 0;
     TUCH_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_arena_mu);
     Arena& a = g_arenas[{{dev, slot}, st}];
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
     if (a.cap < bytes) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(st, &cs);
         TUCH_REQUIRE(cs == cudaStreamCaptureStatusNone,
                      "scratch arena must grow (%zu -> %zu bytes) during CUDA-graph capture; run the call once "
                      "outside the capture first", a.cap, bytes);
         if (a.ptr != nullptr) {
-            TUCH_CUDA(cudaStreamSynchronize(st));
-            TUCH_CUDA(cudaFree(a.ptr));
-            a.ptr = nullptr; a.cap = 0;
+            if (a.captured) {
+                g_retired.emplace_back(dev, a.ptr);           // a graph may still read and write it
+            } else {
+                TUCH_CUDA(cudaStreamSynchronize(st));
+                TUCH_CUDA(cudaFree(a.ptr));
+            }
+            a.ptr = nullptr; a.cap = 0; a.captured = false;
         }
         const size_t want = align_up(bytes + bytes / 4, (size_t)1 << 20);
         TUCH_CUDA(cudaMalloc(&a.ptr, want));
         a.cap = want;
     }
+    if (cs != cudaStreamCaptureStatusNone) a.captured = true;
     *out = a.ptr;
     return 0;
 }
@@ -141,8 +154,14 @@ TUCH_EXPORT int tuch_release_scratch(void) {
             ++it;
         }
     }
+    for (auto it = g_retired.begin(); it != g_retired.end();) {
+        if (it->first == dev) { cudaFree(it->second); it = g_retired.erase(it); } else { ++it; }
+    }
+    g_scratch_generation.fetch_add(1);          // every graph captured before this call is now invalid
     return 0;
 }
+
+TUCH_EXPORT long long tuch_scratch_generation(void) { return g_scratch_generation.load(); }
 
 TUCH_EXPORT int tuch_kernel_timing_enable(int on) {
     std::lock_guard<std::mutex> lk(g_timing_mu);

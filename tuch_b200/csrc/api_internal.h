@@ -1,5 +1,6 @@
 // Internal: opaque handle layouts and the scratch bump allocator behind include/tuch_b200.h.
 #pragma once
+#include <atomic>
 #include <vector>
 
 #include "../../include/tuch_b200.h"
@@ -16,7 +17,8 @@ struct tuch_topology {
     // (tuch_topology_set_template) or lazily from the first body a contact query sees
     int K = 0, NM = 0, NT = 0, T = 0, NG = 0, max_top_leaves = 0;
     int *d_leaf_face = nullptr, *d_mid_off = nullptr, *d_top_off = nullptr, *d_vtile = nullptr, *d_vgroup_off = nullptr;
-    bool has_clusters = false;
+    std::atomic<bool> has_clusters{false};   // published last (release) by install_clusters; the lazy build of the
+                                             // first query may run while other threads read it (acquire)
     uint32_t* d_maskG = nullptr;       // per-group summary of d_maskP (any unmasked row in the tile group)
     uint32_t* d_maskP = nullptr;       // geodesic mask in cluster order (nearest_tiles.cu); valid when both
     bool has_maskP = false;            // the mask and the hierarchy exist

@@ -814,6 +814,9 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
                         const float qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src),
                                     qz = __shfl_sync(0xffffffffu, pz, src);
                         if (q >= 0) acc[q * (WC_LEAF + 1) + slot] += half_solid_angle_n(qx, qy, qz, A, Bv, C);
+                        // a query served by one half-warp in this step may be served by the other half in a later
+                        // one: order the read-modify-writes of the tile across the lanes (racecheck-clean)
+                        __syncwarp();
                     }
                 }
             }

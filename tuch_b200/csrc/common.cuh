@@ -118,11 +118,15 @@ __device__ __forceinline__ float half_solid_angle_n(float px, float py, float pz
 // ---------------------------------------------------------------- order-independent accumulation
 // Gradient scatters add many terms into the same element from different threads.  fp32 atomics make the
 // sum depend on the arrival order (run-to-run differences at the 1e-7 level that a discontinuous objective
-// amplifies); 64-bit fixed-point atomics (2^-32 resolution, +-2^31 range) are exact and therefore
-// deterministic.  A non-finite term is stored as is (it has to poison the result either way).
+// amplifies); 64-bit fixed-point atomics are exact and therefore deterministic.
+// Representable range: every accumulated SUM must stay within +-2^31 (2.1e9) and terms below 2^-33 (1.2e-10) round
+// to zero; a single term beyond +-2^31 saturates (__float2ll_rn) instead of wrapping.  The callers multiply the
+// upstream factor (loss weight x g_loss) in BEFORE the quantisation, so "term" means the final gradient
+// contribution: with the reference's weights (<= 2000 x tanh'() <= 25/m) sums stay below 1e7.  A non-finite term
+// is stored as is into the fp32 destination (it has to poison the result either way) with an atomic exchange.
 constexpr float FIX_SCALE = 4294967296.f;            // 2^32
 __device__ __forceinline__ void fix_add(long long* acc, float* fallback, float v) {
-    if (!isfinite(v)) { *fallback = v; return; }
+    if (!isfinite(v)) { atomicExch(fallback, v); return; }
     atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__float2ll_rn(v * FIX_SCALE));
 }
 __device__ __forceinline__ float fix_value(long long acc) { return (float)((double)acc * (1.0 / 4294967296.0)); }

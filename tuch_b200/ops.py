@@ -51,6 +51,16 @@ def launch_count():
     return int(lib().tuch_launch_count())
 
 
+def release_scratch():
+    """Frees the library's scratch arenas on the current device.  Graphs captured before this call are invalid
+    afterwards (scratch_generation() changes; ContactFit / CameraFit re-capture on their next step)."""
+    check(lib().tuch_release_scratch(), 'tuch_release_scratch')
+
+
+def scratch_generation():
+    return int(lib().tuch_scratch_generation())
+
+
 def kernel_timing(enable=None, reset=False):
     """Per-kernel CUDA-event timing inside the library (bench.py's roofline leg)."""
     if reset:
@@ -118,7 +128,10 @@ def pairwise_dist(x, y, squared=True):
 
 
 def pairwise_dist_backward(x, y, P, gP, squared=True):
-    x, y, P, gP = _f32(x, 'x'), _f32(y, 'y'), _f32(P, 'P'), _f32(gP, 'gP')
+    x, y, gP = _f32(x, 'x'), _f32(y, 'y'), _f32(gP, 'gP')
+    P = _f32(P, 'P') if P is not None else None             # only the sqrt form reads it
+    if P is None and not squared:
+        raise TuchError('pairwise_dist_backward: the sqrt form needs P')
     bs, nx, ny = x.shape[0], x.shape[1], y.shape[1]
     gx, gy = torch.empty_like(x), torch.empty_like(y)
     with torch.cuda.device(x.device):

@@ -107,6 +107,9 @@ class CameraFit:
         self.opt.step()
 
     def step(self):
+        if self._graph is not None and self._gen != ops.scratch_generation():
+            self._graph = None                      # tuch_release_scratch() freed what the graph points at
+            self.capture()
         if self._graph is not None:
             self._graph.replay()
         else:
@@ -115,6 +118,7 @@ class CameraFit:
     def capture(self, warmup=2):
         if self._graph is None:
             self._graph = _capture_iteration(self._step_eager, self.params, self.opt, warmup)
+            self._gen = ops.scratch_generation()
         return self
 
     def load(self, init_pose, init_betas, init_cam_t, camera_center, joints_2d, joints_conf):
@@ -172,6 +176,9 @@ class ContactFit:
     def step(self):
         """One iteration: SMPL forward -> contact_fitting_loss -> backward -> Adam.  Returns the loss (a
         0-d device tensor; after capture() the same tensor object every time)."""
+        if self._graph is not None and self._gen != ops.scratch_generation():
+            self._graph = None                      # tuch_release_scratch() freed what the graph points at
+            self.capture()
         if self._graph is not None:
             self._graph.replay()
             return self.loss
@@ -186,6 +193,7 @@ class ContactFit:
         tensors that every replay overwrites."""
         if self._graph is None:
             self._graph = _capture_iteration(self._step_eager, [self.body_pose, self.global_orient], self.opt, warmup)
+            self._gen = ops.scratch_generation()
         return self
 
     def load(self, init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, gt_contact_l3=None,

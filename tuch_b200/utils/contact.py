@@ -7,16 +7,21 @@ from .. import ops
 
 
 class _PairwiseDist(torch.autograd.Function):
+    """The output is NOT saved for backward: the reference's own idiom writes into it in place under no_grad
+    (`pred_verts_dists[:, ~geomask] = inf`, losses.py:92, eft/loss.py:155) and then differentiates
+    torch.min(...) of it.  The squared form does not need P in backward; the sqrt form recomputes it."""
+
     @staticmethod
     def forward(ctx, x, y, squared):
         P = ops.pairwise_dist(x, y, squared)
-        ctx.save_for_backward(x, y, P)
+        ctx.save_for_backward(x, y)
         ctx.squared = squared
         return P
 
     @staticmethod
     def backward(ctx, g):
-        x, y, P = ctx.saved_tensors
+        x, y = ctx.saved_tensors
+        P = None if ctx.squared else ops.pairwise_dist(x, y, False)
         gx, gy = ops.pairwise_dist_backward(x, y, P, g.contiguous(), ctx.squared)
         return gx, gy, None
 
