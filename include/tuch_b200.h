@@ -128,13 +128,21 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
  * TUCH_WINDING_EXACT sums all F solid angles for every query (values within 2e-5 of the reference).
  * The hierarchy is built from the template given to tuch_topology_set_template (HOST [V,3]) or, when
  * none was given, from the first body a query sees (one blocking device->host copy, outside graph
- * capture only). */
+ * capture only; inside a capture the exact kernels run instead).  Give the template whenever the body model is
+ * at hand (SMPL.v_template): the lazily built hierarchy depends on which body arrives first, and with it the
+ * far-field rounding of the returned `winding` values (never the flags: every value within the band around the
+ * threshold is re-evaluated over all faces).  In TUCH_WINDING_FAST mode `winding` is the hierarchical value:
+ * within 5e-3 of the all-faces sum away from the threshold band, exact (2e-5) inside it. */
 #define TUCH_WINDING_EXACT 0
 #define TUCH_WINDING_FAST 1
 int tuch_topology_set_template(tuch_topology* topo, const float* verts_host);
 int tuch_topology_set_winding_mode(tuch_topology* topo, int mode);
 int tuch_topology_cluster_stats(const tuch_topology* topo, int* n_leaves, int* n_mids, int* n_tops, int* n_tiles,
                                 int* leaf_faces);
+/* how many queries the LAST hierarchical call on this topology re-evaluated exactly (values within the band
+ * around the 0.99 threshold of losses.py:82): mesh-vertex queries (tuch_contact_query and everything built on
+ * it) and HD-point queries (tuch_regressor_contact_loss).  Synchronises `stream`. */
+int tuch_topology_query_stats(const tuch_topology* topo, int* refine_vertices, int* refine_points, void* stream);
 /* the hierarchy builder without a device: leaf_face_out[n_leaves][16] (face id or -1),
  * mid_off_out[n_mids + 1] (leaf ranges), top_off_out[n_tops + 1] (mid ranges), vtile_out[n_tiles][32]
  * (vertex tiles: the 32 neighbouring vertices one warp queries / one word of the cluster-ordered geodesic

@@ -112,9 +112,12 @@ def test_contact_loss_full_size(full_assets):
                                            a['hd_reg'], a['hd_fidx'], use_hd=True, return_aux=True)
     ref.backward()
     assert ref.item() > 0
-    # 20k HD points are dense enough for fp32 near-ties in the nearest-point search: the selection must
-    # be identical, the nearest point / inside flag may differ on a handful of points, and the loss and
-    # its gradient must agree up to those
+    # fp64 adjudication: the same algorithm in double gives the truth both fp32 evaluations are scored
+    # against; the product path must be within the north_star tolerance of it and select / flag / pair identically
+    p64 = torch.tensor(verts, dtype=torch.float64, requires_grad=True)
+    ref64, aux64 = oreg.regressor_contact_loss(p64, [True, True], a['model']['faces'], a['geo'] > 0.3, 0.02, segs,
+                                               a['hd_reg'], a['hd_fidx'], use_hd=True, return_aux=True)
+    ref64.backward()
     _, dbg = crit._topo.regressor_contact_loss(pv.detach(), valid=torch.tensor([True, True], device=DEV),
                                                euclthres=0.02, use_hd=True, debug=True)
     for b in range(2):
@@ -122,12 +125,21 @@ def test_contact_loss_full_size(full_assets):
         n = int(dbg['counts'][b])
         assert n == len(sel) and n > 100
         assert np.array_equal(dbg['sel'][b, :n].cpu().numpy(), sel)
-        assert (dbg['hd_argmin'][b, :n].cpu().numpy() != aux[b]['hd_argmin']).mean() < 0.01
-        assert (dbg['hd_exterior'][b, :n].cpu().numpy().astype(bool) != aux[b]['hd_exterior']).mean() < 0.005
-    assert abs(val.item() - ref.item()) < 2e-3 * abs(ref.item()), (val.item(), ref.item())
-    g, gr = pv.grad.cpu().double().flatten(), p32.grad.double().flatten()
-    assert float((g * gr).sum() / (g.norm() * gr.norm())) > 0.9995
-    assert rel(pv.grad, p32.grad.numpy()) < 5e-2
+        # an fp32 near-tie of the expansion-form distance may resolve differently: allowed only where the fp64
+        # evaluation says it IS one (the two candidates within 2e-6 m^2)
+        am = dbg['hd_argmin'][b, :n].cpu().numpy()
+        diff = np.where(am != aux64[b]['hd_argmin'])[0]
+        if len(diff):
+            hd = (a['hd_reg'][sel].astype(np.float64) @ verts[b].astype(np.float64))
+            d_k = ((hd[diff] - hd[am[diff]]) ** 2).sum(1)
+            d_t = ((hd[diff] - hd[aux64[b]['hd_argmin'][diff]]) ** 2).sum(1)
+            assert np.abs(d_k - d_t).max() < 2e-6, (b, diff, d_k, d_t)
+        assert len(diff) <= 2
+        assert (dbg['hd_exterior'][b, :n].cpu().numpy().astype(bool) != aux64[b]['hd_exterior']).sum() == 0
+    assert abs(val.item() - ref64.item()) < 1e-4 * abs(ref64.item()), (val.item(), ref64.item())
+    assert abs(val.item() - ref.item()) < 1e-4 * abs(ref.item()), (val.item(), ref.item())
+    assert rel(pv.grad, p64.grad.numpy()) < 2e-4
+    assert rel(pv.grad, p32.grad.numpy()) < 2e-4
 
 
 def test_hd_inside_test_hierarchical_vs_all_faces(full_assets):
@@ -174,7 +186,21 @@ def test_contact_loss_full_size_matches_reference_golden(full_assets):
     val = crit.contact_loss(pv, torch.tensor([True, True], device=DEV))
     val.backward()
     ref = float(r['loss'])
-    assert abs(val.item() - ref) < 2e-3 * abs(ref), (val.item(), ref)
+    # measured on the B200 (scripts/diag/regressor_dump.py + the fp64 oracle, round 2): loss identical to the
+    # reference's fp32 value to the last bit, 1.3e-8 from the fp64 evaluation; gradient 9.6e-7 of its max-norm from
+    # the reference's, 1.4e-6 from fp64 (the reference's own fp32 gradient is 9.7e-7 from fp64); the selected HD
+    # points, their nearest points and inside flags are identical.  Held to the north_star tolerance:
+    assert abs(val.item() - ref) < 1e-4 * abs(ref), (val.item(), ref)
     g, gr = pv.grad.cpu().double().flatten(), torch.tensor(r['g_verts']).double().flatten()
-    assert float((g * gr).sum() / (g.norm() * gr.norm())) > 0.9995
-    assert rel(pv.grad, r['g_verts']) < 5e-2
+    assert float((g * gr).sum() / (g.norm() * gr.norm())) > 0.999999
+    assert rel(pv.grad, r['g_verts']) < 2e-4
+    # fp64 adjudication of the SAME golden input: kernel and reference are scored against the double evaluation
+    from oracle import regressor as oreg, segments as oseg
+    segs = oseg.build_segments(a['segs'], a['model']['faces'])
+    p64 = torch.tensor(r['verts'], dtype=torch.float64, requires_grad=True)
+    t64 = oreg.regressor_contact_loss(p64, [True, True], a['model']['faces'], a['geo'] > float(r['geothres']), 0.02, segs,
+                                      a['hd_reg'], a['hd_fidx'], use_hd=True)
+    t64.backward()
+    err_kernel, err_ref = abs(val.item() - t64.item()) / t64.item(), abs(ref - t64.item()) / t64.item()
+    assert err_kernel < 1e-5 and err_kernel <= err_ref + 1e-6, (err_kernel, err_ref)
+    assert rel(pv.grad, p64.grad.numpy()) < 1e-4

@@ -284,6 +284,10 @@ TUCH_EXPORT int tuch_topology_create(int V, int F, const int32_t* faces_host, tu
     t->V = V; t->F = F;
     t->Fp = padded_faces(F); t->Vp = padded_verts(V); t->Vq = padded_verts(V); t->W = cdiv(V, 32);
     if (int rc = upload(faces_host, (size_t)F * 3, &t->d_faces)) { delete t; return rc; }
+    if (cudaMalloc((void**)&t->d_stats, 2 * sizeof(int)) != cudaSuccess || cudaMemset(t->d_stats, 0, 2 * sizeof(int)) != cudaSuccess) {
+        tuch_topology_destroy(t);
+        return cuda_fail(cudaGetLastError(), "tuch_topology_create: stats", __FILE__, __LINE__);
+    }
     if (F > 0) {
         std::vector<int> vid, fid;
         std::vector<uint32_t> flag;
@@ -329,7 +333,7 @@ TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
     free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_vgroup_off);
-    free_dev(t->d_maskP); free_dev(t->d_maskG);
+    free_dev(t->d_maskP); free_dev(t->d_maskG); free_dev(t->d_stats);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -448,6 +452,17 @@ TUCH_EXPORT int tuch_topology_cluster_stats(const tuch_topology* t, int* n_leave
     if (n_tops) *n_tops = t->has_clusters ? t->NT : 0;
     if (n_tiles) *n_tiles = t->has_clusters ? t->T : 0;
     if (leaf_faces) *leaf_faces = WC_LEAF;
+    return 0;
+}
+
+TUCH_EXPORT int tuch_topology_query_stats(const tuch_topology* t, int* refine_vertices, int* refine_points, void* stream) {
+    TUCH_REQUIRE(t != nullptr, "tuch_topology_query_stats: null topology");
+    int h[2] = {0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    TUCH_CUDA(cudaMemcpyAsync(h, t->d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TUCH_CUDA(cudaStreamSynchronize(st));
+    if (refine_vertices) *refine_vertices = h[0];
+    if (refine_points) *refine_points = h[1];
     return 0;
 }
 
@@ -676,6 +691,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
             ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, t->d_vtile, strip4, info,
                          sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
             j.max_top_leaves = t->max_top_leaves;
+            j.stats = t->d_stats;
             if (int rc = launch_winding_clusters(j, st)) return rc;
             if (packed_out != nullptr) {
                 packed_out->ctri = strip4; packed_out->nodes = info;

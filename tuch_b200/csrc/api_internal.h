@@ -23,6 +23,7 @@ struct tuch_topology {
     uint32_t* d_maskP = nullptr;       // geodesic mask in cluster order (nearest_tiles.cu); valid when both
     bool has_maskP = false;            // the mask and the hierarchy exist
     int winding_mode = 1;              // TUCH_WINDING_FAST
+    int* d_stats = nullptr;            // [2] length of the last exact re-evaluation list: vertex query, point query
     uint32_t* d_maskT = nullptr;       // [W][Vq] bit-packed geodesic mask
     bool has_mask = false;
     // DSC regions (CSR) and annotated pairs

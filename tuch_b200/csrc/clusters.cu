@@ -856,10 +856,11 @@ __global__ void cluster_finalize_kernel(const float* __restrict__ partial, int V
 // warps stride over the packed face slots and their partial sums are combined in a fixed order
 __global__ void __launch_bounds__(256)
 cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict__ ctri, int V, int K,
-                      const int* __restrict__ refine_list, float* __restrict__ winding) {
+                      const int* __restrict__ refine_list, float* __restrict__ winding, int* __restrict__ stats) {
     __shared__ float s_part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = refine_list[0];
+    if (stats != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *stats = count;   // tuch_topology_query_stats
     const int n_slots = K * WC_LEAF;
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const int id = refine_list[1 + e];
@@ -957,7 +958,7 @@ int launch_cluster_query(const ClusterJob& j, cudaStream_t st) {
     }
     {
         KernelTimer timer("winding_refine_kernel", st);
-        cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(points, j.ctri, Q, j.K, j.refine_list, j.winding);
+        cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(points, j.ctri, Q, j.K, j.refine_list, j.winding, j.stats);
     }
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;

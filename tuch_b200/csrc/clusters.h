@@ -62,6 +62,7 @@ struct ClusterJob {
     // THAT job packed with (cluster_pack_betas); 0 = the records are this job's own
     float packed_beta_leaf = 0.f, packed_beta_group = 0.f;
     int max_top_leaves = 0;          // largest top group in leaves (shared-memory staging of the pack kernel)
+    int* stats = nullptr;            // optional device int: receives the length of the exact re-evaluation list
 };
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);

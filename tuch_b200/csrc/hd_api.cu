@@ -110,6 +110,7 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
         j.points = off; j.Q = N; j.q_counts = cnt; j.body_active = valid; j.max_top_leaves = t->max_top_leaves;
         j.beta_leaf = WC_BETA_POINTS; j.beta_group = WC_BETA_GROUP_POINTS; j.margin = WC_MARGIN_POINTS;
         j.packed_beta_leaf = packed.beta_leaf; j.packed_beta_group = packed.beta_group;
+        j.stats = t->d_stats + 1;
         if (int rc = launch_cluster_query(j, st)) return rc;
     } else {
         float4* strip4 = sc.get<float4>(h_tri);

@@ -226,6 +226,13 @@ class Topology:
         return dict(leaves=int(k.value), mids=int(nm.value), tops=int(nt.value), vertex_tiles=int(t.value),
                     leaf_faces=int(lf.value))
 
+    def query_stats(self):
+        """-> dict(refine_vertices, refine_points): queries the last hierarchical call re-evaluated exactly."""
+        a, b = C.c_int32(0), C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_query_stats(self._h, C.byref(a), C.byref(b), _stream()), 'tuch_topology_query_stats')
+        return dict(refine_vertices=int(a.value), refine_points=int(b.value))
+
     # geomask = geodist > geothres (smplifydc.py:65)
     def set_geodist(self, geodist, geothres):
         g = _f32(geodist.to(self.device) if isinstance(geodist, torch.Tensor) else

@@ -108,6 +108,7 @@ class _FitObjective(torch.autograd.Function):
         ctx.save_for_backward(*[t if t is not None else torch.empty(0, device=dev)
                                 for t in (rep['g_joints'], rep['g_cam_t'], g_pose, g_betas, g_verts)])
         ctx.have = [t is not None for t in (rep['g_joints'], rep['g_cam_t'], g_pose, g_betas, g_verts)]
+        aux['per_body'] = per_body
         cfg['aux'] = aux
         cfg['per_body'] = per_body
         return per_body.sum()

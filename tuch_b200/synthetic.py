@@ -629,3 +629,48 @@ def make_stand_in_regressor(seed: int = 0, spread: float = 0.15):
             return rotmat, 0.5 * x[:, 144:154], cam
 
     return StandInRegressor()
+
+
+def make_hmr_regressor(seed: int = 0, spread: float = 0.15):
+    """An image regressor of HMR's size and shape for the train-step benchmarks (BASELINE configs 3 and 5): a
+    ResNet-50 trunk (torchvision, random init -- no network for weights) and the iterative regression head of
+    tuch/models/hmr.py:68-171 (2048 + 144 + 13 -> 1024 -> 1024 -> 144 | 10 | 3, three iterations from mean
+    parameters), 26.98 M parameters = 108 MB of fp32 gradients per step for the NCCL all-reduce.  The mean pose is a
+    folded-arm pose and the head's output layers start `spread`-sized, so the predicted meshes self-intersect like
+    early-training predictions do.  The convnet itself is outside the hot path (served by cuDNN, as in the
+    reference); this module exists so that the benchmark's gradient exchange and backward overlap are real."""
+    import torch
+    from torch import nn
+    import torchvision
+    from .utils.geometry import batch_rodrigues, rot6d_to_rotmat
+
+    class HMRSized(nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(seed)
+            trunk = torchvision.models.resnet50(weights=None)
+            self.trunk = nn.Sequential(trunk.conv1, trunk.bn1, trunk.relu, trunk.maxpool, trunk.layer1, trunk.layer2,
+                                       trunk.layer3, trunk.layer4, nn.AdaptiveAvgPool2d(1), nn.Flatten())
+            npose = 24 * 6
+            self.fc1 = nn.Linear(2048 + npose + 13, 1024)
+            self.drop1 = nn.Dropout()
+            self.fc2 = nn.Linear(1024, 1024)
+            self.drop2 = nn.Dropout()
+            self.decpose, self.decshape, self.deccam = nn.Linear(1024, npose), nn.Linear(1024, 10), nn.Linear(1024, 3)
+            for lin, gain in ((self.decpose, spread), (self.decshape, 0.3), (self.deccam, 0.01)):
+                nn.init.xavier_uniform_(lin.weight, gain=gain)
+            base = batch_rodrigues(torch.tensor(fold_arms_pose(1, seed=seed + 5, fold=1.0)).view(24, 3))
+            self.register_buffer('init_pose', base[:, :, :2].reshape(1, npose).clone())
+            self.register_buffer('init_shape', torch.zeros(1, 10))
+            self.register_buffer('init_cam', torch.tensor([[0.9, 0.0, 0.0]]))
+
+        def forward(self, x, n_iter=3):
+            B = x.shape[0]
+            xf = self.trunk(x)
+            pose, shape, cam = self.init_pose.expand(B, -1), self.init_shape.expand(B, -1), self.init_cam.expand(B, -1)
+            for _ in range(n_iter):
+                xc = self.drop2(self.fc2(self.drop1(self.fc1(torch.cat([xf, pose, shape, cam], 1)))))
+                pose, shape, cam = self.decpose(xc) + pose, self.decshape(xc) + shape, self.deccam(xc) + cam
+            return rot6d_to_rotmat(pose).view(B, 24, 3, 3), shape, cam
+
+    return HMRSized()

@@ -19,9 +19,30 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import distributed as tdist, ops
 from ..utils.geometry import batch_rodrigues
 from ..utils.segmentation import BatchBodySegment
+
+
+def masked_mean(rows, mask, dist_mode=None):
+    """`rows[mask].mean()` of the reference (loss.py:182,201,211,225-236,317) for per-body rows of equal size.
+
+    dist_mode None: exactly that, on this process's batch (an empty selection gives NaN, as in the reference).
+    One process per GPU with the batch sharded over the ranks: the mean runs over a data-dependent subset of the
+    GLOBAL batch, so every rank returns its share  local_sum / global_count  (tuch_b200.distributed.
+    global_masked_mean: one scalar all-reduce of the counts).  'sum': the shares add up to the single-process value
+    and a SUM all-reduce of the gradients gives the single-process gradient.  'mean': the share is multiplied by
+    the world size, for gradient reductions that AVERAGE over the ranks (DistributedDataParallel)."""
+    if rows.dim() > 1:
+        rows = rows.reshape(rows.shape[0], -1).mean(dim=1)
+    if dist_mode is None:
+        return rows[mask].mean()
+    val, _ = tdist.global_masked_mean(rows, mask)
+    if dist_mode == 'mean':
+        val = val * tdist.world()[1]
+    elif dist_mode != 'sum':
+        raise ValueError("dist_mode must be None, 'sum' or 'mean'")
+    return val
 
 
 def batch_face_normals(triangles):
@@ -34,23 +55,31 @@ class _RegressorContact(torch.autograd.Function):
     """contact_loss[valid_fit].mean() with the gradient w.r.t. pred_vertices produced by the kernels."""
 
     @staticmethod
-    def forward(ctx, pred_vertices, topo, valid, euclthres, use_hd):
+    def forward(ctx, pred_vertices, topo, valid, euclthres, use_hd, dist_mode=None):
         B = pred_vertices.shape[0]
         valid = valid.bool()
         n_valid = valid.sum()                                                  # stays on the device
-        g_loss = valid.float() / n_valid.clamp(min=1).float()
+        scale = 1.0
+        if dist_mode is not None:                                              # global count, see masked_mean()
+            rank, ws = tdist.world()
+            if ws > 1:
+                import torch.distributed as dist
+                n_valid = n_valid.clone()
+                dist.all_reduce(n_valid, op=dist.ReduceOp.SUM)
+            scale = float(ws) if dist_mode == 'mean' else 1.0
+        g_loss = valid.float() * scale / n_valid.clamp(min=1).float()
         g_verts = torch.zeros(B, topo.V, 3, device=pred_vertices.device, dtype=torch.float32) \
             if ctx.needs_input_grad[0] else None
         per_body = topo.regressor_contact_loss(pred_vertices, valid=valid, euclthres=euclthres, use_hd=use_hd,
                                                g_loss=g_loss, g_verts=g_verts)
         ctx.save_for_backward(g_verts if g_verts is not None else torch.empty(0, device=pred_vertices.device))
         # mean over an empty selection is NaN in the reference (loss.py:317); keep that
-        return (per_body * valid.float()).sum() / n_valid.float()
+        return (per_body * valid.float()).sum() * scale / n_valid.float()
 
     @staticmethod
     def backward(ctx, g):
         (g_verts,) = ctx.saved_tensors
-        return (g_verts * g if g_verts.numel() else None), None, None, None, None
+        return (g_verts * g if g_verts.numel() else None), None, None, None, None, None
 
 
 class RegressorLoss(nn.Module):
@@ -72,6 +101,7 @@ class RegressorLoss(nn.Module):
         self.euclthres = euclthres
         self.face_tensor = face_tensor
         self.use_hd = use_hd
+        self.dist_mode = None            # set_distributed(): count-corrected means over a sharded batch
         if self.use_hd:
             if hd_regressor is None or hd_faces is None:
                 try:                                               # the reference's own files (loss.py:81-88)
@@ -100,6 +130,16 @@ class RegressorLoss(nn.Module):
         if self.use_hd:
             self._topo.set_hd(hd_regressor, hd_faces)
 
+    def set_distributed(self, mode):
+        """One process per GPU, the batch sharded over the ranks: every `x[subset].mean()` of this loss (contact
+        term :317, SPIN terms :182,201,211,225-236, camera term :138) becomes this rank's share of the mean over
+        the GLOBAL batch; see masked_mean().  mode: None (single process), 'sum' or 'mean' (how the caller reduces
+        the gradients over the ranks)."""
+        if mode not in (None, 'sum', 'mean'):
+            raise ValueError("mode must be None, 'sum' or 'mean'")
+        self.dist_mode = mode
+        return self
+
     def forward(self, pred_rotmat, pred_betas, opt_pose, opt_betas, pred_keypoints_2d, gt_keypoints_2d,
                 pred_joints, gt_joints, has_pose_3d, pred_vertices, opt_vertices, pred_camera, valid_fit,
                 valid_fit_shape):
@@ -114,7 +154,9 @@ class RegressorLoss(nn.Module):
                                             o.gt_train_weight, valid_fit)
         loss_keypoints_3d = self.keypoint_3d_loss(pred_joints, gt_joints, has_pose_3d)
         loss_shape = self.shape_loss(pred_vertices, opt_vertices, valid_fit)
-        cam_loss = ((torch.exp(-pred_camera[:, 0] * 10)) ** 2).mean()
+        cam_rows = (torch.exp(-pred_camera[:, 0] * 10)) ** 2
+        cam_loss = cam_rows.mean() if self.dist_mode is None else \
+            masked_mean(cam_rows, torch.ones_like(cam_rows, dtype=torch.bool), self.dist_mode)
         spin_loss = o.shape_loss_weight * loss_shape + o.keypoint_loss_weight * loss_keypoints + \
             o.keypoint_loss_weight * loss_keypoints_3d + o.pose_loss_weight * loss_regr_pose + \
             o.beta_loss_weight * loss_regr_betas + cam_loss
@@ -134,11 +176,18 @@ class RegressorLoss(nn.Module):
         conf[:, :25] *= openpose_weight
         conf[:, 25:] *= gt_weight
         loss = (conf * self.criterion_keypoints(pred_keypoints_2d, gt_keypoints_2d[:, :, :-1])).mean(dim=(1, 2))
-        return loss[valid_fit].mean()
+        return masked_mean(loss, valid_fit, self.dist_mode)
 
     def keypoint_3d_loss(self, pred_keypoints_3d, gt_keypoints_3d, has_pose_3d):
         """pelvis-centred, confidence-weighted 3-D keypoint MSE over the 24 GT joints (:184-203)."""
         sel = has_pose_3d == 1
+        if self.dist_mode is not None:
+            pred = pred_keypoints_3d[:, 25:, :]
+            conf = gt_keypoints_3d[:, :, -1].unsqueeze(-1)
+            gt = gt_keypoints_3d[:, :, :-1]
+            gt = gt - ((gt[:, 2, :] + gt[:, 3, :]) / 2)[:, None, :]
+            pred = pred - ((pred[:, 2, :] + pred[:, 3, :]) / 2)[:, None, :]
+            return self._global_or_zero(conf * self.criterion_keypoints(pred, gt), sel)
         pred = pred_keypoints_3d[:, 25:, :][sel]
         conf = gt_keypoints_3d[:, :, -1].unsqueeze(-1).clone()[sel]
         gt = gt_keypoints_3d[:, :, :-1].clone()[sel]
@@ -148,9 +197,20 @@ class RegressorLoss(nn.Module):
         pred = pred - ((pred[:, 2, :] + pred[:, 3, :]) / 2)[:, None, :]
         return (conf * self.criterion_keypoints(pred, gt)).mean()
 
+    def _global_or_zero(self, rows, sel):
+        """Sharded form of `if len(selection) == 0: return zeros(1)`: the emptiness test is GLOBAL (the count
+        all-reduce of masked_mean), so all ranks take the same branch without a host synchronisation."""
+        rows = rows.reshape(rows.shape[0], -1).mean(dim=1)
+        val, count = tdist.global_masked_mean(rows, sel)
+        if self.dist_mode == 'mean':
+            val = val * tdist.world()[1]
+        return torch.where(count > 0, val, torch.zeros_like(val)).reshape(1)
+
     def shape_loss(self, pred_vertices, gt_vertices, has_smpl):
         """per-vertex L1 on the bodies with a fit (:205-214)."""
         sel = has_smpl == 1
+        if self.dist_mode is not None:
+            return self._global_or_zero((pred_vertices - gt_vertices).abs(), sel)
         if int(sel.sum()) == 0:
             return self._zero()
         return self.criterion_shape(pred_vertices[sel], gt_vertices[sel])
@@ -159,6 +219,9 @@ class RegressorLoss(nn.Module):
         """MSE on rotation matrices / betas of the bodies with a fit (:216-238)."""
         sp, ss = has_smpl_pose == 1, has_smpl_shape == 1
         gt_rotmat = batch_rodrigues(gt_pose.view(-1, 3)).view(-1, 24, 3, 3)
+        if self.dist_mode is not None:
+            return (self._global_or_zero((pred_rotmat - gt_rotmat) ** 2, sp),
+                    self._global_or_zero((pred_betas - gt_betas) ** 2, ss))
         loss_pose = self.criterion_regr(pred_rotmat[sp], gt_rotmat[sp]) if int(sp.sum()) > 0 else self._zero()
         loss_betas = self.criterion_regr(pred_betas[ss], gt_betas[ss]) if int(ss.sum()) > 0 else self._zero()
         return loss_pose, loss_betas
@@ -166,4 +229,5 @@ class RegressorLoss(nn.Module):
     # ------------------------------------------------------------------ the hot term
     def contact_loss(self, pred_vertices, valid_fit):
         """Self-contact push/pull loss on the (HD-resampled) predicted mesh, mean over the valid bodies."""
-        return _RegressorContact.apply(pred_vertices, self._topo, valid_fit, float(self.euclthres), bool(self.use_hd))
+        return _RegressorContact.apply(pred_vertices, self._topo, valid_fit, float(self.euclthres), bool(self.use_hd),
+                                       self.dist_mode)
