@@ -13,7 +13,10 @@
 #include "api_internal.h"
 #include "smpl_internal.h"
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
+#include <cstdlib>
 
 namespace tuch {
 
@@ -92,12 +95,29 @@ constexpr int POSE_WARPS = 4;
 __global__ void __launch_bounds__(POSE_WARPS * 32)
 lbs_pose_kernel(SmplDev m, const float* __restrict__ betas, const float* __restrict__ pose, int pose_is_rotmat,
                 int B, float* __restrict__ Rout, float* __restrict__ Jrest, float* __restrict__ G,
-                float* __restrict__ A, float* __restrict__ pf) {
+                float* __restrict__ A, float* __restrict__ pf, uint16_t* __restrict__ featop) {
     __shared__ float sG[POSE_WARPS][24][12];
     __shared__ float sJ[POSE_WARPS][24][3];
     const int w = threadIdx.x / 32, lane = threadIdx.x & 31;
     const int b = blockIdx.x * POSE_WARPS + w;
     const bool act = (b < B) && lane < 24;
+    // feature operand of lbs_tc.cu: feature k of body b as three bf16 terms at
+    // [b / 128][k / 16][term][(k % 16) / 8][b % 128][k % 8]; rows past the batch and the K padding are zero
+    auto put_feature = [&](int k, float a) {
+        const size_t base = ((size_t)(b / LBS_TC_NB) * LBS_TC_KSTEPS + k / 16) * 3;
+        const size_t tail = ((size_t)((k % 16) / 8) * LBS_TC_NB + b % LBS_TC_NB) * 8 + k % 8;
+        float rem = a;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+            rem -= __bfloat162float(h);
+            featop[(base + p) * 2 * LBS_TC_NB * 8 + tail] = __bfloat16_as_ushort(h);
+        }
+    };
+    if (featop != nullptr && b >= B) {                   // padding bodies of the last 128-body tile
+        for (int k = lane; k < LBS_TC_K; k += 32) put_feature(k, 0.f);
+        return;
+    }
     float R[9], J[3] = {0.f, 0.f, 0.f}, Gk[12];
     if (act) {
         if (pose_is_rotmat) {
@@ -120,9 +140,15 @@ lbs_pose_kernel(SmplDev m, const float* __restrict__ betas, const float* __restr
         if (lane >= 1) {
             float* o = pf + (size_t)b * 207 + (lane - 1) * 9;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) o[i] = R[i] - ((i == 0 || i == 4 || i == 8) ? 1.f : 0.f);
+            for (int i = 0; i < 9; ++i) {
+                const float f = R[i] - ((i == 0 || i == 4 || i == 8) ? 1.f : 0.f);
+                o[i] = f;
+                if (featop != nullptr) put_feature((lane - 1) * 9 + i, f);
+            }
         }
     }
+    if (featop != nullptr && b < B)                      // betas, then the K padding
+        for (int k = 207 + lane; k < LBS_TC_K; k += 32) put_feature(k, k - 207 < m.L ? betas[(size_t)b * m.L + (k - 207)] : 0.f);
     const int par = lane < 24 ? m.parents[lane] : -1;
     const int dep = lane < 24 ? m.depth[lane] : -1;
     if (act) { sJ[w][lane][0] = J[0]; sJ[w][lane][1] = J[1]; sJ[w][lane][2] = J[2]; }
@@ -650,12 +676,21 @@ int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, 
                        const LbsBuffers& w, float* verts, float* joints, cudaStream_t st) {
     if (B == 0) return 0;
     KernelTimer timer("lbs_forward_kernels", st);
-    lbs_pose_kernel<<<cdiv(B, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(m, betas, pose, pose_is_rotmat, B, w.R, w.Jrest,
-                                                                   w.G, w.A, w.pf);
+    // blend shapes + skinning: the tcgen05 kernel (lbs_tc.cu) whenever the model fits its operand layout;
+    // TUCH_LBS_FFMA=1 keeps the CUDA-core kernel for A/B measurements
+    static const bool force_ffma = getenv("TUCH_LBS_FFMA") != nullptr && atoi(getenv("TUCH_LBS_FFMA")) != 0;
+    const bool tc = m.tc_model != nullptr && !force_ffma;
+    const int Bp = tc ? cdiv(B, LBS_TC_NB) * LBS_TC_NB : B;           // the pose kernel zero-fills the padding rows
+    lbs_pose_kernel<<<cdiv(Bp, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(m, betas, pose, pose_is_rotmat, B, w.R, w.Jrest,
+                                                                    w.G, w.A, w.pf, tc ? w.featop : nullptr);
     TUCH_LAUNCH_CHECK(); count_launch();
-    dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
-    lbs_skin_kernel<<<grid, LBS_VT, 0, st>>>(m, betas, w.pf, w.A, B, verts, w.v_posed);
-    TUCH_LAUNCH_CHECK(); count_launch();
+    if (tc) {
+        if (int rc = launch_lbs_skin_tc(m, w.featop, w.A, B, verts, w.v_posed, st)) return rc;
+    } else {
+        dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
+        lbs_skin_kernel<<<grid, LBS_VT, 0, st>>>(m, betas, w.pf, w.A, B, verts, w.v_posed);
+        TUCH_LAUNCH_CHECK(); count_launch();
+    }
     if (joints != nullptr) {
         lbs_joints_kernel<<<B, JOINT_THREADS, 0, st>>>(m, verts, w.G, joints);
         TUCH_LAUNCH_CHECK(); count_launch();

@@ -7,14 +7,18 @@
 
 namespace tuch {
 
-size_t lbs_buffer_floats(int V, int L) {
-    // R 216 | Jrest 72 | G 288 | A 288 | pf 207(->208) | g_pf 208 | gA 288 | g_beta_vert L(->32) | 3 x V*3
-    return 216 + 72 + 288 + 288 + 208 + 208 + 288 + SMPL_MAX_BETAS + 3 * (size_t)V * 3;
+size_t lbs_workspace_floats(int V, int L, int B) {
+    (void)L;
+    // feature operand (whole 128-body tiles, first: cp.async.bulk needs 16-byte alignment) |
+    // per body: R 216 | Jrest 72 | G 288 | A 288 | pf 207(->208) | g_pf 208 | gA 288 | g_beta_vert L(->32) | 3 x V*3
+    const size_t per_body = 216 + 72 + 288 + 288 + 208 + 208 + 288 + SMPL_MAX_BETAS + 3 * (size_t)V * 3;
+    return (size_t)cdiv(B, LBS_TC_NB) * (LBS_TC_FEAT_BYTES_PER_TILE / 4) + per_body * (size_t)B;
 }
 
 void lbs_carve(float* base, int B, int V, int L, LbsBuffers& w) {
     (void)L;
-    float* p = base;
+    w.featop = reinterpret_cast<uint16_t*>(base);
+    float* p = base + (size_t)cdiv(B, LBS_TC_NB) * (LBS_TC_FEAT_BYTES_PER_TILE / 4);
     auto take = [&](size_t per_body) { float* r = p; p += per_body * (size_t)B; return r; };
     w.R = take(216); w.Jrest = take(72); w.G = take(288); w.A = take(288);
     w.pf = take(208); w.g_pf = take(208); w.gA = take(288); w.g_beta_vert = take(SMPL_MAX_BETAS);
@@ -139,6 +143,12 @@ TUCH_EXPORT int tuch_smpl_create(int V, int L, const float* v_template, const fl
     }
     d.K = K;
     int rc = 0;
+    d.tc_model = nullptr;
+    if (K <= LBS_TC_MAXK && 207 + L <= LBS_TC_K) {
+        std::vector<uint16_t> blob;
+        lbs_tc_pack_model(V, L, shapedirs, posedirs, blob);
+        rc = to_device(s, blob, &d.tc_model);
+    }
     rc = rc ? rc : to_device(s, std::vector<float>(v_template, v_template + V3), &d.v_template);
     rc = rc ? rc : to_device(s, ST, &d.shapedirsT);
     rc = rc ? rc : to_device(s, std::vector<float>(posedirs, posedirs + 207 * V3), &d.posedirs);
@@ -173,7 +183,7 @@ TUCH_EXPORT int tuch_smpl_num_joints(const tuch_smpl* s) { return s ? s->dev.NO 
 
 TUCH_EXPORT size_t tuch_smpl_workspace_floats(const tuch_smpl* s, int B) {
     if (!s || B <= 0) return 0;
-    return lbs_buffer_floats(s->dev.V, s->dev.L) * (size_t)B;
+    return lbs_workspace_floats(s->dev.V, s->dev.L, B);
 }
 
 TUCH_EXPORT int tuch_smpl_forward(const tuch_smpl* s, const float* betas, const float* pose, int pose_is_rotmat,
@@ -182,6 +192,7 @@ TUCH_EXPORT int tuch_smpl_forward(const tuch_smpl* s, const float* betas, const 
     TUCH_REQUIRE(B >= 0, "tuch_smpl_forward: negative batch");
     if (B == 0) return 0;
     TUCH_REQUIRE(betas && pose && workspace && vertices, "tuch_smpl_forward: null pointer");
+    TUCH_REQUIRE(((uintptr_t)workspace & 15) == 0, "tuch_smpl_forward: the workspace must be 16-byte aligned");
     LbsBuffers w;
     lbs_carve(workspace, B, s->dev.V, s->dev.L, w);
     return launch_lbs_forward(s->dev, betas, pose, pose_is_rotmat, B, w, vertices, joints, (cudaStream_t)stream);

@@ -9,6 +9,11 @@ namespace tuch {
 constexpr int SMPL_MAX_BETAS = 32;
 constexpr int SMPL_MAX_JOINTS54 = 64;   // 24 posed + picked vertices + regressed extras
 
+// tcgen05 blend-shape GEMM + skinning (lbs_tc.cu): tile = 128 vertices x up to 128 bodies, K = 224 = 14 k-steps of 16
+// (207 pose features + up to 17 betas, zero padded), every fp32 operand as three bf16 terms
+constexpr int LBS_TC_M = 128, LBS_TC_NB = 128, LBS_TC_KSTEPS = 14, LBS_TC_K = 16 * LBS_TC_KSTEPS, LBS_TC_MAXK = 8;
+constexpr size_t LBS_TC_FEAT_BYTES_PER_TILE = (size_t)LBS_TC_KSTEPS * 3 * 2 * LBS_TC_NB * 16;   // 172,032 per 128 bodies
+
 // POD passed by value to the LBS kernels (all pointers are device pointers)
 struct SmplDev {
     int V, L, K, NX, NE, NO;
@@ -32,6 +37,7 @@ struct SmplDev {
     const float* vj_w;
     const int* extra_vertex_ids;  // [NX]
     const int* joint_map;         // [NO]
+    const uint16_t* tc_model;     // bf16 x 3 model operand of lbs_tc.cu, or NULL (K > LBS_TC_MAXK or L > 17)
 };
 
 // per-batch intermediates kept for the backward pass (all [B, ...])
@@ -40,10 +46,14 @@ struct LbsBuffers {
     float *v_posed;                         // [V*3]
     float *g_comb, *g_vposed;               // [V*3] backward scratch
     float *g_pf, *g_beta_vert, *gA;         // [207] [L] [24*12]
+    uint16_t* featop;                       // feature operand of lbs_tc.cu: [ceil(B/128)][14][3][2][128][8] bf16
 };
 
-size_t lbs_buffer_floats(int V, int L);     // floats per body
+size_t lbs_workspace_floats(int V, int L, int B);     // whole workspace of a batch
 void lbs_carve(float* base, int B, int V, int L, LbsBuffers& w);
+void lbs_tc_pack_model(int V, int L, const float* shapedirs, const float* posedirs, std::vector<uint16_t>& blob);
+int launch_lbs_skin_tc(const SmplDev& m, const uint16_t* featop, const float* A, int B, float* verts, float* v_posed,
+                       cudaStream_t st);
 
 int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, int pose_is_rotmat, int B,
                        const LbsBuffers& w, float* verts, float* joints, cudaStream_t st);
