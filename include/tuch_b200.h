@@ -278,6 +278,53 @@ int tuch_region_sum(const float* verts, int B, int V, int n_pairs, const float* 
 int tuch_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                    int32_t* step_dev, double lr, double beta1, double beta2, double eps, void* stream);
 
+/* ------------------------------------------------------------------ a10  SMPLify-DC stage-2 iteration
+ * tuch/smplify/smplifydc.py:155-183, ONE call per iteration for the whole batch:
+ *     smpl_output = self.smpl(global_orient, body_pose, betas)            (:157-160)  tuch_smpl_forward
+ *     loss = contact_fitting_loss(...)                                      (:162-180)  losses.py:34-123
+ *     body_optimizer.zero_grad(); loss.backward(); body_optimizer.step()    (:181-183)  torch.optim.Adam
+ * ~27 kernel launches on `stream`, no host synchronisation; bit-identical to composing tuch_smpl_forward,
+ * tuch_reprojection_loss, tuch_pose_terms, tuch_contact_query, tuch_contact_loss, tuch_region_min / _sum,
+ * tuch_smpl_backward and tuch_adam_step, whose kernels it launches -- minus the pose concatenation, the gradient
+ * round trips and the separate Adam launches: the vertex / joint gradients feed the LBS backward directly and Adam
+ * runs in the epilogue of its last kernel.  All pointers are DEVICE pointers.  Capturable into a CUDA graph after
+ * one warm-up call at the same batch size. */
+typedef struct tuch_contact_fit_args {
+    /* parameters and torch.optim.Adam state (lr, betas, eps below), all updated in place */
+    float* body_pose;            /* [B,69] */
+    float* global_orient;        /* [B,3]  */
+    float* exp_avg_pose;         /* [B,69] */
+    float* exp_avg_sq_pose;      /* [B,69] */
+    float* exp_avg_orient;       /* [B,3]  */
+    float* exp_avg_sq_orient;    /* [B,3]  */
+    int32_t* step_pose;          /* device scalars: steps taken so far, incremented by the call */
+    int32_t* step_orient;
+    /* fixed inputs of the stage (losses.py:34-41) */
+    const float* betas;          /* [B,L]   */
+    const float* camera_t;       /* [B,3]   */
+    const float* camera_center;  /* [B,2]   */
+    const float* joints_2d;      /* [B,J,2] */
+    const float* joints_conf;    /* [B,J]   */
+    const uint8_t* body_active;  /* [B] or NULL: ~ignore_idxs (losses.py:73) */
+    const uint8_t* pair_active;  /* [B,n_pairs] or NULL: gt_contact == 1 & has_discrete_contact & ~ignore (:109-112) */
+    /* outputs */
+    float* smpl_workspace;       /* tuch_smpl_workspace_floats(smpl, B) floats, 16-byte aligned */
+    float* vertices;             /* [B,V,3] of THIS iteration's forward (before the parameter update) */
+    float* joints;               /* [B,J,3] */
+    float* loss;                 /* scalar: the objective summed over the batch (losses.py:123) */
+    float* per_body;             /* [B] or NULL */
+    uint8_t* exterior;           /* [B,V] or NULL */
+    int32_t* argmin;             /* [B,V] or NULL */
+    float* grad_body_pose;       /* [B,69] or NULL: the gradients Adam consumed (both or neither) */
+    float* grad_global_orient;   /* [B,3]  or NULL */
+    /* configuration */
+    float euclthres, focal_length, sigma, pose_prior_weight, contact_loss_weight;
+    int use_segments;
+    double lr, beta1, beta2, eps;
+} tuch_contact_fit_args;
+int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology* topo, const tuch_prior* prior, int B,
+                          const tuch_contact_fit_args* args, void* stream);
+
 /* ------------------------------------------------------------------ a12  RegressorLoss.contact_loss
  * tuch/train/loss.py:240-317.  The HD-point regressor (loss.py:81-83 loads it as a dense [N_hd, V]
  * matrix) is handed over in CSR form (HOST arrays, copied) together with faces_vert_is_sampled_from

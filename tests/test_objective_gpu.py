@@ -381,6 +381,55 @@ def test_contact_fit_cuda_graph_replay_equals_eager(ctx):
     assert le1 == lg1 and torch.equal(eager1.body_pose.detach(), graph.body_pose.detach())
 
 
+@pytest.mark.parametrize('ignore', [False, True])
+def test_fused_iteration_equals_term_by_term_composition(ctx, ignore):
+    """tuch_contact_fit_step (one C-ABI call per iteration: SMPL forward, contact_fitting_loss, backward, Adam in the
+    backward's last kernel) against the same iteration composed term by term through torch autograd and the separate
+    Adam kernel: bit-identical parameters, vertices and flags after every iteration, eager and as a CUDA graph."""
+    from tuch_b200 import synthetic as syn
+    from tuch_b200.smplify.smplifydc import SMPLifyDC
+    g = ctx['g']
+    ign = [syn.JOINT_IDS[n] for n in syn.IGN_JOINTS]
+    opt = SMPLifyDC(step_size=1e-2, batch_size=3, num_iters=5, focal_length=5000.0, geodistssmpl=ctx['geod'],
+                    geothres=float(g['geothres']), euclthres=0.02, device=torch.device(DEV),
+                    smpl=ctx['smpl'], pose_prior=ctx['prior'], ign_joints=ign)
+    ignore_idxs = torch.tensor([False, ignore, False], device=DEV)
+
+    def begin(native):
+        pose = t(g['init_pose'])
+        kp = t(g['keypoints_2d'])
+        conf = kp[:, :, 2].clone()
+        conf[:, ign] = 0.0
+        return opt.begin_contact_fit(pose[:, 3:].clone(), pose[:, :3].clone(), t(g['init_betas']), t(g['init_cam_t']),
+                                     t(g['camera_center']), kp[:, :, :2].contiguous(), conf, ctx['a']['regions'],
+                                     [t(g['gt_contact']), None], ignore_idxs.clone(), t(g['has_discrete_contact']), 2000.0,
+                                     'sum', ctx['segments'], native=native)
+    ref, fused, graphed = begin(False), begin(True), begin(True).capture()
+    assert fused.native and graphed.native and not ref.native
+    for it in range(5):
+        lr, lf, lg = float(ref.step()), float(fused.step()), float(graphed.step())
+        assert abs(lf - lr) <= 1e-6 * abs(lr) and lf == lg, (it, lr, lf, lg)         # the batch sum is reduced in another order
+        for other in (fused, graphed):
+            assert torch.equal(ref.body_pose.detach(), other.body_pose.detach()), it
+            assert torch.equal(ref.global_orient.detach(), other.global_orient.detach()), it
+            assert torch.equal(ref.vertices.detach(), other.vertices), it
+    assert int(fused.state.step_pose) == 5 and int(fused.state.step_orient) == 5
+    # __call__ end to end: fused (default) against the autograd composition
+    outs = []
+    for native in (True, False):
+        o = SMPLifyDC(step_size=1e-2, batch_size=3, num_iters=4, focal_length=5000.0, geodistssmpl=ctx['geod'],
+                      geothres=float(g['geothres']), euclthres=0.02, device=torch.device(DEV), smpl=ctx['smpl'],
+                      pose_prior=ctx['prior'], ign_joints=ign, native_step=native)
+        outs.append(o(t(g['init_pose']), t(g['init_betas']), t(g['init_cam_t']), t(g['camera_center']), t(g['keypoints_2d']),
+                      use_contact=True, contactlist=ctx['a']['regions'], gt_contact=[t(g['gt_contact']), None],
+                      ignore_idxs=ignore_idxs.clone(), has_discrete_contact=t(g['has_discrete_contact']),
+                      has_gt_keypoints=torch.tensor([True, False, False], device=DEV), contact_loss_weight=2000.0,
+                      contact_loss_return='sum', segments=ctx['segments']))
+    for x, y in zip(outs[0][:6], outs[1][:6]):
+        assert torch.equal(x, y)
+    assert len(outs[0][6]) == 4 and all(torch.equal(x, y) for x, y in zip(outs[0][6], outs[1][6]))
+
+
 def test_captured_graph_survives_scratch_growth_and_release(ctx):
     """A graph captured at a small batch keeps working after (i) a later, larger capture on the same stream has
     made the library's scratch arena grow -- the block the first graph points at is retired, not freed -- and

@@ -14,6 +14,18 @@ class TuchError(RuntimeError):
     pass
 
 
+class ContactFitArgs(C.Structure):
+    """tuch_contact_fit_args of include/tuch_b200.h (field for field)."""
+    _fields_ = ([(n, C.c_void_p) for n in (
+        'body_pose', 'global_orient', 'exp_avg_pose', 'exp_avg_sq_pose', 'exp_avg_orient', 'exp_avg_sq_orient',
+        'step_pose', 'step_orient', 'betas', 'camera_t', 'camera_center', 'joints_2d', 'joints_conf', 'body_active',
+        'pair_active', 'smpl_workspace', 'vertices', 'joints', 'loss', 'per_body', 'exterior', 'argmin',
+        'grad_body_pose', 'grad_global_orient')]
+        + [(n, C.c_float) for n in ('euclthres', 'focal_length', 'sigma', 'pose_prior_weight', 'contact_loss_weight')]
+        + [('use_segments', C.c_int)]
+        + [(n, C.c_double) for n in ('lr', 'beta1', 'beta2', 'eps')])
+
+
 def _declare(lib):
     vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
     lib.tuch_last_error.restype = C.c_char_p
@@ -67,6 +79,7 @@ def _declare(lib):
     lib.tuch_pose_terms.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp]
     lib.tuch_contact_loss.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, vp, vp, vp]
     lib.tuch_region_sum.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp]
+    lib.tuch_contact_fit_step.argtypes = [vp, vp, vp, i32, C.POINTER(ContactFitArgs), vp]
     lib.tuch_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
     lib.tuch_topology_set_hd.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.tuch_topology_num_hd.argtypes = [vp]

@@ -1,0 +1,109 @@
+// C ABI: one whole SMPLify-DC stage-2 iteration (tuch/smplify/smplifydc.py:155-183) as ONE call.
+//
+//   SMPL forward -> contact_fitting_loss (losses.py:34-123) -> backward -> torch.optim.Adam on [body_pose, global_orient]
+//
+// The reference spends ~80 ATen launches per BODY on it plus autograd's bookkeeping and Adam's per-parameter loop.
+// Here the whole batch is ~27 kernel launches on the caller's stream, no host synchronisation and nothing but our
+// kernels: the values and analytic gradients of every term come out of the same kernels the per-term entry points
+// use (so the iteration is bit-identical to composing those), the vertex / joint gradients go straight into the
+// LBS backward, and Adam runs in the epilogue of its last kernel.  Scratch comes from the grow-only arenas, so
+// after one warm-up call the step can be captured into a CUDA graph.
+#include "api_internal.h"
+#include "objective_internal.h"
+#include "smpl_internal.h"
+
+using namespace tuch;
+
+TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology* topo, const tuch_prior* prior, int B,
+                                      const tuch_contact_fit_args* a, void* stream) {
+    TUCH_REQUIRE(smpl != nullptr && topo != nullptr && a != nullptr, "tuch_contact_fit_step: null handle");
+    TUCH_REQUIRE(B >= 0, "tuch_contact_fit_step: negative batch");
+    if (B == 0) return 0;
+    TUCH_REQUIRE(B <= 65535, "tuch_contact_fit_step: at most 65535 bodies per call, got %d", B);
+    const SmplDev& m = smpl->dev;
+    const int V = m.V, J = m.NO, P = topo->n_pairs;
+    TUCH_REQUIRE(topo->V == V, "tuch_contact_fit_step: the topology has %d vertices, the body model %d", topo->V, V);
+    TUCH_REQUIRE(topo->has_mask && topo->F > 0, "tuch_contact_fit_step: the topology needs faces and a geodesic mask");
+    TUCH_REQUIRE(a->body_pose && a->global_orient && a->exp_avg_pose && a->exp_avg_sq_pose && a->exp_avg_orient &&
+                     a->exp_avg_sq_orient && a->step_pose && a->step_orient,
+                 "tuch_contact_fit_step: null parameter / optimiser-state pointer");
+    TUCH_REQUIRE(a->betas && a->camera_t && a->camera_center && a->joints_2d && a->joints_conf,
+                 "tuch_contact_fit_step: null input pointer");
+    TUCH_REQUIRE(a->smpl_workspace && a->vertices && a->joints && a->loss, "tuch_contact_fit_step: null output pointer");
+    TUCH_REQUIRE(((uintptr_t)a->smpl_workspace & 15) == 0, "tuch_contact_fit_step: the SMPL workspace must be 16-byte aligned");
+    TUCH_REQUIRE(prior == nullptr || prior->D == 69, "tuch_contact_fit_step: the pose prior must be over 69 pose entries");
+    TUCH_REQUIRE(a->pair_active == nullptr || P > 0, "tuch_contact_fit_step: pair_active given but the topology has no region pairs");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t BV = (size_t)B * V;
+
+    Scratch sc;
+    const size_t h_rep = sc.plan(sizeof(float) * (size_t)B * J), h_gj = sc.plan(sizeof(float) * 3 * (size_t)B * J);
+    const size_t h_val = sc.plan(sizeof(float) * B), h_pv = sc.plan(sizeof(float) * B), h_cmp = sc.plan(sizeof(int) * B);
+    const size_t h_gp = sc.plan(sizeof(float) * (size_t)B * 69);
+    const size_t h_con = sc.plan(sizeof(float) * B), h_r2r = sc.plan(sizeof(float) * B);
+    const size_t h_mn = sc.plan(sizeof(float) * (size_t)B * (P > 0 ? P : 1));
+    const size_t h_ai = sc.plan(sizeof(int) * (size_t)B * (P > 0 ? P : 1)), h_aj = sc.plan(sizeof(int) * (size_t)B * (P > 0 ? P : 1));
+    const size_t h_gv = sc.plan(sizeof(float) * 3 * BV);
+    const size_t h_am = sc.plan(a->argmin ? 0 : sizeof(int) * BV), h_ex = sc.plan(a->exterior ? 0 : BV);
+    const size_t h_v4 = sc.plan(a->pair_active ? sizeof(float4) * (size_t)B * topo->Vp : 0);
+    if (int rc = sc.commit_slot(st, 4)) return rc;
+    float* rep = sc.get<float>(h_rep);
+    float* g_joints = sc.get<float>(h_gj);
+    float* g_prior = sc.get<float>(h_gp);
+    float* contact = sc.get<float>(h_con);
+    float* r2r = sc.get<float>(h_r2r);
+    float* g_verts = sc.get<float>(h_gv);
+    int* am = a->argmin ? a->argmin : sc.get<int>(h_am);
+    uint8_t* ext = a->exterior ? a->exterior : sc.get<uint8_t>(h_ex);
+
+    // ---- SMPL forward (split pose; advances the Adam step counters)
+    LbsBuffers w;
+    lbs_carve(a->smpl_workspace, B, V, m.L, w);
+    if (int rc = launch_lbs_forward(m, a->betas, a->body_pose, 0, B, w, a->vertices, a->joints, st, a->global_orient,
+                                    a->step_pose, a->step_orient)) return rc;
+    // ---- losses.py:56-64: reprojection and pose prior, with their gradients
+    if (int rc = launch_reprojection(a->joints, a->camera_t, a->camera_center, a->joints_2d, a->joints_conf, B, J,
+                                     a->focal_length, a->sigma, nullptr, 0.f, nullptr, rep, nullptr, g_joints, nullptr, st)) return rc;
+    const float wp = a->pose_prior_weight * a->pose_prior_weight;
+    const bool with_prior = prior != nullptr && wp != 0.f;
+    if (with_prior)
+        if (int rc = launch_pose_terms(prior->d_means, prior->d_precisions, prior->d_nll_weights, prior->M, 69, a->body_pose,
+                                       nullptr, 0, B, wp, 0.f, 0.f, sc.get<float>(h_val), sc.get<float>(h_pv),
+                                       sc.get<int>(h_cmp), g_prior, nullptr, st)) return rc;
+    // ---- losses.py:73-105: inside test, allowed self-intersections, masked nearest vertex, push / pull
+    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, st)) return rc;
+    TUCH_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * BV, st));
+    if (int rc = launch_contact_loss(a->vertices, am, ext, a->body_active, nullptr, B, V, a->euclthres, PULL_THRESHOLD,
+                                     REDUCE_SUM, 10.f, nullptr, contact, nullptr, g_verts, st)) return rc;
+    // ---- losses.py:108-117: region-to-region minima of the annotated pairs
+    const bool with_r2r = a->pair_active != nullptr && P > 0;
+    if (with_r2r) {
+        float* mn = sc.get<float>(h_mn);
+        int* ai = sc.get<int>(h_ai);
+        int* aj = sc.get<int>(h_aj);
+        float4* v4 = sc.get<float4>(h_v4);
+        TUCH_CUDA(cudaMemsetAsync(mn, 0, sizeof(float) * (size_t)B * P, st));
+        TUCH_CUDA(cudaMemsetAsync(ai, 0xff, sizeof(int) * (size_t)B * P, st));
+        TUCH_CUDA(cudaMemsetAsync(aj, 0xff, sizeof(int) * (size_t)B * P, st));
+        if (int rc = launch_pack_mesh(a->vertices, topo->d_faces, B, V, topo->F, topo->Fp, topo->Vp, nullptr, v4, st)) return rc;
+        if (int rc = launch_region_min(v4, topo->Vp, topo->d_maskT, topo->Vq, topo->d_region_ids, topo->d_region_off,
+                                       topo->d_pair_a, topo->d_pair_b, a->pair_active, P, B,
+                                       topo->has_pair_mask ? topo->d_pair_mask : nullptr, topo->d_pair_word_off, mn, ai, aj, st)) return rc;
+        if (int rc = launch_region_sum(a->vertices, B, V, P, mn, ai, aj, a->body_active, a->contact_loss_weight, nullptr, r2r,
+                                       g_verts, st)) return rc;
+    }
+    // ---- losses.py:120-123: per-body totals and their sum
+    if (int rc = launch_combine(rep, J, with_prior ? sc.get<float>(h_val) : nullptr, contact, 10.f, with_r2r ? r2r : nullptr,
+                                a->contact_loss_weight, nullptr, B, a->per_body, a->loss, st)) return rc;
+    // ---- backward through the SMPL forward; Adam on [body_pose, global_orient] in its last kernel
+    LbsAdam ad;
+    ad.body_pose = a->body_pose; ad.global_orient = a->global_orient;
+    ad.m_pose = a->exp_avg_pose; ad.v_pose = a->exp_avg_sq_pose; ad.m_orient = a->exp_avg_orient; ad.v_orient = a->exp_avg_sq_orient;
+    ad.step_pose = a->step_pose; ad.step_orient = a->step_orient;
+    ad.g_extra_pose = with_prior ? g_prior : nullptr;
+    ad.g_out_pose = a->grad_body_pose; ad.g_out_orient = a->grad_global_orient;
+    ad.lr = a->lr; ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->eps;
+    TUCH_REQUIRE((a->grad_body_pose == nullptr) == (a->grad_global_orient == nullptr),
+                 "tuch_contact_fit_step: give both gradient outputs or neither");
+    return launch_lbs_backward(m, a->body_pose, 0, B, w, g_verts, g_joints, nullptr, nullptr, st, &ad);
+}

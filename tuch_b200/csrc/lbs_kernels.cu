@@ -93,14 +93,24 @@ __device__ __forceinline__ void rodrigues_bwd(const float* r, const float* gR, f
 constexpr int POSE_WARPS = 4;
 
 __global__ void __launch_bounds__(POSE_WARPS * 32)
-lbs_pose_kernel(SmplDev m, const float* __restrict__ betas, const float* __restrict__ pose, int pose_is_rotmat,
+lbs_pose_kernel(SmplDev m, const float* __restrict__ betas, const float* __restrict__ pose,
+                const float* __restrict__ orient, int pose_is_rotmat,
                 int B, float* __restrict__ Rout, float* __restrict__ Jrest, float* __restrict__ G,
-                float* __restrict__ A, float* __restrict__ pf, uint16_t* __restrict__ featop) {
+                float* __restrict__ A, float* __restrict__ pf, uint16_t* __restrict__ featop, int* __restrict__ step_a,
+                int* __restrict__ step_b) {
+    // `orient` != NULL: split axis-angle pose -- joint 0 from orient[B,3], joints 1..23 from pose[B,69]
+    // (the two parameter tensors of SMPLify-DC's stage 2, smplifydc.py:149) instead of one pose[B,72]
     __shared__ float sG[POSE_WARPS][24][12];
     __shared__ float sJ[POSE_WARPS][24][3];
     const int w = threadIdx.x / 32, lane = threadIdx.x & 31;
     const int b = blockIdx.x * POSE_WARPS + w;
     const bool act = (b < B) && lane < 24;
+    // the fused Adam step at the end of the iteration (lbs_bwd_chain_kernel) reads the step counters this first
+    // kernel of the iteration advances: stream order makes the increment visible to every later kernel
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (step_a != nullptr) *step_a += 1;
+        if (step_b != nullptr) *step_b += 1;
+    }
     // feature operand of lbs_tc.cu: feature k of body b as three bf16 terms at
     // [b / 128][k / 16][term][(k % 16) / 8][b % 128][k % 8]; rows past the batch and the K padding are zero
     auto put_feature = [&](int k, float a) {
@@ -123,6 +133,8 @@ lbs_pose_kernel(SmplDev m, const float* __restrict__ betas, const float* __restr
         if (pose_is_rotmat) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) R[i] = pose[((size_t)b * 24 + lane) * 9 + i];
+        } else if (orient != nullptr) {
+            rodrigues_fwd(lane == 0 ? orient + (size_t)b * 3 : pose + (size_t)b * 69 + (lane - 1) * 3, R);
         } else {
             rodrigues_fwd(pose + ((size_t)b * 24 + lane) * 3, R);
         }
@@ -548,7 +560,7 @@ lbs_bwd_chain_kernel(SmplDev m, const float* __restrict__ pose, int pose_is_rotm
                      const float* __restrict__ Jrest, const float* __restrict__ G, const float* __restrict__ gA,
                      const float* __restrict__ gJ49, const float* __restrict__ g_pf,
                      const float* __restrict__ g_beta_vert, int B, float* __restrict__ g_pose,
-                     float* __restrict__ g_betas) {
+                     float* __restrict__ g_betas, LbsAdam ad) {
     __shared__ float s_c3[POSE_WARPS][24][9];     // child -> parent contribution to gG3
     __shared__ float s_ct[POSE_WARPS][24][3];     // child -> parent contribution to gGt
     __shared__ float s_cj[POSE_WARPS][24][3];     // child -> parent contribution to gJ (= -gt_child)
@@ -654,6 +666,37 @@ lbs_bwd_chain_kernel(SmplDev m, const float* __restrict__ pose, int pose_is_rotm
                 g_pose[((size_t)b * 24 + lane) * 3 + 2] = gr[2];
             }
         }
+        if (ad.body_pose != nullptr) {
+            // SMPLify-DC stage 2 (smplifydc.py:149-183): the two parameter tensors are body_pose [B,69] and
+            // global_orient [B,3]; this lane owns joint `lane`, i.e. three entries of one of them.  The gradient
+            // is the chain's plus the pose-prior term's; torch.optim.Adam follows in place, no g_pose round trip.
+            float* prm = lane == 0 ? ad.global_orient + (size_t)b * 3 : ad.body_pose + (size_t)b * 69 + (lane - 1) * 3;
+            float* mm = lane == 0 ? ad.m_orient + (size_t)b * 3 : ad.m_pose + (size_t)b * 69 + (lane - 1) * 3;
+            float* vv = lane == 0 ? ad.v_orient + (size_t)b * 3 : ad.v_pose + (size_t)b * 69 + (lane - 1) * 3;
+            float gr[3];
+            rodrigues_bwd(prm, gR, gr);
+            if (lane >= 1 && ad.g_extra_pose != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gr[c] += ad.g_extra_pose[(size_t)b * 69 + (lane - 1) * 3 + c];
+            }
+            const int t = lane == 0 ? *ad.step_orient : *ad.step_pose;       // already advanced by lbs_pose_kernel
+            const float w1 = (float)(1.0 - ad.beta1), b2 = (float)ad.beta2, w2 = (float)(1.0 - ad.beta2);
+            const double bc1 = 1.0 - pow(ad.beta1, (double)t);
+            const double bc2 = 1.0 - pow(ad.beta2, (double)t);
+            const float sq2 = (float)sqrt(bc2), eps = (float)ad.eps, lr1 = -(float)(ad.lr / bc1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float g = gr[c];
+                if (ad.g_out_pose != nullptr) {
+                    if (lane == 0) ad.g_out_orient[(size_t)b * 3 + c] = g; else ad.g_out_pose[(size_t)b * 69 + (lane - 1) * 3 + c] = g;
+                }
+                const float mi = fmaf(w1, g - mm[c], mm[c]);
+                const float vi = fmaf(w2, g * g, b2 * vv[c]);
+                mm[c] = mi; vv[c] = vi;
+                const float denom = sqrtf(vi) / sq2 + eps;
+                prm[c] = fmaf(lr1, mi / denom, prm[c]);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) s_gJ[w][lane][c] = gJ[c];
     }
@@ -673,7 +716,8 @@ lbs_bwd_chain_kernel(SmplDev m, const float* __restrict__ pose, int pose_is_rotm
 // host launchers
 // ------------------------------------------------------------------------------------------
 int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, int pose_is_rotmat, int B,
-                       const LbsBuffers& w, float* verts, float* joints, cudaStream_t st) {
+                       const LbsBuffers& w, float* verts, float* joints, cudaStream_t st, const float* orient,
+                       int* step_a, int* step_b) {
     if (B == 0) return 0;
     KernelTimer timer("lbs_forward_kernels", st);
     // blend shapes + skinning: the tcgen05 kernel (lbs_tc.cu) whenever the model fits its operand layout;
@@ -681,8 +725,8 @@ int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, 
     static const bool force_ffma = getenv("TUCH_LBS_FFMA") != nullptr && atoi(getenv("TUCH_LBS_FFMA")) != 0;
     const bool tc = m.tc_model != nullptr && !force_ffma;
     const int Bp = tc ? cdiv(B, LBS_TC_NB) * LBS_TC_NB : B;           // the pose kernel zero-fills the padding rows
-    lbs_pose_kernel<<<cdiv(Bp, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(m, betas, pose, pose_is_rotmat, B, w.R, w.Jrest,
-                                                                    w.G, w.A, w.pf, tc ? w.featop : nullptr);
+    lbs_pose_kernel<<<cdiv(Bp, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(m, betas, pose, orient, pose_is_rotmat, B, w.R, w.Jrest,
+                                                                    w.G, w.A, w.pf, tc ? w.featop : nullptr, step_a, step_b);
     TUCH_LAUNCH_CHECK(); count_launch();
     if (tc) {
         if (int rc = launch_lbs_skin_tc(m, w.featop, w.A, B, verts, w.v_posed, st)) return rc;
@@ -699,19 +743,20 @@ int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, 
 }
 
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
-                        const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st) {
+                        const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st,
+                        const LbsAdam* adam) {
     if (B == 0) return 0;
     KernelTimer timer("lbs_backward_kernels", st);
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
     lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed);
     TUCH_LAUNCH_CHECK(); count_launch();
     {
-        // split K so that the grid fills the machine: tiles x splits >= ~3 CTAs per SM
-        const int tiles = cdiv(207, GT_R) * cdiv(B, GT_B);
-        int S = std::max(1, std::min(64, cdiv(6 * sm_count(), tiles)));
+        // split K into FIXED slabs of 352 coordinates (59 splits at SMPL size, >= 236 CTAs at any batch): the
+        // grouping of the partial sums must not depend on the batch size, or a body fitted in a shard of the batch
+        // (BASELINE config 4) would round differently from the same body fitted in the whole batch
         const int n_coords = m.V * 3;
-        int per = cdiv(cdiv(n_coords, S), GT_K) * GT_K;
-        S = cdiv(n_coords, per);
+        const int per = 11 * GT_K;
+        const int S = cdiv(n_coords, per);
         Scratch sc;
         const size_t h_part = sc.plan(sizeof(float) * (size_t)S * B * 207);
         if (int rc = sc.commit_slot(st, 2)) return rc;
@@ -731,7 +776,7 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     TUCH_LAUNCH_CHECK(); count_launch();
     lbs_bwd_chain_kernel<<<cdiv(B, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(
         m, pose, pose_is_rotmat, w.R, w.Jrest, w.G, w.gA, gJ49, w.g_pf, g_betas ? w.g_beta_vert : nullptr, B, g_pose,
-        g_betas);
+        g_betas, adam != nullptr ? *adam : LbsAdam{});
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

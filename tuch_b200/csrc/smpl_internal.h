@@ -49,16 +49,32 @@ struct LbsBuffers {
     uint16_t* featop;                       // feature operand of lbs_tc.cu: [ceil(B/128)][14][3][2][128][8] bf16
 };
 
+// torch.optim.Adam on SMPLify-DC's stage-2 parameters fused into the last kernel of the LBS backward
+// (lbs_bwd_chain_kernel); body_pose == NULL = off.  The step counters hold the step being taken: the first kernel
+// of the iteration (lbs_pose_kernel) advances them.
+struct LbsAdam {
+    float *body_pose = nullptr, *global_orient = nullptr;     // [B,69], [B,3] parameters, updated in place
+    float *m_pose = nullptr, *v_pose = nullptr, *m_orient = nullptr, *v_orient = nullptr;
+    const int *step_pose = nullptr, *step_orient = nullptr;
+    const float* g_extra_pose = nullptr;                       // optional [B,69] added to the body_pose gradient
+    float *g_out_pose = nullptr, *g_out_orient = nullptr;      // optional: the gradients Adam consumed
+    double lr = 0.0, beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
+};
+
 size_t lbs_workspace_floats(int V, int L, int B);     // whole workspace of a batch
 void lbs_carve(float* base, int B, int V, int L, LbsBuffers& w);
 void lbs_tc_pack_model(int V, int L, const float* shapedirs, const float* posedirs, std::vector<uint16_t>& blob);
 int launch_lbs_skin_tc(const SmplDev& m, const uint16_t* featop, const float* A, int B, float* verts, float* v_posed,
                        cudaStream_t st);
 
+// orient != NULL: split axis-angle pose (pose = body_pose [B,69], orient = global_orient [B,3]);
+// step_a / step_b: optional Adam step counters the first kernel advances (see LbsAdam)
 int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, int pose_is_rotmat, int B,
-                       const LbsBuffers& w, float* verts, float* joints, cudaStream_t st);
+                       const LbsBuffers& w, float* verts, float* joints, cudaStream_t st, const float* orient = nullptr,
+                       int* step_a = nullptr, int* step_b = nullptr);
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
-                        const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st);
+                        const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st,
+                        const LbsAdam* adam = nullptr);
 
 }  // namespace tuch
 

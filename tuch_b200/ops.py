@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import lib, check, TuchError
+from ._lib import lib, check, TuchError, ContactFitArgs
 
 
 def _stream():
@@ -623,6 +623,69 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr, beta1=0.9, beta2=0
         check(lib().tuch_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
                                    _ptr(step_dev), float(lr), float(beta1), float(beta2), float(eps), _stream()),
               'tuch_adam_step')
+
+
+class ContactFitState:
+    """The tensors of one SMPLify-DC stage-2 optimisation as tuch_contact_fit_step reads and writes them: the two
+    parameter tensors and their torch.optim.Adam state (updated in place), the fixed inputs, the outputs of the last
+    iteration.  step() enqueues ONE whole iteration (SMPL forward, contact_fitting_loss, backward, Adam) on the
+    current stream through a single C-ABI call -- no torch op takes part."""
+
+    def __init__(self, smpl, topo, prior, body_pose, global_orient, betas, camera_t, camera_center, joints_2d,
+                 joints_conf, body_active=None, pair_active=None, euclthres=0.0, focal_length=5000.0, sigma=100.0,
+                 pose_prior_weight=1.0, contact_loss_weight=1000.0, use_segments=True, lr=1e-2, betas_adam=(0.9, 0.999),
+                 eps=1e-8, keep_grads=False):
+        dev = body_pose.device
+        B = body_pose.shape[0]
+        self.smpl, self.topo, self.prior, self.B = smpl, topo, prior, B
+        for t, shape, name in ((body_pose, (B, 69), 'body_pose'), (global_orient, (B, 3), 'global_orient'),
+                               (betas, (B, smpl.L), 'betas'), (camera_t, (B, 3), 'camera_t'),
+                               (camera_center, (B, 2), 'camera_center'), (joints_2d, (B, smpl.NO, 2), 'joints_2d'),
+                               (joints_conf, (B, smpl.NO), 'joints_conf')):
+            _dev(t, name)
+            if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise TuchError('ContactFitState: %s must be a contiguous fp32 CUDA tensor %s, got %s %s'
+                                % (name, shape, t.dtype, tuple(t.shape)))
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)
+        self.body_pose, self.global_orient = body_pose, global_orient
+        self.exp_avg_pose, self.exp_avg_sq_pose = z(B, 69), z(B, 69)
+        self.exp_avg_orient, self.exp_avg_sq_orient = z(B, 3), z(B, 3)
+        self.step_pose, self.step_orient = z((), dt=torch.int32), z((), dt=torch.int32)
+        self.betas, self.camera_t, self.camera_center = betas, camera_t, camera_center
+        self.joints_2d, self.joints_conf = joints_2d, joints_conf
+        self.body_active = None if body_active is None else _dev(body_active, 'body_active').to(torch.uint8).contiguous()
+        self.pair_active = None if pair_active is None else _dev(pair_active, 'pair_active').to(torch.uint8).contiguous()
+        self.workspace = smpl.workspace(B)
+        self.vertices, self.joints = z(B, smpl.V, 3), z(B, smpl.NO, 3)
+        self.loss, self.per_body = z(()), z(B)
+        self.exterior, self.argmin = z(B, smpl.V, dt=torch.uint8), z(B, smpl.V, dt=torch.int32)
+        self.grad_body_pose = z(B, 69) if keep_grads else None
+        self.grad_global_orient = z(B, 3) if keep_grads else None
+        a = ContactFitArgs()
+        for n in ('body_pose', 'global_orient', 'exp_avg_pose', 'exp_avg_sq_pose', 'exp_avg_orient', 'exp_avg_sq_orient',
+                  'step_pose', 'step_orient', 'betas', 'camera_t', 'camera_center', 'joints_2d', 'joints_conf',
+                  'body_active', 'pair_active', 'vertices', 'joints', 'loss', 'per_body', 'exterior', 'argmin',
+                  'grad_body_pose', 'grad_global_orient'):
+            t = getattr(self, n)
+            setattr(a, n, t.data_ptr() if t is not None else None)
+        a.smpl_workspace = self.workspace.data_ptr()
+        a.euclthres, a.focal_length, a.sigma = float(euclthres), float(focal_length), float(sigma)
+        a.pose_prior_weight, a.contact_loss_weight = float(pose_prior_weight), float(contact_loss_weight)
+        a.use_segments = int(bool(use_segments))
+        a.lr, a.beta1, a.beta2, a.eps = float(lr), float(betas_adam[0]), float(betas_adam[1]), float(eps)
+        self._args = a
+
+    def step(self):
+        with torch.cuda.device(self.body_pose.device):
+            check(lib().tuch_contact_fit_step(self.smpl.handle, self.topo.handle,
+                                              self.prior.handle if self.prior is not None else None, self.B,
+                                              C.byref(self._args), _stream()), 'tuch_contact_fit_step')
+        return self.loss
+
+    def reset_optimizer(self):
+        for t in (self.exp_avg_pose, self.exp_avg_sq_pose, self.exp_avg_orient, self.exp_avg_sq_orient,
+                  self.step_pose, self.step_orient):
+            t.zero_()
 
 
 # ------------------------------------------------------------------ f2 / f3: camera + pose bookkeeping

@@ -137,22 +137,69 @@ class CameraFit:
         return self
 
 
+class _NativeOptState:
+    """What _capture_iteration saves and restores, for the fused iteration: the Adam state tensors of
+    ops.ContactFitState in torch.optim.Adam's (exp_avg, exp_avg_sq, step) order."""
+
+    def __init__(self, st):
+        self.state = [(st.exp_avg_pose, st.exp_avg_sq_pose, st.step_pose),
+                      (st.exp_avg_orient, st.exp_avg_sq_orient, st.step_orient)]
+
+    def zero_grad(self):
+        pass
+
+
 class ContactFit:
-    """One stage-2 optimisation in flight; see SMPLifyDC.begin_contact_fit."""
+    """One stage-2 optimisation in flight; see SMPLifyDC.begin_contact_fit.
+
+    With the product's own pose prior (MaxMixturePrior or none) and contiguous fp32 parameters the whole iteration
+    is ONE C-ABI call (tuch_contact_fit_step: SMPL forward, contact_fitting_loss, backward, Adam in the backward's
+    last kernel -- no torch op in the loop); otherwise (a foreign pose-prior callable) the same kernels are driven
+    through torch autograd, term by term.  Both give bit-identical parameters."""
 
     def __init__(self, owner, body_pose, global_orient, betas, camera_translation, camera_center, joints_2d,
                  joints_conf, contactlist, gt_contact, ignore_idxs, has_discrete_contact, contact_loss_weight,
-                 contact_loss_return, segments):
+                 contact_loss_return, segments, native=None):
         self.owner = owner
         self.body_pose, self.global_orient, self.betas = body_pose, global_orient, betas
-        self.loop1_pose, self.loop1_orient = body_pose.detach().clone(), global_orient.detach().clone()
-        body_pose.requires_grad_(True)
-        global_orient.requires_grad_(True)
-        self.opt = _Adam([body_pose, global_orient], lr=owner.step_size)
         self.topo = topology_for(owner.geomask, owner.face_tensor, owner.smpl.get_num_verts(), contactlist, segments)
         tmpl = getattr(owner.smpl, 'v_template', None)
         if tmpl is not None and self.topo.F > 0 and self.topo.cluster_stats()['leaves'] == 0:
             self.topo.set_template(tmpl)           # face clusters of the hierarchical winding kernel
+        can_native = (isinstance(owner.pose_prior, MaxMixturePrior) or owner.pose_prior is None) and all(
+            isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+            for t in (body_pose, global_orient, betas, camera_translation, camera_center, joints_2d, joints_conf))
+        self.native = can_native if native is None else (bool(native) and can_native)
+        self.state = None
+        if self.native:
+            dev = body_pose.device
+            B = body_pose.shape[0]
+            self._gt_l3 = gt_contact[0] if gt_contact is not None else None
+            self._has_dc, self._ignore = has_discrete_contact, ignore_idxs
+            self._pair_active = None
+            if self._gt_l3 is not None and has_discrete_contact is not None and len(self.topo.classes) > 0:
+                self._pair_active = torch.zeros(B, len(self.topo.classes), device=dev, dtype=torch.uint8)
+            self._body_active = torch.ones(B, device=dev, dtype=torch.uint8)
+            self.args = dict(camera_t=camera_translation, camera_center=camera_center, joints_2d=joints_2d,
+                             joints_conf=joints_conf, gt_contact=gt_contact, ignore_idxs=ignore_idxs,
+                             has_discrete_contact=has_discrete_contact)
+            self._refresh_masks()
+            prior = owner.pose_prior._handle(dev) if owner.pose_prior is not None else None
+            self.state = ops.ContactFitState(
+                owner.smpl._handle(dev), self.topo, prior, body_pose.detach(), global_orient.detach(), betas.detach(),
+                camera_translation.detach(), camera_center, joints_2d, joints_conf, body_active=self._body_active,
+                pair_active=self._pair_active, euclthres=owner.euclthres, focal_length=owner.focal_length,
+                pose_prior_weight=1.0, contact_loss_weight=contact_loss_weight,
+                use_segments=segments is not None or len(self.topo.segment_names) > 0, lr=owner.step_size)
+            # ContactFitState was built over these very tensors: the masks must stay the same objects
+            self.opt = _NativeOptState(self.state)
+            self.vertices, self.loss = self.state.vertices, self.state.loss
+            self._graph = None
+            return
+        self.loop1_pose, self.loop1_orient = body_pose.detach().clone(), global_orient.detach().clone()
+        body_pose.requires_grad_(True)
+        global_orient.requires_grad_(True)
+        self.opt = _Adam([body_pose, global_orient], lr=owner.step_size)
         self.args = dict(camera_t=camera_translation, camera_center=camera_center, joints_2d=joints_2d,
                          joints_conf=joints_conf, pose_prior=owner.pose_prior, cdict=contactlist,
                          gt_contact=gt_contact, ignore_idxs=ignore_idxs, has_discrete_contact=has_discrete_contact,
@@ -162,7 +209,22 @@ class ContactFit:
         self.loss = None
         self._graph = None
 
+    def _refresh_masks(self):
+        """body_active = ~ignore_idxs (losses.py:73); pair_active = annotated pairs of the bodies that take part
+        (:109-112) -- written IN PLACE into the tensors the fused iteration reads."""
+        ign = self.args['ignore_idxs']
+        with torch.no_grad():
+            if ign is not None:
+                self._body_active.copy_(~ign.bool())
+            else:
+                self._body_active.fill_(1)
+            if self._pair_active is not None:
+                act = (self.args['gt_contact'][0] == 1) & self.args['has_discrete_contact'].bool().view(-1, 1)
+                self._pair_active.copy_(act & self._body_active.bool().view(-1, 1))
+
     def _step_eager(self):
+        if self.native:
+            return self.state.step()
         out = self.owner._forward(self.global_orient, self.body_pose, self.betas)
         self.vertices = out.vertices
         self.loss = contact_fitting_loss(self.body_pose, self.global_orient, self.loop1_pose, self.loop1_orient,
@@ -223,6 +285,8 @@ class ContactFit:
             for st in self.opt.state:
                 for t in st:
                     t.zero_()
+            if self.native:
+                self._refresh_masks()
         return self
 
 
@@ -239,8 +303,11 @@ class SMPLifyDC():
                  geothres=0.0,
                  euclthres=0.0,
                  device=torch.device('cuda'),
-                 smpl=None, pose_prior=None, ign_joints=None, use_cuda_graph=False):
+                 smpl=None, pose_prior=None, ign_joints=None, use_cuda_graph=False, native_step=True):
         self.device = torch.device(device)
+        # stage-2 iterations as one fused C-ABI call each (tuch_contact_fit_step); False keeps the term-by-term
+        # composition through torch autograd (same kernels, bit-identical parameters)
+        self.native_step = bool(native_step)
         # iterations of both stages replayed as one CUDA graph launch each (_call_graphed); pays off when the
         # iteration is launch-bound (small batches, or a training loop that fits every step)
         self.use_cuda_graph = bool(use_cuda_graph)
@@ -279,13 +346,14 @@ class SMPLifyDC():
 
     def begin_contact_fit(self, body_pose, global_orient, betas, camera_translation, camera_center, joints_2d,
                           joints_conf, contactlist, gt_contact, ignore_idxs, has_discrete_contact,
-                          contact_loss_weight=1, contact_loss_return='sum', segments=None):
+                          contact_loss_weight=1, contact_loss_return='sum', segments=None, native=None):
         """Stage-2 contact optimisation state (smplifydc.py:139-183): body_pose / global_orient become the
         optimised leaves (updated in place), everything else is held fixed.  ContactFit.step() runs one
         iteration: SMPL forward -> contact_fitting_loss -> backward -> Adam."""
         return ContactFit(self, body_pose, global_orient, betas, camera_translation, camera_center, joints_2d,
                           joints_conf, contactlist, gt_contact, ignore_idxs, has_discrete_contact,
-                          contact_loss_weight, contact_loss_return, segments)
+                          contact_loss_weight, contact_loss_return, segments,
+                          native=self.native_step if native is None else native)
 
     def __call__(self, init_pose, init_betas, init_cam_t,
                  camera_center, keypoints_2d, use_contact=False,
@@ -335,7 +403,7 @@ class SMPLifyDC():
                                          has_discrete_contact, contact_loss_weight, contact_loss_return, segments)
             for _ in range(self.num_iters):
                 fit.step()
-                optiverts.append(fit.vertices)
+                optiverts.append(fit.vertices.clone() if fit.native else fit.vertices)
         else:
             body_pose.requires_grad_(True)
             betas.requires_grad_(True)
