@@ -626,7 +626,10 @@ static int run_segments(const tuch_topology* t, const float* verts, int B, Scrat
 
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
-                       PackedClusters* packed_out) {
+                       PackedClusters* packed_out, cudaStream_t st_nn) {
+    // st_nn: optional second stream for the masked-nearest-vertex half (independent of the inside test); the
+    // caller orders it after the vertices and joins it before it reads argmin / min_sq
+    if (st_nn == nullptr) st_nn = st;
     TUCH_REQUIRE(t != nullptr, "tuch_contact_query: null topology");
     TUCH_REQUIRE(B >= 0, "tuch_contact_query: negative batch");
     TUCH_REQUIRE(B <= 65535, "tuch_contact_query: at most 65535 bodies per call (the batch is a grid dimension), got %d", B);
@@ -720,7 +723,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         float* mn = min_sq ? min_sq : sc.get<float>(h_mn);
         if (nn_tiles) {
             if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4,
-                                              sc.get<float4>(h_tinfo), am, mn, st)) return rc;
+                                              sc.get<float4>(h_tinfo), am, mn, st_nn)) return rc;
         } else {
             if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;
         }

@@ -892,7 +892,9 @@ cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict_
 // ------------------------------------------------------------------------------------------
 int cluster_splits(int B, int T, int NT, int sm_count) {
     const int qtiles = cdiv(T, WC_WARPS);
-    const long long want = (long long)sm_count * 6;                     // CTAs in flight
+    // CTAs wanted: several per SM slot, so that a small batch is cut into pieces short enough to balance over the
+    // SMs (at 32 bodies one split gave 928 CTAs of ~0.5 ms each on 1184 slots: a single ragged wave)
+    const long long want = (long long)sm_count * 16;
     int S = (int)((want + (long long)qtiles * B - 1) / ((long long)qtiles * B));
     S = std::max(1, std::min(S, NT));
     const int per = cdiv(NT, S);

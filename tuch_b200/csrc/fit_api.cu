@@ -12,7 +12,51 @@
 #include "objective_internal.h"
 #include "smpl_internal.h"
 
+#include <cstdlib>
+#include <mutex>
+
 using namespace tuch;
+
+namespace {
+// Two library-owned side streams per device.  Inside one iteration three chains are independent once the vertices
+// exist: the inside test (face hierarchy pack -> winding numbers -> exact re-evaluation -> segment whitelist), the
+// masked nearest vertex, and the joint-side terms (output joints, reprojection, pose prior, region minima).  The
+// inside test is the critical path, so it runs on a HIGH-PRIORITY stream (`s1`): its CTAs are dispatched first and
+// the nearest-vertex kernel on the caller's stream fills whatever the winding kernel leaves idle; the joint-side
+// terms run on `s2`.  They fork after the LBS forward and join before the losses that consume them.  At small
+// batches, where no single kernel fills the GPU, this is ~25 % of the iteration.  Events and waits are capturable:
+// in a CUDA graph the fork / join become plain dependencies and the kernel nodes keep their stream's priority.
+// At large batches both big kernels fill the GPU on their own and what overlap buys is co-residency (the
+// issue-bound winding kernel and the latency-bound nearest kernel share SMs better than either does alone): there
+// the two run at EQUAL priority (inside test on the caller's stream, nearest vertex on `s0`).
+struct Side {
+    cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;
+    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+};
+constexpr int FIT_PRIORITY_BELOW = 192;      // bodies: below this the inside test gets the high-priority stream
+std::mutex g_side_mu;
+Side g_side[64];
+
+int side_streams(Side** out) {
+    int dev = 0;
+    TUCH_CUDA(cudaGetDevice(&dev));
+    TUCH_REQUIRE(dev >= 0 && dev < 64, "tuch_contact_fit_step: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    Side& s = g_side[dev];
+    if (s.s1 == nullptr) {
+        int least = 0, greatest = 0;
+        TUCH_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        TUCH_CUDA(cudaStreamCreateWithFlags(&s.s0, cudaStreamNonBlocking));
+        TUCH_CUDA(cudaStreamCreateWithPriority(&s.s1, cudaStreamNonBlocking, greatest));
+        TUCH_CUDA(cudaStreamCreateWithFlags(&s.s2, cudaStreamNonBlocking));
+        TUCH_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        TUCH_CUDA(cudaEventCreateWithFlags(&s.join1, cudaEventDisableTiming));
+        TUCH_CUDA(cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming));
+    }
+    *out = &s;
+    return 0;
+}
+}  // namespace
 
 TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology* topo, const tuch_prior* prior, int B,
                                       const tuch_contact_fit_args* a, void* stream) {
@@ -56,42 +100,62 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     int* am = a->argmin ? a->argmin : sc.get<int>(h_am);
     uint8_t* ext = a->exterior ? a->exterior : sc.get<uint8_t>(h_ex);
 
-    // ---- SMPL forward (split pose; advances the Adam step counters)
+    // TUCH_FIT_STREAMS=0 keeps the whole iteration on the caller's stream (A/B measurements)
+    static const bool one_stream = getenv("TUCH_FIT_STREAMS") != nullptr && atoi(getenv("TUCH_FIT_STREAMS")) == 0;
+    Side* side = nullptr;
+    if (!one_stream) if (int rc = side_streams(&side)) return rc;
+    const bool prio = side != nullptr && B < FIT_PRIORITY_BELOW;
+    // s_in: stream of the inside test, s_nn: stream of the masked nearest vertex, s2: joint-side terms
+    cudaStream_t s_in = !side ? st : prio ? side->s1 : st, s_nn = !side ? st : prio ? st : side->s0;
+    cudaStream_t s2 = side ? side->s2 : st;
+
+    // ---- SMPL forward (split pose; advances the Adam step counters); the output joints follow on side 2
     LbsBuffers w;
     lbs_carve(a->smpl_workspace, B, V, m.L, w);
-    if (int rc = launch_lbs_forward(m, a->betas, a->body_pose, 0, B, w, a->vertices, a->joints, st, a->global_orient,
+    if (int rc = launch_lbs_forward(m, a->betas, a->body_pose, 0, B, w, a->vertices, nullptr, st, a->global_orient,
                                     a->step_pose, a->step_orient)) return rc;
-    // ---- losses.py:56-64: reprojection and pose prior, with their gradients
+    if (side) {
+        TUCH_CUDA(cudaEventRecord(side->fork, st));
+        TUCH_CUDA(cudaStreamWaitEvent(prio ? s_in : s_nn, side->fork, 0));
+        TUCH_CUDA(cudaStreamWaitEvent(s2, side->fork, 0));
+    }
+    // ---- side 2: joints, losses.py:56-64 (reprojection, pose prior) and the region minima of :108-117
+    if (int rc = launch_lbs_joints(m, a->vertices, w, B, a->joints, s2)) return rc;
     if (int rc = launch_reprojection(a->joints, a->camera_t, a->camera_center, a->joints_2d, a->joints_conf, B, J,
-                                     a->focal_length, a->sigma, nullptr, 0.f, nullptr, rep, nullptr, g_joints, nullptr, st)) return rc;
+                                     a->focal_length, a->sigma, nullptr, 0.f, nullptr, rep, nullptr, g_joints, nullptr, s2)) return rc;
     const float wp = a->pose_prior_weight * a->pose_prior_weight;
     const bool with_prior = prior != nullptr && wp != 0.f;
     if (with_prior)
         if (int rc = launch_pose_terms(prior->d_means, prior->d_precisions, prior->d_nll_weights, prior->M, 69, a->body_pose,
                                        nullptr, 0, B, wp, 0.f, 0.f, sc.get<float>(h_val), sc.get<float>(h_pv),
-                                       sc.get<int>(h_cmp), g_prior, nullptr, st)) return rc;
-    // ---- losses.py:73-105: inside test, allowed self-intersections, masked nearest vertex, push / pull
-    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, st)) return rc;
-    TUCH_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * BV, st));
-    if (int rc = launch_contact_loss(a->vertices, am, ext, a->body_active, nullptr, B, V, a->euclthres, PULL_THRESHOLD,
-                                     REDUCE_SUM, 10.f, nullptr, contact, nullptr, g_verts, st)) return rc;
-    // ---- losses.py:108-117: region-to-region minima of the annotated pairs
+                                       sc.get<int>(h_cmp), g_prior, nullptr, s2)) return rc;
     const bool with_r2r = a->pair_active != nullptr && P > 0;
+    float* mn = sc.get<float>(h_mn);
+    int* ai = sc.get<int>(h_ai);
+    int* aj = sc.get<int>(h_aj);
     if (with_r2r) {
-        float* mn = sc.get<float>(h_mn);
-        int* ai = sc.get<int>(h_ai);
-        int* aj = sc.get<int>(h_aj);
         float4* v4 = sc.get<float4>(h_v4);
-        TUCH_CUDA(cudaMemsetAsync(mn, 0, sizeof(float) * (size_t)B * P, st));
-        TUCH_CUDA(cudaMemsetAsync(ai, 0xff, sizeof(int) * (size_t)B * P, st));
-        TUCH_CUDA(cudaMemsetAsync(aj, 0xff, sizeof(int) * (size_t)B * P, st));
-        if (int rc = launch_pack_mesh(a->vertices, topo->d_faces, B, V, topo->F, topo->Fp, topo->Vp, nullptr, v4, st)) return rc;
+        TUCH_CUDA(cudaMemsetAsync(mn, 0, sizeof(float) * (size_t)B * P, s2));
+        TUCH_CUDA(cudaMemsetAsync(ai, 0xff, sizeof(int) * (size_t)B * P, s2));
+        TUCH_CUDA(cudaMemsetAsync(aj, 0xff, sizeof(int) * (size_t)B * P, s2));
+        if (int rc = launch_pack_mesh(a->vertices, topo->d_faces, B, V, topo->F, topo->Fp, topo->Vp, nullptr, v4, s2)) return rc;
         if (int rc = launch_region_min(v4, topo->Vp, topo->d_maskT, topo->Vq, topo->d_region_ids, topo->d_region_off,
                                        topo->d_pair_a, topo->d_pair_b, a->pair_active, P, B,
-                                       topo->has_pair_mask ? topo->d_pair_mask : nullptr, topo->d_pair_word_off, mn, ai, aj, st)) return rc;
+                                       topo->has_pair_mask ? topo->d_pair_mask : nullptr, topo->d_pair_word_off, mn, ai, aj, s2)) return rc;
+    }
+    if (side) TUCH_CUDA(cudaEventRecord(side->join2, s2));
+    // ---- losses.py:73-105: inside test + allowed self-intersections (high-priority side 1), masked nearest vertex
+    //      (caller's stream)
+    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, s_in, nullptr, s_nn)) return rc;
+    if (side) TUCH_CUDA(cudaEventRecord(side->join1, prio ? s_in : s_nn));
+    TUCH_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * BV, st));
+    if (side) TUCH_CUDA(cudaStreamWaitEvent(st, side->join1, 0));
+    if (int rc = launch_contact_loss(a->vertices, am, ext, a->body_active, nullptr, B, V, a->euclthres, PULL_THRESHOLD,
+                                     REDUCE_SUM, 10.f, nullptr, contact, nullptr, g_verts, st)) return rc;
+    if (side) TUCH_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
+    if (with_r2r)
         if (int rc = launch_region_sum(a->vertices, B, V, P, mn, ai, aj, a->body_active, a->contact_loss_weight, nullptr, r2r,
                                        g_verts, st)) return rc;
-    }
     // ---- losses.py:120-123: per-body totals and their sum
     if (int rc = launch_combine(rep, J, with_prior ? sc.get<float>(h_val) : nullptr, contact, 10.f, with_r2r ? r2r : nullptr,
                                 a->contact_loss_weight, nullptr, B, a->per_body, a->loss, st)) return rc;

@@ -742,6 +742,13 @@ int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, 
     return 0;
 }
 
+int launch_lbs_joints(const SmplDev& m, const float* verts, const LbsBuffers& w, int B, float* joints, cudaStream_t st) {
+    if (B == 0 || joints == nullptr) return 0;
+    lbs_joints_kernel<<<B, JOINT_THREADS, 0, st>>>(m, verts, w.G, joints);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
                         const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st,
                         const LbsAdam* adam) {
@@ -750,7 +757,10 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
     lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed);
     TUCH_LAUNCH_CHECK(); count_launch();
-    {
+    // the pose-feature gradient is only needed when the pose is differentiated (not in SMPLify-DC's stage 1, which
+    // optimises betas and the camera): skip its [B,3V] x [3V,207] contraction otherwise
+    const bool need_pf = g_pose != nullptr || (adam != nullptr && adam->body_pose != nullptr);
+    if (need_pf) {
         // split K into FIXED slabs of 352 coordinates (59 splits at SMPL size, >= 236 CTAs at any batch): the
         // grouping of the partial sums must not depend on the batch size, or a body fitted in a shard of the batch
         // (BASELINE config 4) would round differently from the same body fitted in the whole batch
@@ -775,8 +785,8 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     lbs_bwd_joint_kernel<<<cdiv(B * 24, 4), 128, 0, st>>>(m, w.g_comb, w.v_posed, B, w.gA);
     TUCH_LAUNCH_CHECK(); count_launch();
     lbs_bwd_chain_kernel<<<cdiv(B, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(
-        m, pose, pose_is_rotmat, w.R, w.Jrest, w.G, w.gA, gJ49, w.g_pf, g_betas ? w.g_beta_vert : nullptr, B, g_pose,
-        g_betas, adam != nullptr ? *adam : LbsAdam{});
+        m, pose, pose_is_rotmat, w.R, w.Jrest, w.G, w.gA, gJ49, need_pf ? w.g_pf : nullptr, g_betas ? w.g_beta_vert : nullptr, B,
+        g_pose, g_betas, adam != nullptr ? *adam : LbsAdam{});
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
 }

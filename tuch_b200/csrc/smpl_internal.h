@@ -72,6 +72,8 @@ int launch_lbs_skin_tc(const SmplDev& m, const uint16_t* featop, const float* A,
 int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, int pose_is_rotmat, int B,
                        const LbsBuffers& w, float* verts, float* joints, cudaStream_t st, const float* orient = nullptr,
                        int* step_a = nullptr, int* step_b = nullptr);
+// the 49 output joints alone (launch_lbs_forward with joints == NULL skips them)
+int launch_lbs_joints(const SmplDev& m, const float* verts, const LbsBuffers& w, int B, float* joints, cudaStream_t st);
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
                         const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st,
                         const LbsAdam* adam = nullptr);
