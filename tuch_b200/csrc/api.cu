@@ -626,10 +626,11 @@ static int run_segments(const tuch_topology* t, const float* verts, int B, Scrat
 
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
-                       PackedClusters* packed_out, cudaStream_t st_nn) {
-    // st_nn: optional second stream for the masked-nearest-vertex half (independent of the inside test); the
-    // caller orders it after the vertices and joins it before it reads argmin / min_sq
-    if (st_nn == nullptr) st_nn = st;
+                       PackedClusters* packed_out, const cudaStream_t* nn_stream) {
+    // nn_stream: optional second stream for the masked-nearest-vertex half (independent of the inside test); the
+    // caller orders it after the vertices and joins it before it reads argmin / min_sq.  A pointer, because the
+    // legacy default stream is itself a null handle.
+    const cudaStream_t st_nn = nn_stream != nullptr ? *nn_stream : st;
     TUCH_REQUIRE(t != nullptr, "tuch_contact_query: null topology");
     TUCH_REQUIRE(B >= 0, "tuch_contact_query: negative batch");
     TUCH_REQUIRE(B <= 65535, "tuch_contact_query: at most 65535 bodies per call (the batch is a grid dimension), got %d", B);

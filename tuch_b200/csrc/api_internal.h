@@ -96,6 +96,6 @@ struct PackedClusters {
 // packed_out: optional, receives the packed hierarchy when the hierarchical winding path ran (else stays null)
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
-                       PackedClusters* packed_out = nullptr, cudaStream_t st_nn = nullptr);
+                       PackedClusters* packed_out = nullptr, const cudaStream_t* nn_stream = nullptr);
 
 }  // namespace tuch

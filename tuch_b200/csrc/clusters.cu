@@ -768,9 +768,12 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
     const float4* nb = nodes + (size_t)b * (NT + NM + K) * WC_NODE_F4;
     const float4* tb = ctri + (size_t)b * K * WC_LEAF * 3;
     const int half = lane >> 4, slot = lane & (WC_LEAF - 1);
-    const int t0 = split * tops_per_split, t1 = min(NT, t0 + tops_per_split);
+    // a query's work sits in the one or two top groups it is near, and neighbouring groups are neighbours in index:
+    // the splits take the tops INTERLEAVED (split, split + S, ...) so that the opened groups of a tile are shared
+    // out among its splits instead of landing in one of them
+    (void)tops_per_split;
     float far = 0.f;
-    for (int t = t0; t < t1; ++t) {
+    for (int t = split; t < NT; t += S) {
         const float4* trec = nb + (size_t)t * WC_NODE_F4;
         const float4 tc = __ldg(trec);
         const float tx = tc.x - px, ty = tc.y - py, tz = tc.z - pz;
@@ -869,7 +872,9 @@ cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict_
         const float px = p[0], py = p[1], pz = p[2];
         const float4* t = ctri + (size_t)b * n_slots * 3;
         float acc = 0.f;
-#pragma unroll 2
+        // ~60 trips per thread over L2-resident triangles: the loop is load-latency bound, so eight trips' loads are
+        // issued together (the adds into `acc` stay in index order: the value does not depend on the unrolling)
+#pragma unroll 8
         for (int i = threadIdx.x; i < n_slots; i += 256) {
             const float4 A = __ldg(t + 3 * i), Bv = __ldg(t + 3 * i + 1), C = __ldg(t + 3 * i + 2);
             acc += half_solid_angle_n(px, py, pz, A, Bv, C);
@@ -893,12 +898,11 @@ cluster_refine_kernel(const float* __restrict__ verts, const float4* __restrict_
 int cluster_splits(int B, int T, int NT, int sm_count) {
     const int qtiles = cdiv(T, WC_WARPS);
     // CTAs wanted: several per SM slot, so that a small batch is cut into pieces short enough to balance over the
-    // SMs (at 32 bodies one split gave 928 CTAs of ~0.5 ms each on 1184 slots: a single ragged wave)
+    // SMs (at 32 bodies one split gave 928 CTAs of ~0.5 ms each on 1184 slots: a single ragged wave).  The splits
+    // take the top groups interleaved, so any count up to NT works; 4 bounds the partial-sum traffic.
     const long long want = (long long)sm_count * 16;
-    int S = (int)((want + (long long)qtiles * B - 1) / ((long long)qtiles * B));
-    S = std::max(1, std::min(S, NT));
-    const int per = cdiv(NT, S);
-    return cdiv(NT, per);
+    const int S = (int)((want + (long long)qtiles * B - 1) / ((long long)qtiles * B));
+    return std::max(1, std::min(S, std::min(NT, 4)));
 }
 
 void cluster_pack_betas(const ClusterJob& j, float* beta_leaf, float* beta_group) {

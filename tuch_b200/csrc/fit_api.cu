@@ -31,7 +31,7 @@ namespace {
 // the two run at EQUAL priority (inside test on the caller's stream, nearest vertex on `s0`).
 struct Side {
     cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;
-    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr, fork_b = nullptr, join_b = nullptr;
 };
 constexpr int FIT_PRIORITY_BELOW = 192;      // bodies: below this the inside test gets the high-priority stream
 std::mutex g_side_mu;
@@ -52,6 +52,8 @@ int side_streams(Side** out) {
         TUCH_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         TUCH_CUDA(cudaEventCreateWithFlags(&s.join1, cudaEventDisableTiming));
         TUCH_CUDA(cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming));
+        TUCH_CUDA(cudaEventCreateWithFlags(&s.fork_b, cudaEventDisableTiming));
+        TUCH_CUDA(cudaEventCreateWithFlags(&s.join_b, cudaEventDisableTiming));
     }
     *out = &s;
     return 0;
@@ -146,7 +148,7 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     if (side) TUCH_CUDA(cudaEventRecord(side->join2, s2));
     // ---- losses.py:73-105: inside test + allowed self-intersections (high-priority side 1), masked nearest vertex
     //      (caller's stream)
-    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, s_in, nullptr, s_nn)) return rc;
+    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, s_in, nullptr, &s_nn)) return rc;
     if (side) TUCH_CUDA(cudaEventRecord(side->join1, prio ? s_in : s_nn));
     TUCH_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * BV, st));
     if (side) TUCH_CUDA(cudaStreamWaitEvent(st, side->join1, 0));
@@ -169,5 +171,6 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     ad.lr = a->lr; ad.beta1 = a->beta1; ad.beta2 = a->beta2; ad.eps = a->eps;
     TUCH_REQUIRE((a->grad_body_pose == nullptr) == (a->grad_global_orient == nullptr),
                  "tuch_contact_fit_step: give both gradient outputs or neither");
-    return launch_lbs_backward(m, a->body_pose, 0, B, w, g_verts, g_joints, nullptr, nullptr, st, &ad);
+    LbsSide bs{s2, side ? side->fork_b : nullptr, side ? side->join_b : nullptr};
+    return launch_lbs_backward(m, a->body_pose, 0, B, w, g_verts, g_joints, nullptr, nullptr, st, &ad, side ? &bs : nullptr);
 }

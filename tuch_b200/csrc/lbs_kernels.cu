@@ -751,12 +751,21 @@ int launch_lbs_joints(const SmplDev& m, const float* verts, const LbsBuffers& w,
 
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
                         const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st,
-                        const LbsAdam* adam) {
+                        const LbsAdam* adam, const LbsSide* side) {
     if (B == 0) return 0;
     KernelTimer timer("lbs_backward_kernels", st);
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
     lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed);
     TUCH_LAUNCH_CHECK(); count_launch();
+    // the per-joint reduction runs beside the contractions when the caller lends a second stream
+    const cudaStream_t st_j = side != nullptr ? side->stream : st;
+    if (side != nullptr) {
+        TUCH_CUDA(cudaEventRecord(side->fork, st));
+        TUCH_CUDA(cudaStreamWaitEvent(st_j, side->fork, 0));
+        lbs_bwd_joint_kernel<<<cdiv(B * 24, 4), 128, 0, st_j>>>(m, w.g_comb, w.v_posed, B, w.gA);
+        TUCH_LAUNCH_CHECK(); count_launch();
+        TUCH_CUDA(cudaEventRecord(side->join, st_j));
+    }
     // the pose-feature gradient is only needed when the pose is differentiated (not in SMPLify-DC's stage 1, which
     // optimises betas and the camera): skip its [B,3V] x [3V,207] contraction otherwise
     const bool need_pf = g_pose != nullptr || (adam != nullptr && adam->body_pose != nullptr);
@@ -782,8 +791,12 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
         lbs_bwd_contract_kernel<<<g3, CT_THREADS, 0, st>>>(m.shapedirsT, m.L, m.V * 3, w.g_vposed, B, w.g_beta_vert);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
-    lbs_bwd_joint_kernel<<<cdiv(B * 24, 4), 128, 0, st>>>(m, w.g_comb, w.v_posed, B, w.gA);
-    TUCH_LAUNCH_CHECK(); count_launch();
+    if (side == nullptr) {
+        lbs_bwd_joint_kernel<<<cdiv(B * 24, 4), 128, 0, st>>>(m, w.g_comb, w.v_posed, B, w.gA);
+        TUCH_LAUNCH_CHECK(); count_launch();
+    } else {
+        TUCH_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    }
     lbs_bwd_chain_kernel<<<cdiv(B, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(
         m, pose, pose_is_rotmat, w.R, w.Jrest, w.G, w.gA, gJ49, need_pf ? w.g_pf : nullptr, g_betas ? w.g_beta_vert : nullptr, B,
         g_pose, g_betas, adam != nullptr ? *adam : LbsAdam{});

@@ -111,6 +111,8 @@ segment_whitelist_kernel(const float* __restrict__ verts, int V, const float* __
     const float* ab = apex + ((size_t)b * n_bands + seg_band0[s]) * 3;
     const float px = vb[3 * v], py = vb[3 * v + 1], pz = vb[3 * v + 2];
     float acc = 0.f;
+    // two dependent loads per trip (face index -> corner): issue four trips' loads together; the adds stay in order
+#pragma unroll 4
     for (int f = seg_face_off[s] + lane; f < seg_face_off[s + 1]; f += 32) {
         float4 c[3];
 #pragma unroll

@@ -61,6 +61,13 @@ struct LbsAdam {
     double lr = 0.0, beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
 };
 
+// optional second stream for the LBS backward: the per-joint reduction (lbs_bwd_joint_kernel) and the pose-blend
+// contraction both consume the vertex pass and are independent of each other
+struct LbsSide {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+
 size_t lbs_workspace_floats(int V, int L, int B);     // whole workspace of a batch
 void lbs_carve(float* base, int B, int V, int L, LbsBuffers& w);
 void lbs_tc_pack_model(int V, int L, const float* shapedirs, const float* posedirs, std::vector<uint16_t>& blob);
@@ -76,7 +83,7 @@ int launch_lbs_forward(const SmplDev& m, const float* betas, const float* pose, 
 int launch_lbs_joints(const SmplDev& m, const float* verts, const LbsBuffers& w, int B, float* joints, cudaStream_t st);
 int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat, int B, const LbsBuffers& w,
                         const float* gV, const float* gJ49, float* g_pose, float* g_betas, cudaStream_t st,
-                        const LbsAdam* adam = nullptr);
+                        const LbsAdam* adam = nullptr, const LbsSide* side = nullptr);
 
 }  // namespace tuch
 
