@@ -47,9 +47,12 @@ def test_tree_disconnected_and_tiny():
     assert len(t['leaf_face']) == 1 and len(t['vtile']) == 1                       # small components share a leaf
 
 
+WC_BETA, WC_MARGIN = 1.6, 0.06          # tuch_b200/csrc/clusters.h
+
+
 def test_far_field_expansion_matches_exact_solid_angles():
     """The node record of cluster_pack_kernel, restated in fp64: centre, radius, M0, tr M1, sym M1, u and
-    the cubic form.  Beyond 2 radii (WC_BETA) its error against the exact cluster solid angles is a few 1e-3
+    the cubic form.  Beyond WC_BETA radii its error against the exact cluster solid angles is a few 1e-3
     of a winding number in total."""
     import torch
     from oracle import clib, lbs as olbs
@@ -84,13 +87,14 @@ def test_far_field_expansion_matches_exact_solid_angles():
         d = np.linalg.norm(r, axis=1)
         omega = (r @ M0 + np.trace(M1)) / d ** 3 - (3 * np.einsum('qi,ij,qj->q', r, M1, r) + 1.5 * r @ u) / d ** 5 \
             + 7.5 * np.einsum('ijk,qi,qj,qk->q', M2, r, r, r) / d ** 7
-        far = d > 2.0 * R
+        far = d > WC_BETA * R
         total_err += np.where(far, np.abs(omega - sa[:, fs].sum(1)), 0.0) / (4 * np.pi)
         signed_err += np.where(far, omega - sa[:, fs].sum(1), 0.0) / (4 * np.pi)
-    # even if every leaf's error had the same sign the total stays below a quarter of the 0.04 re-evaluation
-    # margin (WC_MARGIN); the actual error is a few 1e-3
-    assert total_err.max() < 1e-2, total_err.max()
-    assert np.abs(signed_err).max() < 4e-3, np.abs(signed_err).max()
+    # even if every leaf's error had the same sign (no cancellation at all) the total stays below HALF the
+    # re-evaluation margin (WC_MARGIN); the actual, signed error stays below a quarter of it
+    print('far-field bound: sum |err| %.3e, |sum err| %.3e' % (total_err.max(), np.abs(signed_err).max()))
+    assert total_err.max() < 0.5 * WC_MARGIN, total_err.max()
+    assert np.abs(signed_err).max() < 0.25 * WC_MARGIN, np.abs(signed_err).max()
 
 
 def test_refined_tree_is_a_valid_partition_with_rounder_leaves():

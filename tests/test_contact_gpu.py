@@ -7,6 +7,10 @@ import torch
 from conftest import golden
 
 pytestmark = pytest.mark.gpu
+# hierarchical winding numbers (tuch_b200/csrc/clusters.h): values within the re-evaluation margin of the 0.99
+# threshold are exact; elsewhere the far-field error must stay below a quarter of that margin
+WC_MARGIN = 0.06
+FAR_FIELD_TOL = 0.25 * WC_MARGIN
 
 
 @pytest.fixture(scope='module')
@@ -139,7 +143,7 @@ def check_query(assets, dev, batch, seed, use_segments):
     # hierarchical mode: same nearest vertices, winding numbers within the far-field error, flags
     # identical away from the threshold
     assert torch.equal(fast['argmin'], out['argmin']) and torch.equal(fast['min_sq'], out['min_sq'])
-    assert (fast['winding'] - out['winding']).abs().max() < 5e-3
+    assert (fast['winding'] - out['winding']).abs().max() < FAR_FIELD_TOL
     away = (out['winding'] - 0.99).abs() > 1e-4
     assert torch.equal(fast['exterior'][away], out['exterior'][away])
     for b in range(batch):
@@ -276,9 +280,9 @@ def _fast_vs_exact(assets, dev, batch, seed, template):
     assert stats['leaves'] >= len(assets['model']['faces']) // stats['leaf_faces'] and stats['mids'] >= 1 and stats['tops'] >= 1
     err = (a['winding'] - b['winding']).abs()
     print('hierarchical winding: max |w_fast - w_exact| = %.2e' % float(err.max()))
-    assert float(err.max()) < 5e-3, float(err.max())
+    assert float(err.max()) < FAR_FIELD_TOL, float(err.max())
     # every query the far field could misclassify was re-evaluated exactly
-    band = (b['winding'] - 0.99).abs() < 0.04
+    band = (b['winding'] - 0.99).abs() < WC_MARGIN
     if bool(band.any()):
         assert float(err[band].max()) < 2e-5
     away = (a['winding'] - 0.99).abs() > 1e-4
@@ -337,7 +341,7 @@ def test_contact_query_batch64_properties(dev, full_assets):
     a = ex.contact_query(verts, use_segments=True)
     b = fa.contact_query(verts, use_segments=True)
     assert torch.equal(a['argmin'], b['argmin']) and torch.equal(a['min_sq'], b['min_sq'])
-    assert (a['winding'] - b['winding']).abs().max() < 5e-3
+    assert (a['winding'] - b['winding']).abs().max() < FAR_FIELD_TOL
     away = (a['winding'] - 0.99).abs() > 1e-4
     assert torch.equal(a['exterior'][away], b['exterior'][away])
     assert int((~b['exterior']).sum()) > 1000
