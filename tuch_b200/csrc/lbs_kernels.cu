@@ -341,9 +341,13 @@ lbs_joints_kernel(SmplDev m, const float* __restrict__ verts, const float* __res
 __global__ void __launch_bounds__(LBS_VT)
 lbs_bwd_vertex_kernel(SmplDev m, const float* __restrict__ A, const float* __restrict__ gV,
                       const float* __restrict__ gJ49, int B, float* __restrict__ g_comb,
-                      float* __restrict__ g_vposed) {
+                      float* __restrict__ g_vposed, float* __restrict__ beta_part) {
+    // beta_part != NULL: also the vertex part of the shape gradient, g_beta[b][l] = sum_{v,c} S[l][v,c] g_vposed[b][v,c],
+    // as one partial sum per (vertex tile, body, l) -- beta_part[tile][B][L], summed over the tiles in index order
+    // by lbs_bwd_chain_kernel -- instead of a second pass over g_vposed
     __shared__ float s_A[LBS_NB][24 * 12];
     __shared__ float s_gj[LBS_NB][SMPL_MAX_JOINTS54][3];
+    __shared__ float s_beta[LBS_VT / 32][LBS_NB][SMPL_MAX_BETAS];
     const int b0 = blockIdx.y * LBS_NB;
     for (int i = threadIdx.x; i < LBS_NB * 288; i += LBS_VT) {
         const int bb = i / 288, e = i % 288;
@@ -362,93 +366,83 @@ lbs_bwd_vertex_kernel(SmplDev m, const float* __restrict__ A, const float* __res
         __syncthreads();
     }
     const int v = blockIdx.x * LBS_VT + threadIdx.x;
-    if (v >= m.V) return;
+    const bool live = v < m.V;
     const int K = m.K;
-    const uint8_t* si = m.skin_idx + (size_t)v * K;
-    const float* sw = m.skin_w + (size_t)v * K;
-    const int c0 = m.vj_off[v], c1 = m.vj_off[v + 1];
+    float gp[LBS_NB][3];
 #pragma unroll
-    for (int bb = 0; bb < LBS_NB; ++bb) {
-        if (b0 + bb >= B) break;
-        const size_t o = ((size_t)(b0 + bb) * m.V + v) * 3;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        if (gV != nullptr) { g0 = gV[o]; g1 = gV[o + 1]; g2 = gV[o + 2]; }
-        for (int i = c0; i < c1; ++i) {
-            const float w = m.vj_w[i];
-            const float* gj = s_gj[bb][m.vj_joint[i]];
-            g0 = fmaf(w, gj[0], g0); g1 = fmaf(w, gj[1], g1); g2 = fmaf(w, gj[2], g2);
-        }
-        float T[9];
+    for (int bb = 0; bb < LBS_NB; ++bb) { gp[bb][0] = 0.f; gp[bb][1] = 0.f; gp[bb][2] = 0.f; }
+    if (live) {
+        const uint8_t* si = m.skin_idx + (size_t)v * K;
+        const float* sw = m.skin_w + (size_t)v * K;
+        const int c0 = m.vj_off[v], c1 = m.vj_off[v + 1];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) T[i] = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float wk = sw[k];
-            const float* a = s_A[bb] + 12 * (int)si[k];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                T[3 * r] = fmaf(wk, a[4 * r], T[3 * r]);
-                T[3 * r + 1] = fmaf(wk, a[4 * r + 1], T[3 * r + 1]);
-                T[3 * r + 2] = fmaf(wk, a[4 * r + 2], T[3 * r + 2]);
+        for (int bb = 0; bb < LBS_NB; ++bb) {
+            if (b0 + bb >= B) break;
+            const size_t o = ((size_t)(b0 + bb) * m.V + v) * 3;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            if (gV != nullptr) { g0 = gV[o]; g1 = gV[o + 1]; g2 = gV[o + 2]; }
+            for (int i = c0; i < c1; ++i) {
+                const float w = m.vj_w[i];
+                const float* gj = s_gj[bb][m.vj_joint[i]];
+                g0 = fmaf(w, gj[0], g0); g1 = fmaf(w, gj[1], g1); g2 = fmaf(w, gj[2], g2);
             }
+            g_comb[o] = g0; g_comb[o + 1] = g1; g_comb[o + 2] = g2;
+            // most vertices carry no gradient (the contact terms touch the interior / in-contact vertices and their
+            // partners, the joints a few hundred vertices): their blended transform is never formed
+            if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
+                float T[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) T[i] = 0.f;
+                for (int k = 0; k < K; ++k) {
+                    const float wk = sw[k];
+                    const float* a = s_A[bb] + 12 * (int)si[k];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        T[3 * r] = fmaf(wk, a[4 * r], T[3 * r]);
+                        T[3 * r + 1] = fmaf(wk, a[4 * r + 1], T[3 * r + 1]);
+                        T[3 * r + 2] = fmaf(wk, a[4 * r + 2], T[3 * r + 2]);
+                    }
+                }
+                gp[bb][0] = fmaf(T[6], g2, fmaf(T[3], g1, T[0] * g0));
+                gp[bb][1] = fmaf(T[7], g2, fmaf(T[4], g1, T[1] * g0));
+                gp[bb][2] = fmaf(T[8], g2, fmaf(T[5], g1, T[2] * g0));
+            }
+            g_vposed[o] = gp[bb][0]; g_vposed[o + 1] = gp[bb][1]; g_vposed[o + 2] = gp[bb][2];
         }
-        g_comb[o] = g0; g_comb[o + 1] = g1; g_comb[o + 2] = g2;
-        g_vposed[o] = fmaf(T[6], g2, fmaf(T[3], g1, T[0] * g0));
-        g_vposed[o + 1] = fmaf(T[7], g2, fmaf(T[4], g1, T[1] * g0));
-        g_vposed[o + 2] = fmaf(T[8], g2, fmaf(T[5], g1, T[2] * g0));
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// backward 2/4: contractions over the 3V coordinates,  out[b][r] = sum_c M[r][c] g_vposed[b][c]
-// (M = posedirs -> pose-feature gradient, M = shapedirsT -> vertex part of the beta gradient).
-// Block = CT_ROWS rows x CT_NB bodies, threads stride over the coordinates.
-// ------------------------------------------------------------------------------------------
-constexpr int CT_ROWS = 8;
-constexpr int CT_NB = 8;
-constexpr int CT_THREADS = 256;
-
-__global__ void __launch_bounds__(CT_THREADS)
-lbs_bwd_contract_kernel(const float* __restrict__ M, int n_rows, int n_coords,
-                        const float* __restrict__ g_vposed, int B, float* __restrict__ out) {
-    const int r0 = blockIdx.x * CT_ROWS, b0 = blockIdx.y * CT_NB;
-    float acc[CT_ROWS][CT_NB];
+    if (beta_part == nullptr) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t V3 = (size_t)m.V * 3;
+    for (int l = 0; l < m.L; ++l) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if (live) {
+            const float* row = m.shapedirsT + (size_t)l * V3 + 3 * v;
+            s0 = __ldg(row); s1 = __ldg(row + 1); s2 = __ldg(row + 2);
+        }
 #pragma unroll
-    for (int r = 0; r < CT_ROWS; ++r)
+        for (int bb = 0; bb < LBS_NB; ++bb) {
+            float x = fmaf(s2, gp[bb][2], fmaf(s1, gp[bb][1], s0 * gp[bb][0]));
 #pragma unroll
-        for (int bb = 0; bb < CT_NB; ++bb) acc[r][bb] = 0.f;
-    for (int c = threadIdx.x; c < n_coords; c += CT_THREADS) {
-        float mv[CT_ROWS], gv[CT_NB];
-#pragma unroll
-        for (int r = 0; r < CT_ROWS; ++r) mv[r] = (r0 + r < n_rows) ? __ldg(M + (size_t)(r0 + r) * n_coords + c) : 0.f;
-#pragma unroll
-        for (int bb = 0; bb < CT_NB; ++bb) gv[bb] = (b0 + bb < B) ? g_vposed[(size_t)(b0 + bb) * n_coords + c] : 0.f;
-#pragma unroll
-        for (int r = 0; r < CT_ROWS; ++r)
-#pragma unroll
-            for (int bb = 0; bb < CT_NB; ++bb) acc[r][bb] = fmaf(mv[r], gv[bb], acc[r][bb]);
-    }
-    __shared__ float s_red[CT_THREADS / 32][CT_ROWS * CT_NB];
-    const int warp = threadIdx.x / 32, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int r = 0; r < CT_ROWS; ++r)
-#pragma unroll
-        for (int bb = 0; bb < CT_NB; ++bb) {
-            float x = acc[r][bb];
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0) s_red[warp][r * CT_NB + bb] = x;
+            if (lane == 0) s_beta[warp][bb][l] = x;
         }
+    }
     __syncthreads();
-    if (threadIdx.x < CT_ROWS * CT_NB) {
-        const int r = threadIdx.x / CT_NB, bb = threadIdx.x % CT_NB;
-        if (r0 + r < n_rows && b0 + bb < B) {
-            float x = 0.f;
-            for (int w = 0; w < CT_THREADS / 32; ++w) x += s_red[w][threadIdx.x];
-            out[(size_t)(b0 + bb) * n_rows + r0 + r] = x;
-        }
+    for (int i = threadIdx.x; i < LBS_NB * m.L; i += LBS_VT) {
+        const int bb = i / m.L, l = i % m.L;
+        if (b0 + bb >= B) continue;
+        float x = 0.f;
+#pragma unroll
+        for (int w = 0; w < LBS_VT / 32; ++w) x += s_beta[w][bb][l];
+        beta_part[((size_t)blockIdx.x * B + b0 + bb) * m.L + l] = x;
     }
 }
 
-// Tiled variant for the 207-row pose-blend contraction (a [B, 3V] x [3V, 207] GEMM, K = 20,670): a CTA owns
+// ------------------------------------------------------------------------------------------
+// backward 2/4: the pose-blend contraction over the 3V coordinates,  g_pf[b][r] = sum_c posedirs[r][c] g_vposed[b][c]
+// (the shape-basis contraction is folded into the vertex pass above).
+// ------------------------------------------------------------------------------------------
+// A [B, 3V] x [3V, 207] GEMM, K = 20,670: a CTA owns
 // a 64-body x 64-row output tile over one K split, streams 32-wide K slabs of both operands through shared
 // memory ([k][row] so that a thread reads its 8 rows / 4 bodies as vectors) and keeps a 4 x 8 register
 // tile; the K splits are summed in a fixed order by lbs_contract_reduce_kernel.  Every operand
@@ -559,7 +553,7 @@ __global__ void __launch_bounds__(POSE_WARPS * 32)
 lbs_bwd_chain_kernel(SmplDev m, const float* __restrict__ pose, int pose_is_rotmat, const float* __restrict__ R,
                      const float* __restrict__ Jrest, const float* __restrict__ G, const float* __restrict__ gA,
                      const float* __restrict__ gJ49, const float* __restrict__ g_pf,
-                     const float* __restrict__ g_beta_vert, int B, float* __restrict__ g_pose,
+                     const float* __restrict__ g_beta_vert, int beta_tiles, int B, float* __restrict__ g_pose,
                      float* __restrict__ g_betas, LbsAdam ad) {
     __shared__ float s_c3[POSE_WARPS][24][9];     // child -> parent contribution to gG3
     __shared__ float s_ct[POSE_WARPS][24][3];     // child -> parent contribution to gGt
@@ -703,7 +697,9 @@ lbs_bwd_chain_kernel(SmplDev m, const float* __restrict__ pose, int pose_is_rotm
     __syncwarp();
     if (g_betas != nullptr && b < B) {
         for (int l = lane; l < m.L; l += 32) {
-            float acc = g_beta_vert ? g_beta_vert[(size_t)b * m.L + l] : 0.f;
+            float acc = 0.f;                          // vertex part: the per-tile partials of lbs_bwd_vertex_kernel, in order
+            if (g_beta_vert != nullptr)
+                for (int t = 0; t < beta_tiles; ++t) acc += g_beta_vert[((size_t)t * B + b) * m.L + l];
             for (int k = 0; k < 24; ++k)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) acc = fmaf(m.J_shapedirs[(size_t)(3 * k + c) * m.L + l], s_gJ[w][k][c], acc);
@@ -755,7 +751,16 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     if (B == 0) return 0;
     KernelTimer timer("lbs_backward_kernels", st);
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
-    lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed);
+    const bool need_pf = g_pose != nullptr || (adam != nullptr && adam->body_pose != nullptr);
+    const int n_coords = m.V * 3;
+    const int per = 11 * GT_K;                    // see below
+    const int S = cdiv(n_coords, per);
+    Scratch sc;
+    const size_t h_part = sc.plan(need_pf ? sizeof(float) * (size_t)S * B * 207 : 0);
+    const size_t h_beta = sc.plan(g_betas != nullptr ? sizeof(float) * (size_t)grid.x * B * m.L : 0);
+    if (int rc = sc.commit_slot(st, 2)) return rc;
+    float* beta_part = g_betas != nullptr ? sc.get<float>(h_beta) : nullptr;
+    lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed, beta_part);
     TUCH_LAUNCH_CHECK(); count_launch();
     // the per-joint reduction runs beside the contractions when the caller lends a second stream
     const cudaStream_t st_j = side != nullptr ? side->stream : st;
@@ -768,27 +773,15 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     }
     // the pose-feature gradient is only needed when the pose is differentiated (not in SMPLify-DC's stage 1, which
     // optimises betas and the camera): skip its [B,3V] x [3V,207] contraction otherwise
-    const bool need_pf = g_pose != nullptr || (adam != nullptr && adam->body_pose != nullptr);
     if (need_pf) {
         // split K into FIXED slabs of 352 coordinates (59 splits at SMPL size, >= 236 CTAs at any batch): the
         // grouping of the partial sums must not depend on the batch size, or a body fitted in a shard of the batch
         // (BASELINE config 4) would round differently from the same body fitted in the whole batch
-        const int n_coords = m.V * 3;
-        const int per = 11 * GT_K;
-        const int S = cdiv(n_coords, per);
-        Scratch sc;
-        const size_t h_part = sc.plan(sizeof(float) * (size_t)S * B * 207);
-        if (int rc = sc.commit_slot(st, 2)) return rc;
         float* partial = sc.get<float>(h_part);
         dim3 g2(cdiv(207, GT_R), cdiv(B, GT_B), S);
         lbs_contract_tiled_kernel<<<g2, GT_THREADS, 0, st>>>(m.posedirs, w.g_vposed, 207, n_coords, B, per, partial);
         TUCH_LAUNCH_CHECK(); count_launch();
         lbs_contract_reduce_kernel<<<cdiv(B * 207, 256), 256, 0, st>>>(partial, B * 207, S, w.g_pf);
-        TUCH_LAUNCH_CHECK(); count_launch();
-    }
-    if (g_betas != nullptr) {
-        dim3 g3(cdiv(m.L, CT_ROWS), cdiv(B, CT_NB));
-        lbs_bwd_contract_kernel<<<g3, CT_THREADS, 0, st>>>(m.shapedirsT, m.L, m.V * 3, w.g_vposed, B, w.g_beta_vert);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     if (side == nullptr) {
@@ -798,7 +791,7 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
         TUCH_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     }
     lbs_bwd_chain_kernel<<<cdiv(B, POSE_WARPS), POSE_WARPS * 32, 0, st>>>(
-        m, pose, pose_is_rotmat, w.R, w.Jrest, w.G, w.gA, gJ49, need_pf ? w.g_pf : nullptr, g_betas ? w.g_beta_vert : nullptr, B,
+        m, pose, pose_is_rotmat, w.R, w.Jrest, w.G, w.gA, gJ49, need_pf ? w.g_pf : nullptr, beta_part, (int)grid.x, B,
         g_pose, g_betas, adam != nullptr ? *adam : LbsAdam{});
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
