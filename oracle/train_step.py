@@ -2,10 +2,11 @@
 of the SPIN terms of RegressorLoss.forward, tuch/train/loss.py:94-238, on torch CPU, composed from the
 other oracle modules (LBS, SMPLify-DC loop, regressor contact loss, pose bookkeeping).
 
-The reference module itself cannot be imported here (torchgeometry, smplx, data.essentials are absent),
-so this follows its statements one by one; the image regressor is whatever callable the test passes.
-Parity unpinned as a whole (the reference has no test for it); every piece it calls is pinned by
-tests/golden/.
+This follows the reference's statements one by one; the image regressor is whatever callable the test passes.
+PINNED: tests/golden/make_golden_train.py executes the reference's own forward_train_step (stub modules for the
+absent smplx / trimesh / data tree, torchgeometry's two conversions from oracle/pose.py) and
+tests/test_train_step_cpu.py holds this restatement to the recorded losses, gradients, supervision flags,
+optimised bodies and fits-store rows.
 """
 import numpy as np
 import torch

@@ -122,6 +122,37 @@ def test_forward_train_step_against_oracle(small_assets, run_smplify):
     assert rel(net_gpu.fc.bias.grad, net_cpu.fc.bias.grad) < 2e-3
 
 
+@pytest.mark.parametrize('tag,run_smplify', [('fit', True), ('nofit', False)])
+def test_forward_train_step_matches_reference_golden(small_assets, tag, run_smplify):
+    """The train-step mirror against what the reference's OWN TUCH.forward_train_step (tuch/train/train_module.py:
+    112-336, with its own SMPLifyDC, RegressorLoss, FitsDict and estimate_translation) produced on the same batch:
+    tests/golden/train_step.npz, recorded by tests/golden/make_golden_train.py."""
+    from conftest import golden
+    from tuch_b200 import synthetic as syn
+    g = golden('train_step.npz')
+    a = small_assets
+    o = options(run_smplify)
+    tm, batch, store = make_inputs(a)
+    net = syn.make_stand_in_regressor().to(DEV)
+    tuch = build_mirror(a, store.copy(), o, net)
+    gb = {k: (v if k == 'dataset_name' else torch.tensor(v, device=DEV)) for k, v in batch.items()}
+    loss, losses, out = tuch.forward_train_step(gb)
+    loss.backward()
+    for k, v in losses.items():
+        ref = g['%s/losses/%s' % (tag, k)]
+        assert rel(v.reshape(-1), ref) < 5e-4, (k, float(v.reshape(-1)[0]), ref)
+    assert np.array_equal(out['valid_kpts_anno'].cpu().numpy(), g[tag + '/out/valid_kpts_anno'])
+    for k in ('pred_vertices', 'opt_vertices', 'pred_cam_t', 'opt_cam_t', 'gt_keypoints'):
+        assert rel(out[k], g['%s/out/%s' % (tag, k)]) < 5e-4, k
+    new_store = tuch.fits_dict.fits_dict['dsc'].cpu().numpy()
+    assert np.array_equal((new_store != store).any(axis=1), (g[tag + '/store'] != g['store']).any(axis=1))
+    assert rel(new_store, g[tag + '/store']) < 1e-3
+    assert rel(net.fc.weight.grad, g[tag + '/g_weight']) < 2e-3
+    assert rel(net.fc.bias.grad, g[tag + '/g_bias']) < 2e-3
+    n = 0 if out['smplifyoptiverts'] is None else len(out['smplifyoptiverts'])
+    assert n == int(g[tag + '/n_optiverts'])
+
+
 def test_get_verts_in_contact_against_oracle(small_assets):
     """train_module.py:93-110 per body on CPU: rows with a partner closer than euclthres among the vertices
     at least geothres away along the surface, and the first closest such partner."""
