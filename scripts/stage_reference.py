@@ -6,7 +6,8 @@ staged copy, bench.py's `ref_gpu` leg falls back to the restatement in tests/tes
 says so in its `source` field.
 
     python scripts/stage_reference.py     ->   baseline/_ref/{configs/config.py, tuch/utils/{contact,geometry}.py,
-                                                              tuch/smplify/{losses,prior}.py}
+                                                              tuch/smplify/{losses,prior}.py,
+                                                              tuch/train/{train_module,fits_dict}.py}
 """
 import os
 import shutil
@@ -16,7 +17,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = '/root/reference'
 DST = os.path.join(ROOT, 'baseline', '_ref')
 FILES = ['configs/config.py', 'tuch/utils/contact.py', 'tuch/utils/geometry.py', 'tuch/smplify/losses.py',
-         'tuch/smplify/prior.py']
+         'tuch/smplify/prior.py',
+         # the reference's CALLER code for the drop-in acceptance test (tests/test_dropin_gpu.py): its own train step
+         # and fits store, run unchanged against the aliased tuch_b200 modules
+         'tuch/train/train_module.py', 'tuch/train/fits_dict.py']
 
 
 def stage(verbose=True):
