@@ -341,7 +341,10 @@ lbs_joints_kernel(SmplDev m, const float* __restrict__ verts, const float* __res
 __global__ void __launch_bounds__(LBS_VT)
 lbs_bwd_vertex_kernel(SmplDev m, const float* __restrict__ A, const float* __restrict__ gV,
                       const float* __restrict__ gJ49, int B, float* __restrict__ g_comb,
-                      float* __restrict__ g_vposed, float* __restrict__ beta_part) {
+                      float* __restrict__ g_vposed, float* __restrict__ beta_part, uint16_t* __restrict__ gradop,
+                      int ks_total) {
+    // gradop != NULL: g_vposed goes out as the bf16 x 3 operand of the tensor-core contraction (lbs_tc_bwd.cu),
+    // [body tile][c / 16][term][(c % 16) / 8][body % 128][c % 8], instead of the fp32 array
     // beta_part != NULL: also the vertex part of the shape gradient, g_beta[b][l] = sum_{v,c} S[l][v,c] g_vposed[b][v,c],
     // as one partial sum per (vertex tile, body, l) -- beta_part[tile][B][L], summed over the tiles in index order
     // by lbs_bwd_chain_kernel -- instead of a second pass over g_vposed
@@ -407,7 +410,24 @@ lbs_bwd_vertex_kernel(SmplDev m, const float* __restrict__ A, const float* __res
                 gp[bb][1] = fmaf(T[7], g2, fmaf(T[4], g1, T[1] * g0));
                 gp[bb][2] = fmaf(T[8], g2, fmaf(T[5], g1, T[2] * g0));
             }
-            g_vposed[o] = gp[bb][0]; g_vposed[o + 1] = gp[bb][1]; g_vposed[o + 2] = gp[bb][2];
+            if (gradop == nullptr) {
+                g_vposed[o] = gp[bb][0]; g_vposed[o + 1] = gp[bb][1]; g_vposed[o + 2] = gp[bb][2];
+            } else {
+                const int b = b0 + bb;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int c = 3 * v + i;
+                    const size_t base = ((size_t)(b / LBS_TC_NB) * ks_total + c / 16) * 3;
+                    const size_t tail = ((size_t)((c % 16) / 8) * LBS_TC_NB + b % LBS_TC_NB) * 8 + c % 8;
+                    float rem = gp[bb][i];
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+                        rem -= __bfloat162float(h);
+                        gradop[(base + p) * 2 * LBS_TC_NB * 8 + tail] = __bfloat16_as_ushort(h);
+                    }
+                }
+            }
         }
     }
     if (beta_part == nullptr) return;
@@ -752,15 +772,27 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     KernelTimer timer("lbs_backward_kernels", st);
     dim3 grid(cdiv(m.V, LBS_VT), cdiv(B, LBS_NB));
     const bool need_pf = g_pose != nullptr || (adam != nullptr && adam->body_pose != nullptr);
+    static const bool force_ffma = getenv("TUCH_LBS_FFMA") != nullptr && atoi(getenv("TUCH_LBS_FFMA")) != 0;
+    const bool tc = need_pf && m.tcb_model != nullptr && !force_ffma;        // tensor-core contraction (lbs_tc_bwd.cu)
     const int n_coords = m.V * 3;
     const int per = 11 * GT_K;                    // see below
-    const int S = cdiv(n_coords, per);
+    const int S = tc ? lbs_tcb_slabs(m.V) : cdiv(n_coords, per);
     Scratch sc;
-    const size_t h_part = sc.plan(need_pf ? sizeof(float) * (size_t)S * B * 207 : 0);
+    const size_t h_part = sc.plan(!need_pf ? 0 : tc ? sizeof(float) * (size_t)S * B * 256 : sizeof(float) * (size_t)S * B * 207);
     const size_t h_beta = sc.plan(g_betas != nullptr ? sizeof(float) * (size_t)grid.x * B * m.L : 0);
     if (int rc = sc.commit_slot(st, 2)) return rc;
     float* beta_part = g_betas != nullptr ? sc.get<float>(h_beta) : nullptr;
-    lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed, beta_part);
+    const int ks_total = lbs_tcb_slabs(m.V) * LBS_TCB_KSTEPS;
+    if (tc) {
+        // the K padding behind the last coordinate must be finite (it multiplies zero rows of the model operand):
+        // zero the k-steps from the one that holds coordinate 3V on, per body tile, before the vertex pass fills in
+        const int first = n_coords / 16;
+        for (int bt = 0; bt < cdiv(B, LBS_TC_NB); ++bt)
+            TUCH_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(w.gradop) + ((size_t)bt * ks_total + first) * LBS_TCB_STEP_BYTES, 0,
+                                      (size_t)(ks_total - first) * LBS_TCB_STEP_BYTES, st));
+    }
+    lbs_bwd_vertex_kernel<<<grid, LBS_VT, 0, st>>>(m, w.A, gV, gJ49, B, w.g_comb, w.g_vposed, beta_part,
+                                                   tc ? w.gradop : nullptr, ks_total);
     TUCH_LAUNCH_CHECK(); count_launch();
     // the per-joint reduction runs beside the contractions when the caller lends a second stream
     const cudaStream_t st_j = side != nullptr ? side->stream : st;
@@ -773,7 +805,9 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     }
     // the pose-feature gradient is only needed when the pose is differentiated (not in SMPLify-DC's stage 1, which
     // optimises betas and the camera): skip its [B,3V] x [3V,207] contraction otherwise
-    if (need_pf) {
+    if (tc) {
+        if (int rc = launch_lbs_tc_bwd(m, w.gradop, B, sc.get<float>(h_part), w.g_pf, st)) return rc;
+    } else if (need_pf) {
         // split K into FIXED slabs of 352 coordinates (59 splits at SMPL size, >= 236 CTAs at any batch): the
         // grouping of the partial sums must not depend on the batch size, or a body fitted in a shard of the batch
         // (BASELINE config 4) would round differently from the same body fitted in the whole batch

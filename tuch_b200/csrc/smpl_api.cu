@@ -12,13 +12,16 @@ size_t lbs_workspace_floats(int V, int L, int B) {
     // feature operand (whole 128-body tiles, first: cp.async.bulk needs 16-byte alignment) |
     // per body: R 216 | Jrest 72 | G 288 | A 288 | pf 207(->208) | g_pf 208 | gA 288 | g_beta_vert L(->32) | 3 x V*3
     const size_t per_body = 216 + 72 + 288 + 288 + 208 + 208 + 288 + SMPL_MAX_BETAS + 3 * (size_t)V * 3;
-    return (size_t)cdiv(B, LBS_TC_NB) * (LBS_TC_FEAT_BYTES_PER_TILE / 4) + per_body * (size_t)B;
+    const size_t per_tile = LBS_TC_FEAT_BYTES_PER_TILE / 4 + (size_t)lbs_tcb_slabs(V) * LBS_TCB_KSTEPS * (LBS_TCB_STEP_BYTES / 4);
+    return (size_t)cdiv(B, LBS_TC_NB) * per_tile + per_body * (size_t)B;
 }
 
 void lbs_carve(float* base, int B, int V, int L, LbsBuffers& w) {
     (void)L;
+    const size_t tiles = (size_t)cdiv(B, LBS_TC_NB);
     w.featop = reinterpret_cast<uint16_t*>(base);
-    float* p = base + (size_t)cdiv(B, LBS_TC_NB) * (LBS_TC_FEAT_BYTES_PER_TILE / 4);
+    w.gradop = reinterpret_cast<uint16_t*>(base + tiles * (LBS_TC_FEAT_BYTES_PER_TILE / 4));
+    float* p = base + tiles * (LBS_TC_FEAT_BYTES_PER_TILE / 4 + (size_t)lbs_tcb_slabs(V) * LBS_TCB_KSTEPS * (LBS_TCB_STEP_BYTES / 4));
     auto take = [&](size_t per_body) { float* r = p; p += per_body * (size_t)B; return r; };
     w.R = take(216); w.Jrest = take(72); w.G = take(288); w.A = take(288);
     w.pf = take(208); w.g_pf = take(208); w.gA = take(288); w.g_beta_vert = take(SMPL_MAX_BETAS);
@@ -144,10 +147,16 @@ TUCH_EXPORT int tuch_smpl_create(int V, int L, const float* v_template, const fl
     d.K = K;
     int rc = 0;
     d.tc_model = nullptr;
+    d.tcb_model = nullptr;
     if (K <= LBS_TC_MAXK && 207 + L <= LBS_TC_K) {
         std::vector<uint16_t> blob;
         lbs_tc_pack_model(V, L, shapedirs, posedirs, blob);
         rc = to_device(s, blob, &d.tc_model);
+    }
+    if (!rc) {
+        std::vector<uint16_t> blob;
+        lbs_tcb_pack_model(V, posedirs, blob);
+        rc = to_device(s, blob, &d.tcb_model);
     }
     rc = rc ? rc : to_device(s, std::vector<float>(v_template, v_template + V3), &d.v_template);
     rc = rc ? rc : to_device(s, ST, &d.shapedirsT);

@@ -13,6 +13,9 @@ constexpr int SMPL_MAX_JOINTS54 = 64;   // 24 posed + picked vertices + regresse
 // (207 pose features + up to 17 betas, zero padded), every fp32 operand as three bf16 terms
 constexpr int LBS_TC_M = 128, LBS_TC_NB = 128, LBS_TC_KSTEPS = 14, LBS_TC_K = 16 * LBS_TC_KSTEPS, LBS_TC_MAXK = 8;
 constexpr size_t LBS_TC_FEAT_BYTES_PER_TILE = (size_t)LBS_TC_KSTEPS * 3 * 2 * LBS_TC_NB * 16;   // 172,032 per 128 bodies
+// tcgen05 pose-blend gradient contraction (lbs_tc_bwd.cu): K = the 3V coordinates in fixed slabs of 11 k-steps
+constexpr int LBS_TCB_KSTEPS = 11, LBS_TCB_SLAB = 16 * LBS_TCB_KSTEPS;
+constexpr size_t LBS_TCB_STEP_BYTES = (size_t)3 * 2 * LBS_TC_NB * 16;                           // 12,288 per k-step and body tile
 
 // POD passed by value to the LBS kernels (all pointers are device pointers)
 struct SmplDev {
@@ -38,6 +41,7 @@ struct SmplDev {
     const int* extra_vertex_ids;  // [NX]
     const int* joint_map;         // [NO]
     const uint16_t* tc_model;     // bf16 x 3 model operand of lbs_tc.cu, or NULL (K > LBS_TC_MAXK or L > 17)
+    const uint16_t* tcb_model;    // bf16 x 3 model operand of lbs_tc_bwd.cu (posedirs, K-major over the coordinates)
 };
 
 // per-batch intermediates kept for the backward pass (all [B, ...])
@@ -47,6 +51,7 @@ struct LbsBuffers {
     float *g_comb, *g_vposed;               // [V*3] backward scratch
     float *g_pf, *g_beta_vert, *gA;         // [207] [L] [24*12]
     uint16_t* featop;                       // feature operand of lbs_tc.cu: [ceil(B/128)][14][3][2][128][8] bf16
+    uint16_t* gradop;                       // gradient operand of lbs_tc_bwd.cu: [ceil(B/128)][slabs * 11][3][2][128][8] bf16
 };
 
 // torch.optim.Adam on SMPLify-DC's stage-2 parameters fused into the last kernel of the LBS backward
@@ -73,6 +78,10 @@ void lbs_carve(float* base, int B, int V, int L, LbsBuffers& w);
 void lbs_tc_pack_model(int V, int L, const float* shapedirs, const float* posedirs, std::vector<uint16_t>& blob);
 int launch_lbs_skin_tc(const SmplDev& m, const uint16_t* featop, const float* A, int B, float* verts, float* v_posed,
                        cudaStream_t st);
+int lbs_tcb_slabs(int V);
+void lbs_tcb_pack_model(int V, const float* posedirs, std::vector<uint16_t>& blob);
+// partial: [slabs][B][256] floats of scratch; g_pf [B][207] out
+int launch_lbs_tc_bwd(const SmplDev& m, const uint16_t* gradop, int B, float* partial, float* g_pf, cudaStream_t st);
 
 // orient != NULL: split axis-angle pose (pose = body_pose [B,69], orient = global_orient [B,3]);
 // step_a / step_b: optional Adam step counters the first kernel advances (see LbsAdam)
