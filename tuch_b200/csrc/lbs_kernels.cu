@@ -412,22 +412,35 @@ lbs_bwd_vertex_kernel(SmplDev m, const float* __restrict__ A, const float* __res
             }
             if (gradop == nullptr) {
                 g_vposed[o] = gp[bb][0]; g_vposed[o + 1] = gp[bb][1]; g_vposed[o + 2] = gp[bb][2];
-            } else {
-                const int b = b0 + bb;
+            }
+        }
+    }
+    if (gradop != nullptr) {
+        // the tile's 384 coordinates x 8 bodies as bf16 x 3, staged in shared memory so that they leave as 16-byte
+        // rows of the operand layout (one row = 8 consecutive coordinates of one body and term) instead of 72
+        // two-byte stores per thread; the tile starts at a multiple of 16 coordinates, so rows never straddle tiles
+        __shared__ __align__(16) uint16_t s_op[3][LBS_NB][3 * LBS_VT];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int c = 3 * v + i;
-                    const size_t base = ((size_t)(b / LBS_TC_NB) * ks_total + c / 16) * 3;
-                    const size_t tail = ((size_t)((c % 16) / 8) * LBS_TC_NB + b % LBS_TC_NB) * 8 + c % 8;
-                    float rem = gp[bb][i];
+        for (int bb = 0; bb < LBS_NB; ++bb)
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
-                        rem -= __bfloat162float(h);
-                        gradop[(base + p) * 2 * LBS_TC_NB * 8 + tail] = __bfloat16_as_ushort(h);
-                    }
+            for (int i = 0; i < 3; ++i) {
+                float rem = gp[bb][i];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+                    rem -= __bfloat162float(h);
+                    s_op[p][bb][3 * threadIdx.x + i] = __bfloat16_as_ushort(h);
                 }
             }
+        __syncthreads();
+        const int c_tile = blockIdx.x * 3 * LBS_VT;                 // first coordinate of the tile
+        const int n_rows = 3 * LBS_NB * (3 * LBS_VT / 8);           // (term, body, chunk of 8 coordinates)
+        for (int r = threadIdx.x; r < n_rows; r += LBS_VT) {
+            const int ch8 = r % (3 * LBS_VT / 8), bb = (r / (3 * LBS_VT / 8)) % LBS_NB, p = r / (3 * LBS_VT / 8 * LBS_NB);
+            const int b = b0 + bb, c = c_tile + 8 * ch8;
+            if (b >= B || c / 16 >= ks_total) continue;
+            const size_t row = ((((size_t)(b / LBS_TC_NB) * ks_total + c / 16) * 3 + p) * 2 + (c % 16) / 8) * LBS_TC_NB + b % LBS_TC_NB;
+            *reinterpret_cast<uint4*>(gradop + row * 8) = *reinterpret_cast<const uint4*>(&s_op[p][bb][8 * ch8]);
         }
     }
     if (beta_part == nullptr) return;
