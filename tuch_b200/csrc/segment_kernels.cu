@@ -111,17 +111,33 @@ segment_whitelist_kernel(const float* __restrict__ verts, int V, const float* __
     const float* ab = apex + ((size_t)b * n_bands + seg_band0[s]) * 3;
     const float px = vb[3 * v], py = vb[3 * v + 1], pz = vb[3 * v + 2];
     float acc = 0.f;
-    // two dependent loads per trip (face index -> corner): issue four trips' loads together; the adds stay in order
-#pragma unroll 4
-    for (int f = seg_face_off[s] + lane; f < seg_face_off[s + 1]; f += 32) {
-        float4 c[3];
+    // Two dependent loads per face (corner index -> corner) over ~100 trips: the loop is pure load latency (ncu: 12
+    // warps waiting on long_scoreboard per issue), so four trips are software-pipelined by hand -- all twelve indices
+    // first, then all thirty-six coordinates, then the arithmetic.  The adds into `acc` stay in face order.
+    const int f_end = seg_face_off[s + 1];
+    for (int f0 = seg_face_off[s] + lane; f0 < f_end; f0 += 4 * 32) {
+        int idx[4][3];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            const int i = seg_faces[3 * f + e];
-            const float* p = (i < V) ? (vb + 3 * i) : (ab + 3 * (i - V));
-            c[e] = make_float4(p[0], p[1], p[2], 0.f);
+        for (int u = 0; u < 4; ++u) {
+            const int f = f0 + 32 * u;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) idx[u][e] = f < f_end ? __ldg(seg_faces + 3 * f + e) : 0;
         }
-        acc += half_solid_angle(px, py, pz, c[0], c[1], c[2]);
+        float c[4][3][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int i = idx[u][e];
+                const float* p = (i < V) ? (vb + 3 * i) : (ab + 3 * (i - V));
+                c[u][e][0] = p[0]; c[u][e][1] = p[1]; c[u][e][2] = p[2];
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (f0 + 32 * u < f_end)
+                acc += half_solid_angle(px, py, pz, make_float4(c[u][0][0], c[u][0][1], c[u][0][2], 0.f),
+                                        make_float4(c[u][1][0], c[u][1][1], c[u][1][2], 0.f),
+                                        make_float4(c[u][2][0], c[u][2][1], c[u][2][2], 0.f));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
