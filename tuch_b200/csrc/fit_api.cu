@@ -13,7 +13,9 @@
 #include "smpl_internal.h"
 
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 using namespace tuch;
 
@@ -35,14 +37,17 @@ struct Side {
 };
 constexpr int FIT_PRIORITY_BELOW = 192;      // bodies: below this the inside test gets the high-priority stream
 std::mutex g_side_mu;
-Side g_side[64];
+// one set per (device, caller's stream): fits that run concurrently on different streams must not meet on a shared
+// side stream.  (Tried, round 2: a batch of 256 as two concurrent fits of 128 on two streams, so that one half's
+// latency-bound head and tail overlap the other half's big kernels: 3.77 ms against 3.65 for the one fit, four fits
+// of 64: 3.93 -- the iteration is bound by its total instruction count, scripts/diag/two_halves.py.)
+std::map<std::pair<int, cudaStream_t>, Side> g_side;
 
-int side_streams(Side** out) {
+int side_streams(cudaStream_t caller, Side** out) {
     int dev = 0;
     TUCH_CUDA(cudaGetDevice(&dev));
-    TUCH_REQUIRE(dev >= 0 && dev < 64, "tuch_contact_fit_step: device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_side_mu);
-    Side& s = g_side[dev];
+    Side& s = g_side[std::make_pair(dev, caller)];
     if (s.s1 == nullptr) {
         int least = 0, greatest = 0;
         TUCH_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -105,8 +110,9 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     // TUCH_FIT_STREAMS=0 keeps the whole iteration on the caller's stream (A/B measurements)
     static const bool one_stream = getenv("TUCH_FIT_STREAMS") != nullptr && atoi(getenv("TUCH_FIT_STREAMS")) == 0;
     Side* side = nullptr;
-    if (!one_stream) if (int rc = side_streams(&side)) return rc;
-    const bool prio = side != nullptr && B < FIT_PRIORITY_BELOW;
+    if (!one_stream) if (int rc = side_streams(st, &side)) return rc;
+    static const int prio_below = getenv("TUCH_FIT_PRIORITY_BELOW") != nullptr ? atoi(getenv("TUCH_FIT_PRIORITY_BELOW")) : FIT_PRIORITY_BELOW;
+    const bool prio = side != nullptr && B < prio_below;
     // s_in: stream of the inside test, s_nn: stream of the masked nearest vertex, s2: joint-side terms
     cudaStream_t s_in = !side ? st : prio ? side->s1 : st, s_nn = !side ? st : prio ? st : side->s0;
     cudaStream_t s2 = side ? side->s2 : st;
