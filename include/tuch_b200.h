@@ -143,6 +143,12 @@ int tuch_topology_cluster_stats(const tuch_topology* topo, int* n_leaves, int* n
  * around the 0.99 threshold of losses.py:82): mesh-vertex queries (tuch_contact_query and everything built on
  * it) and HD-point queries (tuch_regressor_contact_loss).  Synchronises `stream`. */
 int tuch_topology_query_stats(const tuch_topology* topo, int* refine_vertices, int* refine_points, void* stream);
+/* Introspection for the tests: the per-body node records (tops, mids, leaves: 28 floats each = centre, squared
+ * opening radius, scaled moments) the hierarchical winding path packs for `verts` [B,V,3] (device) into nodes_out
+ * [B, n_tops + n_mids + n_leaves, 28] (device).  direct != 0: every node straight from its own faces (the slow
+ * reference); 0: the shipped kernel (group nodes from their children's shifted moments). */
+int tuch_topology_pack_nodes(const tuch_topology* topo, const float* verts, int B, int direct, float* nodes_out,
+                             void* stream);
 /* the hierarchy builder without a device: leaf_face_out[n_leaves][16] (face id or -1),
  * mid_off_out[n_mids + 1] (leaf ranges), top_off_out[n_tops + 1] (mid ranges), vtile_out[n_tiles][32]
  * (vertex tiles: the 32 neighbouring vertices one warp queries / one word of the cluster-ordered geodesic

@@ -17,8 +17,8 @@ import numpy as np
 
 from tuch_b200 import ops, synthetic as syn
 
-BETA_LEAF, BETA_GROUP = 2.0, 2.5
-W_TEST, W_FAR, W_NEAR_STEP = 12, 48, 60          # warp instructions per node test / far field / near step
+BETA_LEAF, BETA_GROUP = 1.6, 2.0
+W_TEST, W_FAR, W_NEAR_STEP = 15, 50, 84          # warp instructions per node test / far field / near step
 
 
 def node_sphere(tri, area, cen, ids):

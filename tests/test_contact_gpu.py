@@ -305,6 +305,33 @@ def test_hierarchical_winding_full_size(dev, full_assets, full_assets_uv):
     _fast_vs_exact(full_assets_uv, dev, batch=4, seed=23, template=True)
 
 
+def test_group_nodes_from_shifted_child_moments(dev, full_assets, full_assets_uv):
+    """The pack kernel forms mid and top nodes from their children's moments, re-expressed about the parent's
+    centre (exact identities, clusters.cu add_shifted), instead of a second and third pass over the faces:
+    compare every node record with the one computed straight from the node's own faces."""
+    from oracle import lbs as olbs
+    from tuch_b200 import synthetic as syn
+    for assets, seed in ((full_assets, 61), (full_assets_uv, 62)):
+        topo = make_topology(assets, dev, segments=False, regions=False, exact=False)
+        tm = olbs.to_torch_model(assets['model'])
+        pose = torch.tensor(syn.fold_arms_pose(5, seed=seed, fold=0.8))
+        betas = torch.tensor(np.random.default_rng(seed).normal(0, 0.7, size=(5, 10)).astype(np.float32))
+        verts = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev).contiguous()
+        st = topo.cluster_stats()
+        a = topo.pack_nodes(verts, direct=True).double()
+        b = topo.pack_nodes(verts, direct=False).double()
+        groups = st['tops'] + st['mids']
+        assert torch.equal(a[:, groups:], b[:, groups:])                     # leaves: the same arithmetic
+        ga, gb = a[:, :groups], b[:, :groups]
+        assert (ga[..., :3] - gb[..., :3]).abs().max() < 2e-6                # centres
+        assert ((ga[..., 3] - gb[..., 3]).abs() / ga[..., 3]).max() < 1e-4   # squared opening radius
+        # moments: zeroth .. third order scale with area x radius^k; compare per record against its largest entry
+        # of the same order (cancellation makes single entries arbitrarily small)
+        for lo, hi in ((4, 8), (8, 14), (14, 17), (17, 27)):
+            scale = ga[..., lo:hi].abs().amax(-1, keepdim=True) + 1e-12
+            assert ((ga[..., lo:hi] - gb[..., lo:hi]).abs() / scale).max() < 2e-3, (lo, hi)
+
+
 def test_hierarchical_winding_touching_contact(dev, full_assets):
     """SMPLify-DC converges to touching contact, where vertices sit right at the 0.99 threshold: sweep
     the arm fold so that vertices cross the torso surface in small steps and compare the flags with the

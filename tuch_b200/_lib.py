@@ -52,6 +52,7 @@ def _declare(lib):
     lib.tuch_topology_set_winding_mode.argtypes = [vp, i32]
     lib.tuch_topology_cluster_stats.argtypes = [vp] + [C.POINTER(i32)] * 5
     lib.tuch_topology_query_stats.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp]
+    lib.tuch_topology_pack_nodes.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.tuch_cluster_tree_host.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, vp, i32, vp, i32] + [C.POINTER(i32)] * 4
     lib.tuch_strip_stream_host.argtypes = [vp, i32, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.tuch_topology_num_faces.argtypes = [vp]

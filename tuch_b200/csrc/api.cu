@@ -466,6 +466,27 @@ TUCH_EXPORT int tuch_topology_query_stats(const tuch_topology* t, int* refine_ve
     return 0;
 }
 
+TUCH_EXPORT int tuch_topology_pack_nodes(const tuch_topology* t, const float* verts, int B, int direct, float* nodes_out,
+                                         void* stream) {
+    TUCH_REQUIRE(t != nullptr && verts != nullptr && nodes_out != nullptr, "tuch_topology_pack_nodes: null pointer");
+    TUCH_REQUIRE(t->has_clusters, "tuch_topology_pack_nodes: the topology has no face hierarchy (tuch_topology_set_template)");
+    TUCH_REQUIRE(B >= 0 && B <= 65535, "tuch_topology_pack_nodes: batch out of range");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_nodes = (size_t)t->NT + t->NM + t->K;
+    Scratch sc;
+    const size_t h_tri = sc.plan(sizeof(float4) * 3 * (size_t)B * t->K * WC_LEAF);
+    const size_t h_info = sc.plan(sizeof(float4) * WC_NODE_F4 * (size_t)B * n_nodes);
+    if (int rc = sc.commit(st)) return rc;
+    ClusterJob j{verts, t->d_faces, t->d_leaf_face, t->d_mid_off, t->d_top_off, t->d_vtile, sc.get<float4>(h_tri),
+                 sc.get<float4>(h_info), nullptr, nullptr, nullptr, B, t->V, t->K, t->NM, t->NT, 1, t->T};
+    j.max_top_leaves = t->max_top_leaves;
+    j.direct_pack = direct != 0;
+    if (int rc = launch_cluster_pack(j, st)) return rc;
+    TUCH_CUDA(cudaMemcpyAsync(nodes_out, j.nodes, sizeof(float4) * WC_NODE_F4 * (size_t)B * n_nodes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 TUCH_EXPORT int tuch_topology_num_verts(const tuch_topology* t) { return t ? t->V : -1; }
 TUCH_EXPORT int tuch_topology_num_faces(const tuch_topology* t) { return t ? t->F : -1; }
 TUCH_EXPORT int tuch_topology_total_segment_verts(const tuch_topology* t) { return t ? t->n_sv : -1; }
@@ -626,11 +647,8 @@ static int run_segments(const tuch_topology* t, const float* verts, int B, Scrat
 
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
-                       PackedClusters* packed_out, const cudaStream_t* nn_stream) {
-    // nn_stream: optional second stream for the masked-nearest-vertex half (independent of the inside test); the
-    // caller orders it after the vertices and joins it before it reads argmin / min_sq.  A pointer, because the
-    // legacy default stream is itself a null handle.
-    const cudaStream_t st_nn = nn_stream != nullptr ? *nn_stream : st;
+                       PackedClusters* packed_out, const QueryStreams* qs) {
+    const cudaStream_t st_nn = qs != nullptr ? qs->nn : st;
     TUCH_REQUIRE(t != nullptr, "tuch_contact_query: null topology");
     TUCH_REQUIRE(B >= 0, "tuch_contact_query: negative batch");
     TUCH_REQUIRE(B <= 65535, "tuch_contact_query: at most 65535 bodies per call (the batch is a grid dimension), got %d", B);
@@ -696,7 +714,17 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                          sc.get<float>(h_par), w, sc.get<int>(h_ref), B, V, t->K, t->NM, t->NT, S, t->T};
             j.max_top_leaves = t->max_top_leaves;
             j.stats = t->d_stats;
-            if (int rc = launch_winding_clusters(j, st)) return rc;
+            if (qs != nullptr && qs->split_trav) {
+                if (int rc = launch_cluster_pack(j, st)) return rc;
+                TUCH_CUDA(cudaEventRecord(qs->before_trav, st));
+                TUCH_CUDA(cudaStreamWaitEvent(qs->trav, qs->before_trav, 0));
+                if (int rc = launch_cluster_traverse(j, 0, j.B, qs->trav)) return rc;
+                TUCH_CUDA(cudaEventRecord(qs->after_trav, qs->trav));
+                TUCH_CUDA(cudaStreamWaitEvent(st, qs->after_trav, 0));
+                if (int rc = launch_cluster_finish(j, st)) return rc;
+            } else {
+                if (int rc = launch_winding_clusters(j, st)) return rc;
+            }
             if (packed_out != nullptr) {
                 packed_out->ctri = strip4; packed_out->nodes = info;
                 cluster_pack_betas(j, &packed_out->beta_leaf, &packed_out->beta_group);

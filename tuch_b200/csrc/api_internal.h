@@ -94,8 +94,17 @@ struct PackedClusters {
 
 // vert4_out: optional caller-owned [B][Vp] float4 buffer that receives the packed vertices
 // packed_out: optional, receives the packed hierarchy when the hierarchical winding path ran (else stays null)
+// Optional extra streams of one contact query (the fused iteration hands in library-owned streams of different
+// priorities).  nn: the masked-nearest-vertex half, independent of the inside test; the caller orders it after the
+// vertices and joins it before it reads argmin / min_sq.  trav: the hierarchical winding kernel alone -- the pack
+// before it and the finalize / exact re-evaluation / segment pass after it stay on `st`; the two events order them.
+struct QueryStreams {
+    cudaStream_t nn = nullptr, trav = nullptr;
+    bool split_trav = false;
+    cudaEvent_t before_trav = nullptr, after_trav = nullptr;
+};
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,
-                       PackedClusters* packed_out = nullptr, const cudaStream_t* nn_stream = nullptr);
+                       PackedClusters* packed_out = nullptr, const QueryStreams* qs = nullptr);
 
 }  // namespace tuch

@@ -382,6 +382,43 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
+// Sums of N per-lane values over aligned groups of W lanes as a butterfly reduce-scatter: in the round with lane
+// offset O a lane keeps the half of its values its bit O picks and hands the other half to lane ^ O.  Every total
+// is built by the tree group_sum<W> builds (bit-identical), with N (1 - 1 / W) shuffles instead of N log2 W.
+// Afterwards, with `sub` the lane's index in its group: N >= W: v[0 .. N / W) hold the totals of the values
+// [sub N / W, (sub + 1) N / W);  N < W: v[0] holds the total of value sub / (W / N).
+template <int O, int N>
+struct ReduceScatter {
+    static __device__ __forceinline__ void run(float* v, int lane) {
+        if constexpr (O > 0) {
+            if constexpr (N > 1) {
+                const bool up = (lane & O) != 0;
+#pragma unroll
+                for (int i = 0; i < N / 2; ++i) {
+                    const float keep = up ? v[i + N / 2] : v[i];
+                    const float send = up ? v[i] : v[i + N / 2];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+                }
+                ReduceScatter<O / 2, N / 2>::run(v, lane);
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+                ReduceScatter<O / 2, 1>::run(v, lane);
+            }
+        }
+    }
+};
+// the N < W case followed by a broadcast: every lane of the group ends up with all N totals
+template <int W, int N>
+__device__ __forceinline__ void group_sums(float (&v)[N], int lane) {
+    static_assert(N < W, "group_sums: fewer values than lanes");
+    float t[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) t[k] = v[k];
+    ReduceScatter<W / 2, N>::run(t, lane);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = __shfl_sync(0xffffffffu, t[0], k * (W / N), W);
+}
+
 // One warp per node; nodes are laid out [tops | mids | leaves].  The two half-warps walk alternate leaves
 // of the node, one lane per face slot.  Record layout (all moments pre-scaled so that the kernel's sum is
 // Omega / 2, the quantity the finalize step expects):
@@ -577,18 +614,57 @@ struct NodeMoments {
     }
 };
 
+// Per-node record kept in shared memory while a top group is packed: centre, area, plain centroid sum and count
+// (the centre of a zero-area node), then the 23 raw sums about that centre.
+constexpr int PK_REC = 32, PK_SUMS = 8;
+
+// Moments of a child node, taken about its own centre, re-expressed about the parent's centre p and added to `mo`.
+// With d = child centre - p every relative position grows by d, a face centroid h -> h + d and the face's second
+// moment S -> S + h d' + d h' + d d' (its three edge midpoints average to h), hence
+//   M0' = M0,  tr' = tr + M0.d,  Q'_ab = Q_ab + M0_a d_b,
+//   u'  = u + 2 (Q + Q') d + 2 d (tr + M0.d) + |d|^2 M0,
+//   T'(r) = T(r) + 2 (d.r) r'Q r + (d.r)^2 (M0.r)
+// -- exact identities, so a group node costs one such shift per child instead of a second pass over its faces.
+__device__ __forceinline__ void add_shifted(NodeMoments& mo, const float* __restrict__ rec, float px, float py, float pz) {
+    const float dx = rec[0] - px, dy = rec[1] - py, dz = rec[2] - pz;
+    const float* s = rec + PK_SUMS;
+    const float m0x = s[0], m0y = s[1], m0z = s[2], tr = s[3], qxx = s[4], qyy = s[5], qzz = s[6], qxy = s[7], qxz = s[8],
+                qyz = s[9];
+    const float dm = dx * m0x + dy * m0y + dz * m0z, d2 = dx * dx + dy * dy + dz * dz, trd = tr + dm;
+    mo.m0x += m0x; mo.m0y += m0y; mo.m0z += m0z;
+    mo.tr += trd;
+    mo.qxx += qxx + m0x * dx; mo.qyy += qyy + m0y * dy; mo.qzz += qzz + m0z * dz;
+    mo.qxy += qxy + m0x * dy + m0y * dx; mo.qxz += qxz + m0x * dz + m0z * dx; mo.qyz += qyz + m0y * dz + m0z * dy;
+    mo.uvx += s[10] + 2.f * (2.f * qxx * dx + qxy * dy + qxz * dz) + 2.f * dx * trd + d2 * m0x;
+    mo.uvy += s[11] + 2.f * (qxy * dx + 2.f * qyy * dy + qyz * dz) + 2.f * dy * trd + d2 * m0y;
+    mo.uvz += s[12] + 2.f * (qxz * dx + qyz * dy + 2.f * qzz * dz) + 2.f * dz * trd + d2 * m0z;
+    mo.txxx += s[13] + 2.f * dx * qxx + dx * dx * m0x;
+    mo.tyyy += s[14] + 2.f * dy * qyy + dy * dy * m0y;
+    mo.tzzz += s[15] + 2.f * dz * qzz + dz * dz * m0z;
+    mo.txxy += s[16] + 2.f * (dx * qxy + dy * qxx) + dx * dx * m0y + 2.f * dx * dy * m0x;
+    mo.txxz += s[17] + 2.f * (dx * qxz + dz * qxx) + dx * dx * m0z + 2.f * dx * dz * m0x;
+    mo.tyyx += s[18] + 2.f * (dy * qxy + dx * qyy) + dy * dy * m0x + 2.f * dx * dy * m0y;
+    mo.tyyz += s[19] + 2.f * (dy * qyz + dz * qyy) + dy * dy * m0z + 2.f * dy * dz * m0y;
+    mo.tzzx += s[20] + 2.f * (dz * qxz + dx * qzz) + dz * dz * m0x + 2.f * dx * dz * m0z;
+    mo.tzzy += s[21] + 2.f * (dz * qyz + dy * qzz) + dz * dz * m0y + 2.f * dy * dz * m0z;
+    mo.txyz += s[22] + 2.f * (dx * qyz + dy * qxz + dz * qxy) + 2.f * (dx * dy * m0z + dx * dz * m0y + dy * dz * m0x);
+}
+
 __global__ void __launch_bounds__(256)
 cluster_pack_top_kernel(const float* __restrict__ verts, int V, const int* __restrict__ faces,
                         const int* __restrict__ leaf_face, const int* __restrict__ mid_off,
                         const int* __restrict__ top_off, int K, int NM, int NT, float beta_leaf, float beta_group,
                         float4* __restrict__ ctri, float4* __restrict__ nodes, const uint8_t* __restrict__ body_active) {
-    extern __shared__ float s_c[];                               // [n_slots][9] corners, then [n_slots] validity
+    extern __shared__ float s_c[];                               // [n_slots][9] corners, [n_slots] validity, records
     const int b = blockIdx.y, t = blockIdx.x;
     if (body_active != nullptr && !body_active[b]) return;
     const int m0 = top_off[t], m1 = top_off[t + 1];
     const int l0 = mid_off[m0], l1 = mid_off[m1];
-    const int n_slots = (l1 - l0) * WC_LEAF;
+    const int nm = m1 - m0, nl = l1 - l0;
+    const int n_slots = nl * WC_LEAF;
     float* s_ok = s_c + (size_t)n_slots * 9;
+    float* s_leaf = s_ok + n_slots;                              // [nl][PK_REC]
+    float* s_mid = s_leaf + (size_t)nl * PK_REC;                 // [nm][PK_REC]
     const float* vb = verts + (size_t)b * V * 3;
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
         const int f = leaf_face[(size_t)l0 * WC_LEAF + i];
@@ -614,103 +690,125 @@ cluster_pack_top_kernel(const float* __restrict__ verts, int V, const int* __res
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nm = m1 - m0, nl = l1 - l0;
-    // one node at a time: W = 32 lanes stride over the slots [s0, s1) of a group node, W = 16 lanes own the
-    // 16 slots of a leaf (the two half-warps take two leaves at once)
-    auto reduce_node = [&](auto width, int s0, int s1, int sub, int node, float beta, bool live) {
-        constexpr int W = decltype(width)::value;
-        float wsum = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f, cnt = 0.f;
-        for (int i = s0 + sub; i < s1; i += W) {
-            if (!live || s_ok[i] == 0.f) continue;
-            const float* c = s_c + (size_t)i * 9;
+    float4* nb = nodes + (size_t)b * (NT + NM + K) * WC_NODE_F4;
+
+    // scale of raw sum k in the node record (NodeMoments::write), which holds it at float 4 + k
+    auto rec_scale = [](int k) { return k < 4 ? 0.5f : k < 10 ? -1.5f : k < 13 ? -0.75f : 3.75f; };
+    // ---- leaves from their faces, one per half-warp (lane = face slot); the raw sums stay in shared memory
+    for (int pair = warp; 2 * pair < nl; pair += 8) {
+        const int j = 2 * pair + (lane >> 4), sub = lane & 15;
+        const bool live = j < nl;
+        const int i = j * WC_LEAF + sub;
+        const bool ok = live && s_ok[i] != 0.f;
+        const float* c = s_c + (size_t)(ok ? i : 0) * 9;
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // area, area * centroid, centroid, count
+        if (ok) {
             const float e1x = c[3] - c[0], e1y = c[4] - c[1], e1z = c[5] - c[2];
             const float e2x = c[6] - c[0], e2y = c[7] - c[1], e2z = c[8] - c[2];
             const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
             const float area = 0.5f * sqrtf(nx * nx + ny * ny + nz * nz);
             const float gx = (c[0] + c[3] + c[6]) * (1.f / 3.f), gy = (c[1] + c[4] + c[7]) * (1.f / 3.f),
                         gz = (c[2] + c[5] + c[8]) * (1.f / 3.f);
-            wsum += area; cx += area * gx; cy += area * gy; cz += area * gz;
-            ux += gx; uy += gy; uz += gz; cnt += 1.f;
+            cs[0] = area; cs[1] = area * gx; cs[2] = area * gy; cs[3] = area * gz;
+            cs[4] = gx; cs[5] = gy; cs[6] = gz; cs[7] = 1.f;
         }
-        wsum = group_sum<W>(wsum); cnt = group_sum<W>(cnt);
-        // area-weighted centre (plain centroid mean for zero-area nodes); both candidates are reduced so that
-        // the shuffles stay convergent when the two half-warps disagree
-        const float ax_ = group_sum<W>(cx), ay_ = group_sum<W>(cy), az_ = group_sum<W>(cz);
-        const float bx_ = group_sum<W>(ux), by_ = group_sum<W>(uy), bz_ = group_sum<W>(uz);
-        const bool weighted = wsum > 1e-30f;
-        const float inv = weighted ? 1.f / wsum : 1.f / fmaxf(cnt, 1.f);
-        const float px = (weighted ? ax_ : bx_) * inv, py = (weighted ? ay_ : by_) * inv, pz = (weighted ? az_ : bz_) * inv;
+        group_sums<16>(cs, lane);
+        // area-weighted centre (plain centroid mean for zero-area nodes)
+        const bool weighted = cs[0] > 1e-30f;
+        const float inv = weighted ? 1.f / cs[0] : 1.f / fmaxf(cs[7], 1.f);
+        const float px = (weighted ? cs[1] : cs[4]) * inv, py = (weighted ? cs[2] : cs[5]) * inv,
+                    pz = (weighted ? cs[3] : cs[6]) * inv;
         NodeMoments mo;
-        for (int i = s0 + sub; i < s1; i += W) {
-            if (!live || s_ok[i] == 0.f) continue;
-            const float* c = s_c + (size_t)i * 9;
-            mo.add(c[0] - px, c[1] - py, c[2] - pz, c[3] - px, c[4] - py, c[5] - pz, c[6] - px, c[7] - py, c[8] - pz);
-        }
-        mo.template reduce<W>();
-        if (live && sub == 0) mo.write(nodes + ((size_t)b * (NT + NM + K) + node) * WC_NODE_F4, px, py, pz, beta);
-    };
-    // the top node spans every slot of the CTA (up to 64 leaves): all eight warps take a share -- one warp alone
-    // would be the critical path of the whole pack -- and their partial sums meet in shared memory in warp order
-    {
-        __shared__ float s_part[8][NodeMoments::N_SUMS + 1];
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // area, area * centroid, centroid, count
-        for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
-            if (s_ok[i] == 0.f) continue;
-            const float* c = s_c + (size_t)i * 9;
-            const float e1x = c[3] - c[0], e1y = c[4] - c[1], e1z = c[5] - c[2];
-            const float e2x = c[6] - c[0], e2y = c[7] - c[1], e2z = c[8] - c[2];
-            const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
-            const float area = 0.5f * sqrtf(nx * nx + ny * ny + nz * nz);
-            const float gx = (c[0] + c[3] + c[6]) * (1.f / 3.f), gy = (c[1] + c[4] + c[7]) * (1.f / 3.f),
-                        gz = (c[2] + c[5] + c[8]) * (1.f / 3.f);
-            acc[0] += area; acc[1] += area * gx; acc[2] += area * gy; acc[3] += area * gz;
-            acc[4] += gx; acc[5] += gy; acc[6] += gz; acc[7] += 1.f;
-        }
+        if (ok) mo.add(c[0] - px, c[1] - py, c[2] - pz, c[3] - px, c[4] - py, c[5] - pz, c[6] - px, c[7] - py, c[8] - pz);
+        const float r2 = group_max<16>(mo.r2);
+        float v[32];
+        mo.store_sums(v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            acc[k] = group_sum<32>(acc[k]);
-            if (lane == 0) s_part[warp][k] = acc[k];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float v = 0.f;
-            for (int w = 0; w < 8; ++w) v += s_part[w][k];
-            acc[k] = v;
-        }
-        __syncthreads();
-        const bool weighted = acc[0] > 1e-30f;
-        const float inv = weighted ? 1.f / acc[0] : 1.f / fmaxf(acc[7], 1.f);
-        const float px = (weighted ? acc[1] : acc[4]) * inv, py = (weighted ? acc[2] : acc[5]) * inv,
-                    pz = (weighted ? acc[3] : acc[6]) * inv;
-        NodeMoments mo;
-        for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
-            if (s_ok[i] == 0.f) continue;
-            const float* c = s_c + (size_t)i * 9;
-            mo.add(c[0] - px, c[1] - py, c[2] - pz, c[3] - px, c[4] - py, c[5] - pz, c[6] - px, c[7] - py, c[8] - pz);
-        }
-        mo.template reduce<32>();
-        if (lane == 0) {
-            mo.store_sums(s_part[warp]);
-            s_part[warp][NodeMoments::N_SUMS] = mo.r2;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            NodeMoments top;
-            for (int w = 0; w < 8; ++w) {
-                top.add_sums(s_part[w]);
-                top.r2 = fmaxf(top.r2, s_part[w][NodeMoments::N_SUMS]);
+        for (int k = NodeMoments::N_SUMS; k < 32; ++k) v[k] = 0.f;
+        ReduceScatter<8, 32>::run(v, lane);                      // lane `sub` holds the totals 2 sub, 2 sub + 1
+        if (live && sub < 12) {
+            float* r = s_leaf + (size_t)j * PK_REC;
+            float* o = (float*)(nb + (size_t)(NT + NM + l0 + j) * WC_NODE_F4);
+            r[PK_SUMS + 2 * sub] = v[0]; r[PK_SUMS + 2 * sub + 1] = v[1];
+            *(float2*)(o + 4 + 2 * sub) = make_float2(rec_scale(2 * sub) * v[0], rec_scale(2 * sub + 1) * v[1]);
+            if (sub == 0) {
+                r[0] = px; r[1] = py; r[2] = pz; r[3] = cs[0]; r[4] = cs[4]; r[5] = cs[5]; r[6] = cs[6]; r[7] = cs[7];
+                *(float4*)o = make_float4(px, py, pz, r2 * (beta_leaf * beta_leaf * 1.0002f));
             }
-            top.write(nodes + ((size_t)b * (NT + NM + K) + t) * WC_NODE_F4, px, py, pz, beta_group);
         }
     }
-    for (int n = warp; n < nm; n += 8)                           // its mids: one full warp each
-        reduce_node(std::integral_constant<int, 32>(), (mid_off[m0 + n] - l0) * WC_LEAF,
-                    (mid_off[m0 + n + 1] - l0) * WC_LEAF, lane, NT + m0 + n, beta_group, true);
-    for (int pair = warp; 2 * pair < nl; pair += 8) {            // leaves: one per half-warp
-        const int j = 2 * pair + (lane >> 4);
-        reduce_node(std::integral_constant<int, 16>(), j * WC_LEAF, (j + 1) * WC_LEAF, lane & 15, NT + NM + l0 + j, beta_leaf,
-                    j < nl);
+    __syncthreads();
+
+    // ---- a group node from its children: centre from the children's areas and centres, radius from one pass
+    //      over its corners, moments by shifting the children's (add_shifted).  One warp per mid.
+    struct Centre { float px, py, pz, w, ux, uy, uz, cnt; };
+    auto centre_of = [&](const float* child, int nc) {
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = lane; c < nc; c += 32) {
+            const float* r = child + (size_t)c * PK_REC;
+            cs[0] += r[3]; cs[1] += r[3] * r[0]; cs[2] += r[3] * r[1]; cs[3] += r[3] * r[2];
+            cs[4] += r[4]; cs[5] += r[5]; cs[6] += r[6]; cs[7] += r[7];
+        }
+        group_sums<32>(cs, lane);
+        const bool weighted = cs[0] > 1e-30f;
+        const float inv = weighted ? 1.f / cs[0] : 1.f / fmaxf(cs[7], 1.f);
+        return Centre{(weighted ? cs[1] : cs[4]) * inv, (weighted ? cs[2] : cs[5]) * inv, (weighted ? cs[3] : cs[6]) * inv,
+                      cs[0], cs[4], cs[5], cs[6], cs[7]};
+    };
+    auto radius2 = [&](const Centre& p, int s0, int s1, int first, int stride) {
+        float r2 = 0.f;
+        for (int i = s0 + first; i < s1; i += stride) {
+            if (s_ok[i] == 0.f) continue;
+            const float* c = s_c + (size_t)i * 9;
+            const float ax = c[0] - p.px, ay = c[1] - p.py, az = c[2] - p.pz, bx = c[3] - p.px, by = c[4] - p.py,
+                        bz = c[5] - p.pz, gx = c[6] - p.px, gy = c[7] - p.py, gz = c[8] - p.pz;
+            r2 = fmaxf(r2, fmaxf(ax * ax + ay * ay + az * az, fmaxf(bx * bx + by * by + bz * bz, gx * gx + gy * gy + gz * gz)));
+        }
+        return group_max<32>(r2);
+    };
+    // the children's moments about p, summed over the warp: lane k < 23 returns raw sum k
+    auto shifted_sum = [&](const float* child, int nc, const Centre& p) {
+        NodeMoments mo;
+        for (int c = lane; c < nc; c += 32) add_shifted(mo, child + (size_t)c * PK_REC, p.px, p.py, p.pz);
+        float v[32];
+        mo.store_sums(v);
+#pragma unroll
+        for (int k = NodeMoments::N_SUMS; k < 32; ++k) v[k] = 0.f;
+        ReduceScatter<16, 32>::run(v, lane);
+        return v[0];
+    };
+    for (int n = warp; n < nm; n += 8) {
+        const int c0 = mid_off[m0 + n] - l0, c1 = mid_off[m0 + n + 1] - l0;
+        const float* child = s_leaf + (size_t)c0 * PK_REC;
+        const Centre p = centre_of(child, c1 - c0);
+        const float r2 = radius2(p, c0 * WC_LEAF, c1 * WC_LEAF, lane, 32);
+        const float total = shifted_sum(child, c1 - c0, p);
+        float* r = s_mid + (size_t)n * PK_REC;
+        float* o = (float*)(nb + (size_t)(NT + m0 + n) * WC_NODE_F4);
+        if (lane < 24) { r[PK_SUMS + lane] = total; o[4 + lane] = rec_scale(lane) * total; }
+        if (lane == 0) {
+            r[0] = p.px; r[1] = p.py; r[2] = p.pz; r[3] = p.w; r[4] = p.ux; r[5] = p.uy; r[6] = p.uz; r[7] = p.cnt;
+            *(float4*)o = make_float4(p.px, p.py, p.pz, r2 * (beta_group * beta_group * 1.0002f));
+        }
+    }
+    __syncthreads();
+    // ---- the top node from its mids: every warp takes a share of the radius pass, warp 0 shifts the moments
+    {
+        __shared__ float s_r2[8];
+        const Centre p = centre_of(s_mid, nm);                   // same sums in the same order in every warp
+        const float r2w = radius2(p, 0, n_slots, threadIdx.x, blockDim.x);
+        if (lane == 0) s_r2[warp] = r2w;
+        __syncthreads();
+        if (warp == 0) {
+            const float total = shifted_sum(s_mid, nm, p);
+            float* o = (float*)(nb + (size_t)t * WC_NODE_F4);
+            if (lane < 24) o[4 + lane] = rec_scale(lane) * total;
+            if (lane == 0) {
+                float r2 = 0.f;
+                for (int w = 0; w < 8; ++w) r2 = fmaxf(r2, s_r2[w]);
+                *(float4*)o = make_float4(p.px, p.py, p.pz, r2 * (beta_group * beta_group * 1.0002f));
+            }
+        }
     }
 }
 
@@ -923,8 +1021,8 @@ int launch_cluster_pack(const ClusterJob& j, cudaStream_t st) {
     dim3 grid(cdiv(j.NT + j.NM + j.K, 4), j.B);
     float beta_leaf, beta_group;
     cluster_pack_betas(j, &beta_leaf, &beta_group);
-    const size_t smem = (size_t)j.max_top_leaves * WC_LEAF * 10 * sizeof(float);
-    if (j.max_top_leaves > 0 && smem <= 200 * 1024) {
+    const size_t smem = (size_t)j.max_top_leaves * (WC_LEAF * 10 + 2 * PK_REC) * sizeof(float);
+    if (j.max_top_leaves > 0 && smem <= 200 * 1024 && !j.direct_pack) {
         static size_t attr_smem = 0;
         if (smem > attr_smem) {
             TUCH_CUDA(cudaFuncSetAttribute(cluster_pack_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -942,7 +1040,7 @@ int launch_cluster_pack(const ClusterJob& j, cudaStream_t st) {
 }
 
 // the far-field / near-field traversal alone, for the bodies [b0, b0 + nb) of the job
-static int launch_cluster_traverse(const ClusterJob& j, int b0, int nb, cudaStream_t st) {
+int launch_cluster_traverse(const ClusterJob& j, int b0, int nb, cudaStream_t st) {
     const float* points = j.points != nullptr ? j.points : j.verts;
     const int Q = j.points != nullptr ? j.Q : j.V;
     const int T = j.vtile != nullptr ? j.T : cdiv(Q, 32);
@@ -962,7 +1060,7 @@ static int launch_cluster_traverse(const ClusterJob& j, int b0, int nb, cudaStre
 }
 
 // split sum + list of the queries near the threshold, then their exact re-evaluation; whole job
-static int launch_cluster_finish(const ClusterJob& j, cudaStream_t st) {
+int launch_cluster_finish(const ClusterJob& j, cudaStream_t st) {
     const float* points = j.points != nullptr ? j.points : j.verts;
     const int Q = j.points != nullptr ? j.Q : j.V;
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));

@@ -71,6 +71,7 @@ struct ClusterJob {
     float packed_beta_leaf = 0.f, packed_beta_group = 0.f;
     int max_top_leaves = 0;          // largest top group in leaves (shared-memory staging of the pack kernel)
     int* stats = nullptr;            // optional device int: receives the length of the exact re-evaluation list
+    bool direct_pack = false;        // every node straight from its faces (cluster_pack_kernel): the test reference
 };
 // nearest_tiles.cu: masked nearest vertex over cluster-ordered 32-vertex tiles with bounding-sphere pruning
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);
@@ -83,6 +84,8 @@ int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
 void cluster_pack_betas(const ClusterJob& job, float* beta_leaf, float* beta_group);   // the radii it bakes in
+int launch_cluster_traverse(const ClusterJob& job, int b0, int nb, cudaStream_t st);   // the winding kernel alone
+int launch_cluster_finish(const ClusterJob& job, cudaStream_t st);    // finalize + exact refine
 int launch_cluster_query(const ClusterJob& job, cudaStream_t st);     // winding kernel + finalize + exact refine
 int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);  // both
 

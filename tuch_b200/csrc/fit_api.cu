@@ -12,53 +12,65 @@
 #include "objective_internal.h"
 #include "smpl_internal.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
-#include <utility>
+#include <tuple>
 
 using namespace tuch;
 
 namespace {
-// Two library-owned side streams per device.  Inside one iteration three chains are independent once the vertices
-// exist: the inside test (face hierarchy pack -> winding numbers -> exact re-evaluation -> segment whitelist), the
-// masked nearest vertex, and the joint-side terms (output joints, reprojection, pose prior, region minima).  The
-// inside test is the critical path, so it runs on a HIGH-PRIORITY stream (`s1`): its CTAs are dispatched first and
-// the nearest-vertex kernel on the caller's stream fills whatever the winding kernel leaves idle; the joint-side
-// terms run on `s2`.  They fork after the LBS forward and join before the losses that consume them.  At small
-// batches, where no single kernel fills the GPU, this is ~25 % of the iteration.  Events and waits are capturable:
-// in a CUDA graph the fork / join become plain dependencies and the kernel nodes keep their stream's priority.
-// At large batches both big kernels fill the GPU on their own and what overlap buys is co-residency (the
-// issue-bound winding kernel and the latency-bound nearest kernel share SMs better than either does alone): there
-// the two run at EQUAL priority (inside test on the caller's stream, nearest vertex on `s0`).
+// Library-owned streams of one iteration, per (device, caller's stream).  The iteration is two big kernels -- the
+// hierarchical winding kernel and the masked nearest vertex, ~80 % of the work -- and ~25 smaller ones before,
+// between and after them:
+//   hi   the chain (SMPL forward, hierarchy pack, finalize .. segment pass, losses, SMPL backward)
+//   s2   the joint-side terms (output joints, reprojection, pose prior, region minima; the per-joint reduction of
+//        the SMPL backward)
+//   mid  the winding kernel
+//   lo   the masked nearest vertex
+// The caller's stream only forks into `hi` at the start and joins it at the end.  Events and waits are capturable:
+// in a CUDA graph the forks / joins become plain dependencies and the kernel nodes keep their stream's priority.
+//
+// What the CUPTI timeline shows (scripts/diag/timeline.py, 256 bodies): the block scheduler hands out the CTAs of
+// equal-priority kernels in launch order, so the two big kernels run one after the other and only overlap at their
+// tails, and a small kernel launched behind a big one on another stream waits until that kernel's whole grid has
+// been DISPATCHED.  The iteration is bound by the sum of its kernels' work, not by exposed latency: giving the
+// chain priority moves its kernels forward but slows the nearest-vertex kernel by as much.  Measured, ms per
+// iteration, all streams at one priority / hi = s2 = mid above lo: 8 bodies 0.388 / 0.390, 32: 0.753 / 0.733,
+// 64: 1.179 / 1.130, 128: 1.955 / 1.991, 256: 3.607 / 3.690 (more than two levels change nothing).  So below
+// FIT_PRIORITY_BELOW bodies, where no kernel fills the GPU for long and the inside test is the longer chain, the
+// nearest vertex runs at low priority; from there on everything runs at one priority.
 struct Side {
-    cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;
-    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr, fork_b = nullptr, join_b = nullptr;
+    cudaStream_t hi = nullptr, mid = nullptr, lo = nullptr, s2 = nullptr;
+    cudaEvent_t begin = nullptr, fork = nullptr, before_trav = nullptr, after_trav = nullptr, join1 = nullptr,
+                join2 = nullptr, fork_b = nullptr, join_b = nullptr, done = nullptr;
 };
-constexpr int FIT_PRIORITY_BELOW = 192;      // bodies: below this the inside test gets the high-priority stream
+constexpr int FIT_PRIORITY_BELOW = 96;
 std::mutex g_side_mu;
-// one set per (device, caller's stream): fits that run concurrently on different streams must not meet on a shared
-// side stream.  (Tried, round 2: a batch of 256 as two concurrent fits of 128 on two streams, so that one half's
-// latency-bound head and tail overlap the other half's big kernels: 3.77 ms against 3.65 for the one fit, four fits
-// of 64: 3.93 -- the iteration is bound by its total instruction count, scripts/diag/two_halves.py.)
-std::map<std::pair<int, cudaStream_t>, Side> g_side;
+std::map<std::tuple<int, cudaStream_t, bool>, Side> g_side;
 
-int side_streams(cudaStream_t caller, Side** out) {
+int side_streams(cudaStream_t caller, bool prioritised, Side** out) {
     int dev = 0;
     TUCH_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_side_mu);
-    Side& s = g_side[std::make_pair(dev, caller)];
-    if (s.s1 == nullptr) {
+    Side& s = g_side[std::make_tuple(dev, caller, prioritised)];
+    if (s.hi == nullptr) {
         int least = 0, greatest = 0;
-        TUCH_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        TUCH_CUDA(cudaStreamCreateWithFlags(&s.s0, cudaStreamNonBlocking));
-        TUCH_CUDA(cudaStreamCreateWithPriority(&s.s1, cudaStreamNonBlocking, greatest));
-        TUCH_CUDA(cudaStreamCreateWithFlags(&s.s2, cudaStreamNonBlocking));
-        TUCH_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-        TUCH_CUDA(cudaEventCreateWithFlags(&s.join1, cudaEventDisableTiming));
-        TUCH_CUDA(cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming));
-        TUCH_CUDA(cudaEventCreateWithFlags(&s.fork_b, cudaEventDisableTiming));
-        TUCH_CUDA(cudaEventCreateWithFlags(&s.join_b, cudaEventDisableTiming));
+        TUCH_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));     // numerically lower = higher priority
+        // TUCH_FIT_PRIORITIES="h,m,l": levels above the default priority for hi (= s2) / mid / lo, at every batch
+        // size (A/B measurements)
+        int lv[3] = {prioritised ? 1 : 0, prioritised ? 1 : 0, 0};
+        if (const char* e = getenv("TUCH_FIT_PRIORITIES")) sscanf(e, "%d,%d,%d", &lv[0], &lv[1], &lv[2]);
+        auto level = [&](int l) { return least - l < greatest ? greatest : least - l; };
+        const int p_hi = level(lv[0]), p_mid = level(lv[1]), p_lo = level(lv[2]);
+        TUCH_CUDA(cudaStreamCreateWithPriority(&s.hi, cudaStreamNonBlocking, p_hi));
+        TUCH_CUDA(cudaStreamCreateWithPriority(&s.s2, cudaStreamNonBlocking, p_hi));
+        TUCH_CUDA(cudaStreamCreateWithPriority(&s.mid, cudaStreamNonBlocking, p_mid));
+        TUCH_CUDA(cudaStreamCreateWithPriority(&s.lo, cudaStreamNonBlocking, p_lo));
+        for (cudaEvent_t* e : {&s.begin, &s.fork, &s.before_trav, &s.after_trav, &s.join1, &s.join2, &s.fork_b, &s.join_b,
+                               &s.done})
+            TUCH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     *out = &s;
     return 0;
@@ -110,12 +122,14 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     // TUCH_FIT_STREAMS=0 keeps the whole iteration on the caller's stream (A/B measurements)
     static const bool one_stream = getenv("TUCH_FIT_STREAMS") != nullptr && atoi(getenv("TUCH_FIT_STREAMS")) == 0;
     Side* side = nullptr;
-    if (!one_stream) if (int rc = side_streams(st, &side)) return rc;
-    static const int prio_below = getenv("TUCH_FIT_PRIORITY_BELOW") != nullptr ? atoi(getenv("TUCH_FIT_PRIORITY_BELOW")) : FIT_PRIORITY_BELOW;
-    const bool prio = side != nullptr && B < prio_below;
-    // s_in: stream of the inside test, s_nn: stream of the masked nearest vertex, s2: joint-side terms
-    cudaStream_t s_in = !side ? st : prio ? side->s1 : st, s_nn = !side ? st : prio ? st : side->s0;
-    cudaStream_t s2 = side ? side->s2 : st;
+    if (!one_stream) if (int rc = side_streams((cudaStream_t)stream, B < FIT_PRIORITY_BELOW, &side)) return rc;
+    const cudaStream_t caller = (cudaStream_t)stream;
+    if (side) {                                  // from here on `st` is the high-priority chain
+        TUCH_CUDA(cudaEventRecord(side->begin, caller));
+        TUCH_CUDA(cudaStreamWaitEvent(side->hi, side->begin, 0));
+        st = side->hi;
+    }
+    const cudaStream_t s_nn = side ? side->lo : st, s2 = side ? side->s2 : st;
 
     // ---- SMPL forward (split pose; advances the Adam step counters); the output joints follow on side 2
     LbsBuffers w;
@@ -124,7 +138,7 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
                                     a->step_pose, a->step_orient)) return rc;
     if (side) {
         TUCH_CUDA(cudaEventRecord(side->fork, st));
-        TUCH_CUDA(cudaStreamWaitEvent(prio ? s_in : s_nn, side->fork, 0));
+        TUCH_CUDA(cudaStreamWaitEvent(s_nn, side->fork, 0));
         TUCH_CUDA(cudaStreamWaitEvent(s2, side->fork, 0));
     }
     // ---- side 2: joints, losses.py:56-64 (reprojection, pose prior) and the region minima of :108-117
@@ -152,10 +166,16 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
                                        topo->has_pair_mask ? topo->d_pair_mask : nullptr, topo->d_pair_word_off, mn, ai, aj, s2)) return rc;
     }
     if (side) TUCH_CUDA(cudaEventRecord(side->join2, s2));
-    // ---- losses.py:73-105: inside test + allowed self-intersections (high-priority side 1), masked nearest vertex
-    //      (caller's stream)
-    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, s_in, nullptr, &s_nn)) return rc;
-    if (side) TUCH_CUDA(cudaEventRecord(side->join1, prio ? s_in : s_nn));
+    // ---- losses.py:73-105: inside test + allowed self-intersections (winding kernel on `mid`, the rest on the
+    //      chain), masked nearest vertex (`lo`)
+    QueryStreams qs;
+    if (side) {
+        qs.nn = s_nn; qs.trav = side->mid; qs.split_trav = true;
+        qs.before_trav = side->before_trav; qs.after_trav = side->after_trav;
+    }
+    if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, st, nullptr,
+                                    side ? &qs : nullptr)) return rc;
+    if (side) TUCH_CUDA(cudaEventRecord(side->join1, s_nn));
     TUCH_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * BV, st));
     if (side) TUCH_CUDA(cudaStreamWaitEvent(st, side->join1, 0));
     if (int rc = launch_contact_loss(a->vertices, am, ext, a->body_active, nullptr, B, V, a->euclthres, PULL_THRESHOLD,
@@ -178,5 +198,11 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     TUCH_REQUIRE((a->grad_body_pose == nullptr) == (a->grad_global_orient == nullptr),
                  "tuch_contact_fit_step: give both gradient outputs or neither");
     LbsSide bs{s2, side ? side->fork_b : nullptr, side ? side->join_b : nullptr};
-    return launch_lbs_backward(m, a->body_pose, 0, B, w, g_verts, g_joints, nullptr, nullptr, st, &ad, side ? &bs : nullptr);
+    if (int rc = launch_lbs_backward(m, a->body_pose, 0, B, w, g_verts, g_joints, nullptr, nullptr, st, &ad,
+                                     side ? &bs : nullptr)) return rc;
+    if (side) {
+        TUCH_CUDA(cudaEventRecord(side->done, st));
+        TUCH_CUDA(cudaStreamWaitEvent(caller, side->done, 0));
+    }
+    return 0;
 }

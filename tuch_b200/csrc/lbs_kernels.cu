@@ -540,20 +540,25 @@ __global__ void lbs_contract_reduce_kernel(const float* __restrict__ partial, in
 
 // ------------------------------------------------------------------------------------------
 // backward 3/4: per (body, joint) reduction gA[b][k] = sum_{v in list(k)} w_vk g_v [v_posed; 1]^T.
-// One warp per (body, joint), no atomics (deterministic).
+// One CTA per (body, joint), no atomics (deterministic).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 lbs_bwd_joint_kernel(SmplDev m, const float* __restrict__ g_comb, const float* __restrict__ v_posed, int B,
                      float* __restrict__ gA) {
-    const int gw = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x & 31;
-    if (gw >= B * 24) return;
-    const int b = gw / 24, k = gw % 24;
+    // one CTA of four warps per (body, joint): the longest lists (torso joints, ~3k entries) were the critical
+    // path of the whole backward with one warp each; the four partial sums meet in warp order (deterministic,
+    // independent of the batch)
+    __shared__ float s_part[4][12];
+    const int b = blockIdx.x / 24, k = blockIdx.x % 24;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) acc[i] = 0.f;
     const float* gb = g_comb + (size_t)b * m.V * 3;
     const float* pb = v_posed + (size_t)b * m.V * 3;
-    for (int i = m.jl_off[k] + lane; i < m.jl_off[k + 1]; i += 32) {
+    const int i1 = m.jl_off[k + 1];
+#pragma unroll 2
+    for (int i = m.jl_off[k] + threadIdx.x; i < i1; i += 128) {
         const int v = m.jl_vert[i];
         const float w = m.jl_w[i];
         const float g[3] = {w * gb[3 * v], w * gb[3 * v + 1], w * gb[3 * v + 2]};
@@ -567,13 +572,14 @@ lbs_bwd_joint_kernel(SmplDev m, const float* __restrict__ g_comb, const float* _
         }
     }
 #pragma unroll
-    for (int i = 0; i < 12; ++i)
+    for (int i = 0; i < 12; ++i) {
         for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-    if (lane == 0) {
-        float* out = gA + ((size_t)b * 24 + k) * 12;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) out[i] = acc[i];
+        if (lane == 0) s_part[warp][i] = acc[i];
     }
+    __syncthreads();
+    if (threadIdx.x < 12)
+        gA[((size_t)b * 24 + k) * 12 + threadIdx.x] =
+            ((s_part[0][threadIdx.x] + s_part[1][threadIdx.x]) + s_part[2][threadIdx.x]) + s_part[3][threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -812,7 +818,7 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
     if (side != nullptr) {
         TUCH_CUDA(cudaEventRecord(side->fork, st));
         TUCH_CUDA(cudaStreamWaitEvent(st_j, side->fork, 0));
-        lbs_bwd_joint_kernel<<<cdiv(B * 24, 4), 128, 0, st_j>>>(m, w.g_comb, w.v_posed, B, w.gA);
+        lbs_bwd_joint_kernel<<<B * 24, 128, 0, st_j>>>(m, w.g_comb, w.v_posed, B, w.gA);
         TUCH_LAUNCH_CHECK(); count_launch();
         TUCH_CUDA(cudaEventRecord(side->join, st_j));
     }
@@ -832,7 +838,7 @@ int launch_lbs_backward(const SmplDev& m, const float* pose, int pose_is_rotmat,
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     if (side == nullptr) {
-        lbs_bwd_joint_kernel<<<cdiv(B * 24, 4), 128, 0, st>>>(m, w.g_comb, w.v_posed, B, w.gA);
+        lbs_bwd_joint_kernel<<<B * 24, 128, 0, st>>>(m, w.g_comb, w.v_posed, B, w.gA);
         TUCH_LAUNCH_CHECK(); count_launch();
     } else {
         TUCH_CUDA(cudaStreamWaitEvent(st, side->join, 0));

@@ -195,7 +195,7 @@ __device__ __forceinline__ void nearest_visit_tile(const float4* __restrict__ vb
 }
 
 // grid (groups of NT_WARPS query tiles, bodies)
-__global__ void __launch_bounds__(NT_WARPS * 32)
+__global__ void __launch_bounds__(NT_WARPS * 32, 10)
 nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
                      const uint32_t* __restrict__ maskP, const uint32_t* __restrict__ maskG,
                      const int* __restrict__ vtile, const int* __restrict__ vgroup_off, int V, int T, int NG,
@@ -255,34 +255,35 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     // pass 2: every tile whose sphere can still hold a row at or below the running minimum; groups of
     // tiles are tested first.  The slack covers the rows' fp32 expansion-form values undershooting their
     // true squared distance (<= 3.6e-7 (|v|^2 + |q|^2)).
+    // thr: the running minimum with the query's share of the slack folded in, refreshed after every visit
+    float thr = fmaf(st.best, 1.00001f, 4e-6f * q.w);
     for (int g = 0; g < NG; ++g) {
         const float4 gs = __ldg(ib + 2 * (T + g)), gs2 = __ldg(ib + 2 * (T + g) + 1);
         const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
         const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
         // lanes without any unmasked row (padding slots, fully masked columns) never vote
-        const bool gneed = tstar >= 0 && (glo <= 0.f || glo * glo <= fmaf(st.best, 1.00001f, 4e-6f * (q.w + gs2.x)));
+        const bool gneed = tstar >= 0 && (glo <= 0.f || glo * glo <= fmaf(4e-6f, gs2.x, thr));
         if (!__any_sync(0xffffffffu, gneed)) continue;
         const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
-        for (int t = t0; t < t1; ++t) {
-            const uint32_t m = mcol[(size_t)t * mstride];
-            const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
+        const uint32_t* mp = mcol + (size_t)t0 * mstride;
+        const float4* sp = ib + 2 * t0;
+        for (int t = t0; t < t1; ++t, mp += mstride, sp += 2) {
+            const uint32_t m = *mp;
+            const float4 s = __ldg(sp), s2 = __ldg(sp + 1);
             const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
             const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
-            const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(st.best, 1.00001f, 4e-6f * (q.w + s2.x)));
+            const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(4e-6f, s2.x, thr));
             if (!__any_sync(0xffffffffu, need)) continue;
             if (__any_sync(0xffffffffu, tstar == t)) continue;          // evaluated for the whole warp above
             nearest_visit_tile(vb, vtile, mcol, mstride, t, m, pad, q, st);
+            thr = fmaf(st.best, 1.00001f, 4e-6f * q.w);
         }
     }
-    // the attaining rows: one scan per distinct attaining tile of the warp (its queries are neighbours: a few)
-    todo = __ballot_sync(0xffffffffu, st.bi < 0 && st.btile >= 0);
-    while (todo != 0u) {
-        const int ts = __shfl_sync(0xffffffffu, st.btile, __ffs(todo) - 1);
-        const bool mine = st.bi < 0 && st.btile == ts;
-        const int r = tile_first_row(vb + ts * 32, vtile + ts * 32, mcol[(size_t)ts * mstride], q, st.best);
-        if (mine) st.bi = r;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-    }
+    // the attaining rows: every query scans the 32 rows of ITS attaining tile once (per-lane gathers -- a warp's
+    // queries attain their minima in ~9 different tiles, and one uniform scan per distinct tile was 17 % of the
+    // kernel's instructions)
+    if (st.bi < 0 && st.btile >= 0)
+        st.bi = tile_first_row(vb + st.btile * 32, vtile + st.btile * 32, mcol[(size_t)st.btile * mstride], q, st.best);
     if (oc >= 0) {
         const bool none = st.btile < 0;                                // fully masked column
         argmin_out[(size_t)b * V + oc] = none ? 0 : st.bi;

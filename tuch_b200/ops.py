@@ -233,6 +233,16 @@ class Topology:
             check(lib().tuch_topology_query_stats(self._h, C.byref(a), C.byref(b), _stream()), 'tuch_topology_query_stats')
         return dict(refine_vertices=int(a.value), refine_points=int(b.value))
 
+    def pack_nodes(self, verts, direct=False):
+        """-> [B, tops + mids + leaves, 28] node records of the face hierarchy for verts [B,V,3] (test hook)."""
+        v = _f32(verts, 'verts')
+        st = self.cluster_stats()
+        out = torch.empty(v.shape[0], st['tops'] + st['mids'] + st['leaves'], 28, device=v.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().tuch_topology_pack_nodes(self._h, _ptr(v), int(v.shape[0]), int(bool(direct)), _ptr(out), _stream()),
+                  'tuch_topology_pack_nodes')
+        return out
+
     # geomask = geodist > geothres (smplifydc.py:65)
     def set_geodist(self, geodist, geothres):
         g = _f32(geodist.to(self.device) if isinstance(geodist, torch.Tensor) else
