@@ -173,6 +173,15 @@ int tuch_cluster_tree_host(const int32_t* faces_host, int F, int V, const float*
 int tuch_contact_query(const tuch_topology* topo, const float* verts, int B, int use_segments,
                        int32_t* argmin, float* min_sq, float* winding, uint8_t* exterior, void* stream);
 
+/* The same query with the nearest vertex restricted to what SMPLify-DC's contact term consumes (losses.py:96-103:
+ * the nearest allowed vertex of every INTERIOR vertex, and of an exterior vertex only when it is closer than
+ * euclthres): argmin / min_sq are exactly tuch_contact_query's for every interior vertex (before the segment
+ * whitelist) and for every vertex with an allowed vertex within `radius` metres, and (-1, +inf) for the others
+ * ((0, +inf), as above, for a vertex whose mask column is empty).  tuch_contact_loss reads -1 as "infinitely far".
+ * About a fifth of the unlimited query's work at radius = 0.02.  exterior and one of argmin / min_sq are required. */
+int tuch_contact_query_within(const tuch_topology* topo, const float* verts, int B, int use_segments, float radius,
+                              int32_t* argmin, float* min_sq, float* winding, uint8_t* exterior, void* stream);
+
 /* has_self_isect for every segment (segmentation.py:81-99,117-124): out[b][k] = 1 where the k-th
  * entry of the concatenated segment vertex lists is EXTERIOR to its closed segment.
  * out uint8 [B, total_segment_verts]. */
@@ -320,7 +329,7 @@ typedef struct tuch_contact_fit_args {
     float* loss;                 /* scalar: the objective summed over the batch (losses.py:123) */
     float* per_body;             /* [B] or NULL */
     uint8_t* exterior;           /* [B,V] or NULL */
-    int32_t* argmin;             /* [B,V] or NULL */
+    int32_t* argmin;             /* [B,V] or NULL: as tuch_contact_query_within(radius = euclthres) leaves it */
     float* grad_body_pose;       /* [B,69] or NULL: the gradients Adam consumed (both or neither) */
     float* grad_global_orient;   /* [B,3]  or NULL */
     /* configuration */

@@ -22,7 +22,7 @@ for B in [int(x) for x in sys.argv[1:]] or [32]:
     fit = rig.begin(s, a, d)
     ms_e, _ = rig.timed(fit.step, 20, warmup=5)
     fit_g = rig.begin(s, a, d).capture()
-    ms_g, _ = rig.timed(fit_g.step, 50, warmup=5)
+    ms_g, _ = rig.timed(fit_g.step, 20, warmup=5)      # same iterations as the eager fit: later ones do more work
     cam = bench.stage1_fit(rig, s, d)
     ms_1, _ = rig.timed(cam.step, 50, warmup=5)
     print('B=%d  stage-2 eager %.3f ms  graph %.3f ms  | stage-1 graph %.3f ms' % (B, ms_e, ms_g, ms_1))

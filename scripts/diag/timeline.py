@@ -1,5 +1,5 @@
 """Kernel timeline of one fused stage-2 iteration (CUPTI through torch.profiler): name, stream, start and duration
-of every kernel, relative to the first kernel of the iteration.  Usage: python scripts/diag/timeline.py [B]"""
+of every kernel, relative to the first kernel of the iteration.  Usage: python scripts/diag/timeline.py [B] [graph]"""
 import json
 import os
 import sys
@@ -18,11 +18,14 @@ class A:
 
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+graph = len(sys.argv) > 2 and sys.argv[2] == 'graph'
 rig = bench.Rig(A)
 a = bench.make_assets(B, seed=1000)
 d = {k: rig.t(a['inp'][k]) for k in bench.INPUT_KEYS}
 s = rig.stack(a, B, num_iters=10)
 fit = rig.begin(s, a, d)
+if graph:
+    fit = fit.capture()
 for _ in range(5):
     fit.step()
 torch.cuda.synchronize()

@@ -305,6 +305,35 @@ def test_hierarchical_winding_full_size(dev, full_assets, full_assets_uv):
     _fast_vs_exact(full_assets_uv, dev, batch=4, seed=23, template=True)
 
 
+@pytest.mark.parametrize('radius', [0.02, 0.05, 0.0])
+def test_contact_query_within_radius(dev, full_assets, radius):
+    """tuch_contact_query_within: the nearest vertex only where losses.py:96-103 reads it.  Interior vertices and
+    vertices with an allowed vertex within the radius get exactly the unlimited answer, the rest (-1, inf)."""
+    from oracle import lbs as olbs
+    from tuch_b200 import synthetic as syn
+    tm = olbs.to_torch_model(full_assets['model'])
+    pose = torch.tensor(np.concatenate([syn.fold_arms_pose(3, seed=70 + k, fold=0.7 + 0.1 * k) for k in range(3)]))
+    betas = torch.tensor(np.random.default_rng(70).normal(0, 0.5, size=(9, 10)).astype(np.float32))
+    verts = olbs.smpl_forward(tm, betas, pose[:, 3:], pose[:, :3])[0].to(dev).contiguous()
+    topo = make_topology(full_assets, dev, regions=False, exact=False)
+    full = topo.contact_query(verts, use_segments=True)
+    lim = topo.contact_query(verts, use_segments=True, within=radius)
+    assert torch.equal(full['exterior'], lim['exterior']) and torch.equal(full['winding'], lim['winding'])
+    must = (full['winding'] > 0.99) | (full['min_sq'] <= radius * radius)
+    assert int(must.sum()) > 100 and int((~must).sum()) > 10000
+    assert torch.equal(lim['argmin'][must], full['argmin'][must]) and torch.equal(lim['min_sq'][must], full['min_sq'][must])
+    rest_ok = (lim['argmin'] == -1) & torch.isinf(lim['min_sq']) | (lim['argmin'] == full['argmin']) & (lim['min_sq'] == full['min_sq'])
+    assert bool(rest_ok.all())
+    assert int((lim['argmin'][~must] == -1).sum()) > 0.9 * int((~must).sum())
+    # the contact term over either answer is the same number and the same gradient
+    from tuch_b200 import ops
+    if radius > 0:
+        ga, gb = torch.zeros_like(verts), torch.zeros_like(verts)
+        la, _ = ops.contact_loss(verts, full['argmin'], full['exterior'], radius, g_points=ga)
+        lb, _ = ops.contact_loss(verts, lim['argmin'], lim['exterior'], radius, g_points=gb)
+        assert torch.equal(la, lb) and torch.equal(ga, gb) and float(ga.abs().max()) > 0
+
+
 def test_group_nodes_from_shifted_child_moments(dev, full_assets, full_assets_uv):
     """The pack kernel forms mid and top nodes from their children's moments, re-expressed about the parent's
     centre (exact identities, clusters.cu add_shifted), instead of a second and third pass over the faces:

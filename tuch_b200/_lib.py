@@ -62,6 +62,7 @@ def _declare(lib):
     lib.tuch_topology_set_regions.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     lib.tuch_topology_set_segments.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.tuch_contact_query.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.tuch_contact_query_within.argtypes = [vp, vp, i32, i32, f32, vp, vp, vp, vp, vp]
     lib.tuch_segment_exterior.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.tuch_region_min.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.tuch_smpl_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, vp, C.POINTER(vp)]

@@ -699,6 +699,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     const size_t h_am = sc.plan((want_nn && !argmin) ? sizeof(int) * (size_t)B * V : 0);
     const size_t h_mn = sc.plan((want_nn && !min_sq) ? sizeof(float) * (size_t)B * V : 0);
     const size_t h_apex = sc.plan(segs ? sizeof(float) * 3 * (size_t)B * (t->n_bands > 0 ? t->n_bands : 1) : 0);
+    const size_t h_wl = sc.plan(segs ? sizeof(int) * ((size_t)B * t->n_sv + 1) : 0);
     if (int rc = sc.commit(st)) return rc;
 
     float4* strip4 = want_w ? sc.get<float4>(h_tri) : nullptr;
@@ -706,6 +707,12 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     if (vert4 != nullptr && !nn_tiles)
         if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, nullptr, vert4, st)) return rc;
 
+    const bool nn_after_flags = nn_tiles && qs != nullptr && qs->nn_limit >= 0.f && exterior != nullptr && want_w;
+    int* am_nn = want_nn ? (argmin ? argmin : sc.get<int>(h_am)) : nullptr;
+    float* mn_nn = want_nn ? (min_sq ? min_sq : sc.get<float>(h_mn)) : nullptr;
+    if (nn_after_flags)                                   // tile / group spheres: independent of the inside test
+        if (int rc = launch_nearest_tiles_pack(verts, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4, sc.get<float4>(h_tinfo),
+                                               st_nn)) return rc;
     if (want_w) {
         float* w = winding ? winding : sc.get<float>(h_w);
         float4* info = sc.get<float4>(h_info);
@@ -738,18 +745,31 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
             uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;
             if (any) TUCH_CUDA(cudaMemsetAsync(any, 0, (size_t)B, st));
             if (int rc = launch_exterior_init(w, B, V, exterior, any, st)) return rc;
+            if (nn_after_flags) {
+                // the nearest vertex once the flags exist: interior vertices without a limit, exterior ones within
+                // nn_limit.  It reads the flags while the segment pass below may still turn some of them to
+                // "exterior": either value is fine, a vertex read as interior merely gets the unlimited answer
+                // where the limited one would have done
+                if (st_nn != st) {
+                    TUCH_CUDA(cudaEventRecord(qs->after_ext, st));
+                    TUCH_CUDA(cudaStreamWaitEvent(st_nn, qs->after_ext, 0));
+                }
+                if (int rc = launch_nearest_tiles_query(t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, 0, B, V, T, t->NG,
+                                                        vert4, sc.get<float4>(h_tinfo), qs->nn_limit, exterior, am_nn, mn_nn,
+                                                        st_nn)) return rc;
+            }
             if (segs) {
                 float* apex = sc.get<float>(h_apex);
                 if (int rc = launch_segment_apex(verts, B, V, t->d_loop_off, t->d_loop_ids, t->n_bands, apex, any, st)) return rc;
                 if (int rc = launch_segment_whitelist(verts, B, V, apex, t->n_bands, t->d_seg_faces, t->d_seg_face_off,
                                                       t->d_seg_band0, t->d_seg_vidx, t->d_member_seg, t->n_sv, exterior,
-                                                      any, st)) return rc;
+                                                      any, sc.get<int>(h_wl), st)) return rc;
             }
         }
     }
-    if (want_nn) {
-        int* am = argmin ? argmin : sc.get<int>(h_am);
-        float* mn = min_sq ? min_sq : sc.get<float>(h_mn);
+    if (want_nn && !nn_after_flags) {
+        int* am = am_nn;
+        float* mn = mn_nn;
         if (nn_tiles) {
             if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4,
                                               sc.get<float4>(h_tinfo), am, mn, st_nn)) return rc;
@@ -767,6 +787,20 @@ TUCH_EXPORT int tuch_contact_query(const tuch_topology* topo, const float* verts
                                    void* stream) {
     return contact_query_impl(topo, verts, B, use_segments, argmin, min_sq, winding, exterior, nullptr,
                               (cudaStream_t)stream);
+}
+
+TUCH_EXPORT int tuch_contact_query_within(const tuch_topology* topo, const float* verts, int B, int use_segments,
+                                          float radius, int32_t* argmin, float* min_sq, float* winding, uint8_t* exterior,
+                                          void* stream) {
+    TUCH_REQUIRE(radius >= 0.f, "tuch_contact_query_within: negative radius");
+    TUCH_REQUIRE(exterior != nullptr && (argmin != nullptr || min_sq != nullptr),
+                 "tuch_contact_query_within: needs the exterior output and a nearest-vertex output");
+    TUCH_REQUIRE(topo != nullptr && topo->has_maskP, "tuch_contact_query_within: the topology needs a geodesic mask and vertex tiles");
+    QueryStreams qs;
+    qs.nn = (cudaStream_t)stream;
+    qs.nn_limit = radius;
+    return contact_query_impl(topo, verts, B, use_segments, argmin, min_sq, winding, exterior, nullptr, (cudaStream_t)stream,
+                              nullptr, &qs);
 }
 
 TUCH_EXPORT int tuch_segment_exterior(const tuch_topology* t, const float* verts, int B, uint8_t* out,

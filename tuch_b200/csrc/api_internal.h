@@ -78,7 +78,7 @@ int launch_segment_pack(const float* verts, int B, int V, const float* apex, int
 int launch_segment_whitelist(const float* verts, int B, int V, const float* apex, int n_bands, const int* seg_faces,
                              const int* seg_face_off, const int* seg_band0, const int* seg_vidx,
                              const int* member_seg, int n_sv, uint8_t* exterior, const uint8_t* body_active,
-                             cudaStream_t st);
+                             int* list, cudaStream_t st);
 int launch_exterior_init(const float* winding, int B, int V, uint8_t* exterior, uint8_t* any_interior,
                          cudaStream_t st);
 int launch_segment_apply(const float* seg_winding, const int* seg_vidx, int n_sv, int B, int V,
@@ -102,6 +102,12 @@ struct QueryStreams {
     cudaStream_t nn = nullptr, trav = nullptr;
     bool split_trav = false;
     cudaEvent_t before_trav = nullptr, after_trav = nullptr;
+    // nn_limit >= 0 (needs the exterior output): the nearest vertex is searched AFTER the inside test, without a
+    // limit for the interior vertices and among the candidates within nn_limit metres for the exterior ones.
+    // argmin / min_sq are then exact for every interior vertex and for every vertex with an allowed vertex within
+    // the limit, and (-1, +inf) elsewhere: all that losses.py:96-103 consumes.
+    float nn_limit = -1.f;
+    cudaEvent_t after_ext = nullptr;          // orders that search (on nn) after the flags (on st) when nn != st
 };
 int contact_query_impl(const tuch_topology* t, const float* verts, int B, int use_segments, int32_t* argmin,
                        float* min_sq, float* winding, uint8_t* exterior, float4* vert4_out, cudaStream_t st,

@@ -81,6 +81,12 @@ int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32
                          const int* vgroup_off, int B, int V, int T, int NG, float4* vert4p, float4* tinfo,
                          int* argmin, float* minval, cudaStream_t st);
 
+int launch_nearest_tiles_pack(const float* verts, const int* vtile, const int* vgroup_off, int B, int V, int T, int NG,
+                              float4* vert4p, float4* tinfo, cudaStream_t st);
+int launch_nearest_tiles_query(const uint32_t* maskP, const uint32_t* maskG, const int* vtile, const int* vgroup_off,
+                               int b0, int nb, int V, int T, int NG, const float4* vert4p, const float4* tinfo,
+                               float limit, const uint8_t* exterior, int* argmin, float* minval, cudaStream_t st);
+
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
 void cluster_pack_betas(const ClusterJob& job, float* beta_leaf, float* beta_group);   // the radii it bakes in

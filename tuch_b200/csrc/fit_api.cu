@@ -41,12 +41,15 @@ namespace {
 // 64: 1.179 / 1.130, 128: 1.955 / 1.991, 256: 3.607 / 3.690 (more than two levels change nothing).  So below
 // FIT_PRIORITY_BELOW bodies, where no kernel fills the GPU for long and the inside test is the longer chain, the
 // nearest vertex runs at low priority; from there on everything runs at one priority.
+// Also tried at 256 bodies: the nearest-vertex query in two launches, one ahead of the hierarchy pack and one behind
+// the winding kernel, so that the pack is overlapped too: 3.52 against 3.53 ms eager, no gain (the pack kernel's
+// CTAs fill the register file, nothing co-resides with them).
 struct Side {
     cudaStream_t hi = nullptr, mid = nullptr, lo = nullptr, s2 = nullptr;
     cudaEvent_t begin = nullptr, fork = nullptr, before_trav = nullptr, after_trav = nullptr, join1 = nullptr,
-                join2 = nullptr, fork_b = nullptr, join_b = nullptr, done = nullptr;
+                join2 = nullptr, fork_b = nullptr, join_b = nullptr, done = nullptr, after_ext = nullptr;
 };
-constexpr int FIT_PRIORITY_BELOW = 96;
+constexpr int FIT_NN_LIMIT_FROM = 48;
 std::mutex g_side_mu;
 std::map<std::tuple<int, cudaStream_t, bool>, Side> g_side;
 
@@ -69,7 +72,7 @@ int side_streams(cudaStream_t caller, bool prioritised, Side** out) {
         TUCH_CUDA(cudaStreamCreateWithPriority(&s.mid, cudaStreamNonBlocking, p_mid));
         TUCH_CUDA(cudaStreamCreateWithPriority(&s.lo, cudaStreamNonBlocking, p_lo));
         for (cudaEvent_t* e : {&s.begin, &s.fork, &s.before_trav, &s.after_trav, &s.join1, &s.join2, &s.fork_b, &s.join_b,
-                               &s.done})
+                               &s.done, &s.after_ext})
             TUCH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     *out = &s;
@@ -122,7 +125,7 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     // TUCH_FIT_STREAMS=0 keeps the whole iteration on the caller's stream (A/B measurements)
     static const bool one_stream = getenv("TUCH_FIT_STREAMS") != nullptr && atoi(getenv("TUCH_FIT_STREAMS")) == 0;
     Side* side = nullptr;
-    if (!one_stream) if (int rc = side_streams((cudaStream_t)stream, B < FIT_PRIORITY_BELOW, &side)) return rc;
+    if (!one_stream) if (int rc = side_streams((cudaStream_t)stream, true, &side)) return rc;
     const cudaStream_t caller = (cudaStream_t)stream;
     if (side) {                                  // from here on `st` is the high-priority chain
         TUCH_CUDA(cudaEventRecord(side->begin, caller));
@@ -168,13 +171,23 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     if (side) TUCH_CUDA(cudaEventRecord(side->join2, s2));
     // ---- losses.py:73-105: inside test + allowed self-intersections (winding kernel on `mid`, the rest on the
     //      chain), masked nearest vertex (`lo`)
+    // The contact term (launch_contact_loss below, PULL_THRESHOLD) reads the nearest allowed vertex of interior
+    // vertices and of exterior vertices closer than euclthres only: the query is limited accordingly (nn_limit),
+    // which leaves loss, gradients and parameters bit-identical (tests/test_objective_gpu.py compares with the
+    // composition over the unlimited query) at a fifth of the nearest-vertex work.
     QueryStreams qs;
+    qs.nn = st;
+    static const bool nn_full = getenv("TUCH_FIT_NN_FULL") != nullptr && atoi(getenv("TUCH_FIT_NN_FULL")) != 0;   // A/B
+    // (below FIT_NN_LIMIT_FROM bodies the unlimited query hides behind the inside test anyway and the second pass
+    // would only lengthen the chain: 32 bodies 0.687 against 0.716 ms)
+    static const int nn_from = getenv("TUCH_FIT_NN_FROM") != nullptr ? atoi(getenv("TUCH_FIT_NN_FROM")) : FIT_NN_LIMIT_FROM;
+    if (!nn_full && topo->has_maskP && B >= nn_from) qs.nn_limit = a->euclthres > 0.f ? a->euclthres : 0.f;
     if (side) {
         qs.nn = s_nn; qs.trav = side->mid; qs.split_trav = true;
-        qs.before_trav = side->before_trav; qs.after_trav = side->after_trav;
+        qs.before_trav = side->before_trav; qs.after_trav = side->after_trav; qs.after_ext = side->after_ext;
     }
     if (int rc = contact_query_impl(topo, a->vertices, B, a->use_segments, am, nullptr, nullptr, ext, nullptr, st, nullptr,
-                                    side ? &qs : nullptr)) return rc;
+                                    &qs)) return rc;
     if (side) TUCH_CUDA(cudaEventRecord(side->join1, s_nn));
     TUCH_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * BV, st));
     if (side) TUCH_CUDA(cudaStreamWaitEvent(st, side->join1, 0));

@@ -182,7 +182,7 @@ __device__ __forceinline__ void nearest_visit_tile(const float4* __restrict__ vb
                                                    bool pad, const float4& q, NearestState& st) {
     const bool full = __all_sync(0xffffffffu, m == 0xffffffffu || pad);
     const float lb = full ? tile_min<true>(vb + t * 32, m, q) : tile_min<false>(vb + t * 32, m, q);
-    const bool tie = lb == st.best && lb < INFINITY && t != st.btile;
+    const bool tie = lb == st.best && lb < INFINITY && t != st.btile && st.btile >= 0;
     if (lb < st.best) { st.best = lb; st.btile = t; st.bi = -1; }
     if (__any_sync(0xffffffffu, tie)) {
         if (tie) {
@@ -195,17 +195,31 @@ __device__ __forceinline__ void nearest_visit_tile(const float4* __restrict__ vb
 }
 
 // grid (groups of NT_WARPS query tiles, bodies)
-__global__ void __launch_bounds__(NT_WARPS * 32, 10)
+//
+// MIXED: per query, only candidates within `limit` (metres) count unless the query's `unlimited` byte is 0 ... see
+// below.  SMPLify-DC's contact term consumes the nearest allowed vertex of an INTERIOR vertex at any distance, but
+// of an EXTERIOR vertex only when it is closer than euclthres (losses.py:96-103, 2 cm): with the limit as the
+// initial bound of the exterior queries nearly every tile is pruned at the group level, and the seeding pass runs
+// for the interior queries only.  A limited query with an allowed vertex inside the limit gets exactly the
+// unlimited answer (same values, same tie-breaking); one without gets (-1, +inf) -- or (0, +inf), as in the
+// unlimited case, when its mask column is empty.  The limit carries the slack by which an fp32 expansion-form value
+// can exceed the true squared distance.
+// exterior (MIXED only, [B][V]): the inside test's flags; 0 = interior = unlimited query.
+template <bool MIXED>
+__global__ void __launch_bounds__(NT_WARPS * 32)
 nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
                      const uint32_t* __restrict__ maskP, const uint32_t* __restrict__ maskG,
                      const int* __restrict__ vtile, const int* __restrict__ vgroup_off, int V, int T, int NG,
-                     int* __restrict__ argmin_out, float* __restrict__ min_out) {
+                     float limit, const uint8_t* __restrict__ exterior, int* __restrict__ argmin_out,
+                     float* __restrict__ min_out) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int qt = blockIdx.x * NT_WARPS + (threadIdx.x >> 5);
     if (qt >= T) return;
     const int slot = qt * 32 + lane;                                   // query column (tile slot)
     const int oc = vtile[slot];                                        // original vertex id, -1 = padding
+    const bool limited = MIXED && oc >= 0 && exterior[(size_t)b * V + oc] != 0;
+    const bool seeded = oc >= 0 && !limited;                           // takes part in pass 1
     const float4* vb = vert4p + (size_t)b * T * 32;
     const float4* ib = tinfo + (size_t)b * (T + NG) * 2;
     const float4 q = vb[slot];
@@ -216,14 +230,14 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     // its sphere -- that holds an unmasked row for this query, then the tile of that group whose sphere promises
     // the smallest masked distance |q - c| + R.  Queries of a warp are neighbours: few distinct groups.
     int gstar = -1;
-    {
+    if (!MIXED || __any_sync(0xffffffffu, seeded)) {
         float glo_best = INFINITY;
         for (int g = 0; g < NG; ++g) {
             const float4 gs = __ldg(ib + 2 * (T + g));
             const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
             const float glo = sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))) - gs.w;
             const bool has = (maskG[(size_t)(g >> 5) * mstride + slot] >> (g & 31)) & 1u;
-            if (has && glo < glo_best) { glo_best = glo; gstar = g; }
+            if (has && seeded && glo < glo_best) { glo_best = glo; gstar = g; }
         }
     }
     float ub = INFINITY;
@@ -245,7 +259,9 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     // evaluate those tiles first (a warp's queries are neighbours: few distinct ones): from here on
     // `best` is a tight bound for the sphere test
     NearestState st;
+    if (limited) st.best = fmaf(limit * limit, 1.001f, 4e-6f * (3.f * q.w + 2.f * limit * limit));
     const bool pad = oc < 0;
+    const bool live = limited || tstar >= 0;                           // votes in pass 2
     unsigned todo = __ballot_sync(0xffffffffu, tstar >= 0);
     while (todo != 0u) {
         const int ts = __shfl_sync(0xffffffffu, tstar, __ffs(todo) - 1);
@@ -262,17 +278,26 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
         const float glo = fmaf(sqrt_approx(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w);
         // lanes without any unmasked row (padding slots, fully masked columns) never vote
-        const bool gneed = tstar >= 0 && (glo <= 0.f || glo * glo <= fmaf(4e-6f, gs2.x, thr));
+        const bool gneed = live && (glo <= 0.f || glo * glo <= fmaf(4e-6f, gs2.x, thr));
         if (!__any_sync(0xffffffffu, gneed)) continue;
         const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
         const uint32_t* mp = mcol + (size_t)t0 * mstride;
         const float4* sp = ib + 2 * t0;
         for (int t = t0; t < t1; ++t, mp += mstride, sp += 2) {
-            const uint32_t m = *mp;
+            uint32_t m = 0u;
+            if (!MIXED) m = *mp;
             const float4 s = __ldg(sp), s2 = __ldg(sp + 1);
             const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
             const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
-            const bool need = m != 0u && (lo <= 0.f || lo * lo <= fmaf(4e-6f, s2.x, thr));
+            const bool reach = lo <= 0.f || lo * lo <= fmaf(4e-6f, s2.x, thr);
+            if (MIXED) {
+                // limited queries reach next to no tile: test the sphere first and only then wait for the mask
+                // word (an L2 round trip per tile; for unlimited queries, whose spheres mostly pass, the word is
+                // better requested up front)
+                if (!__any_sync(0xffffffffu, live && reach)) continue;
+                m = *mp;
+            }
+            const bool need = m != 0u && reach && (!MIXED || live);
             if (!__any_sync(0xffffffffu, need)) continue;
             if (__any_sync(0xffffffffu, tstar == t)) continue;          // evaluated for the whole warp above
             nearest_visit_tile(vb, vtile, mcol, mstride, t, m, pad, q, st);
@@ -285,8 +310,14 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     if (st.bi < 0 && st.btile >= 0)
         st.bi = tile_first_row(vb + st.btile * 32, vtile + st.btile * 32, mcol[(size_t)st.btile * mstride], q, st.best);
     if (oc >= 0) {
-        const bool none = st.btile < 0;                                // fully masked column
-        argmin_out[(size_t)b * V + oc] = none ? 0 : st.bi;
+        const bool none = st.btile < 0;                                // fully masked column, or nothing within the limit
+        int none_id = 0;
+        if (limited && none) {
+            uint32_t any = 0u;
+            for (int w = 0; w < (NG + 31) / 32; ++w) any |= maskG[(size_t)w * mstride + slot];
+            none_id = any != 0u ? -1 : 0;
+        }
+        argmin_out[(size_t)b * V + oc] = none ? none_id : st.bi;
         min_out[(size_t)b * V + oc] = none ? INFINITY : st.best;
     }
 }
@@ -305,27 +336,47 @@ int launch_group_mask(const uint32_t* maskP, const int* vgroup_off, int T, int N
     return 0;
 }
 
+// tile / group spheres of every body, then the query kernel over the bodies [b0, b0 + nb): the fused iteration
+// launches the bodies in two parts, one ahead of the inside test and one behind it (fit_api.cu)
+int launch_nearest_tiles_pack(const float* verts, const int* vtile, const int* vgroup_off, int B, int V, int T, int NG,
+                              float4* vert4p, float4* tinfo, cudaStream_t st) {
+    if (B == 0) return 0;
+    KernelTimer timer("nearest_pack_kernels", st);
+    dim3 grid(cdiv(T, 4), B);
+    pack_tiles_kernel<<<grid, 128, 0, st>>>(verts, V, vtile, T, NG, vert4p, tinfo);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    dim3 g2(cdiv(NG, 4), B);
+    pack_groups_kernel<<<g2, 128, 0, st>>>(vgroup_off, T, NG, tinfo);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+// limit < 0: every query unlimited; else the queries whose exterior byte is non-zero are limited (see the kernel)
+int launch_nearest_tiles_query(const uint32_t* maskP, const uint32_t* maskG, const int* vtile, const int* vgroup_off,
+                               int b0, int nb, int V, int T, int NG, const float4* vert4p, const float4* tinfo,
+                               float limit, const uint8_t* exterior, int* argmin, float* minval, cudaStream_t st) {
+    if (nb == 0) return 0;
+    dim3 grid(cdiv(T, NT_WARPS), nb);
+    KernelTimer timer("nearest_kernel", st);
+    const float4* v4 = vert4p + (size_t)b0 * T * 32;
+    const float4* ti = tinfo + (size_t)b0 * (T + NG) * 2;
+    if (limit >= 0.f && exterior != nullptr)
+        nearest_tiles_kernel<true><<<grid, NT_WARPS * 32, 0, st>>>(v4, ti, maskP, maskG, vtile, vgroup_off, V, T, NG, limit,
+                                                                   exterior + (size_t)b0 * V, argmin + (size_t)b0 * V,
+                                                                   minval + (size_t)b0 * V);
+    else
+        nearest_tiles_kernel<false><<<grid, NT_WARPS * 32, 0, st>>>(v4, ti, maskP, maskG, vtile, vgroup_off, V, T, NG, -1.f,
+                                                                    nullptr, argmin + (size_t)b0 * V, minval + (size_t)b0 * V);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
 int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32_t* maskG, const int* vtile,
                          const int* vgroup_off, int B, int V, int T, int NG, float4* vert4p, float4* tinfo,
                          int* argmin, float* minval, cudaStream_t st) {
     if (B == 0) return 0;
-    {
-        KernelTimer timer("nearest_pack_kernels", st);
-        dim3 grid(cdiv(T, 4), B);
-        pack_tiles_kernel<<<grid, 128, 0, st>>>(verts, V, vtile, T, NG, vert4p, tinfo);
-        TUCH_LAUNCH_CHECK(); count_launch();
-        dim3 g2(cdiv(NG, 4), B);
-        pack_groups_kernel<<<g2, 128, 0, st>>>(vgroup_off, T, NG, tinfo);
-        TUCH_LAUNCH_CHECK(); count_launch();
-    }
-    {
-        dim3 grid(cdiv(T, NT_WARPS), B);
-        KernelTimer timer("nearest_kernel", st);
-        nearest_tiles_kernel<<<grid, NT_WARPS * 32, 0, st>>>(vert4p, tinfo, maskP, maskG, vtile, vgroup_off, V, T, NG, argmin,
-                                                             minval);
-    }
-    TUCH_LAUNCH_CHECK(); count_launch();
-    return 0;
+    if (int rc = launch_nearest_tiles_pack(verts, vtile, vgroup_off, B, V, T, NG, vert4p, tinfo, st)) return rc;
+    return launch_nearest_tiles_query(maskP, maskG, vtile, vgroup_off, 0, B, V, T, NG, vert4p, tinfo, -1.f, nullptr, argmin, minval, st);
 }
 
 }  // namespace tuch

@@ -229,9 +229,9 @@ contact_loss_kernel(const float* __restrict__ points, const int* __restrict__ ar
 
     float push = 0.f, pull = 0.f, n_push = 0.f, n_pull = 0.f;
     for (int i = threadIdx.x; i < n; i += CL_THREADS) {
-        const int j = am[i];
+        const int j0 = am[i], j = j0 < 0 ? i : j0;       // -1: no allowed vertex within the query's limit = infinitely far
         const float dx = p[3 * i] - p[3 * j], dy = p[3 * i + 1] - p[3 * j + 1], dz = p[3 * i + 2] - p[3 * j + 2];
-        const float d = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        const float d = j0 < 0 ? INFINITY : sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
         if (!ext[i]) {
             const float t = tanhf(d / 0.04f);
             push += t * t; n_push += 1.f;
@@ -263,9 +263,9 @@ contact_loss_kernel(const float* __restrict__ points, const int* __restrict__ ar
     for (int k = threadIdx.x; k < 3 * N; k += CL_THREADS) gf[k] = 0;      // partners may lie beyond counts[b]
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += CL_THREADS) {
-        const int j = am[i];
+        const int j0 = am[i], j = j0 < 0 ? i : j0;       // -1: no allowed vertex within the query's limit = infinitely far
         const float dx = p[3 * i] - p[3 * j], dy = p[3 * i + 1] - p[3 * j + 1], dz = p[3 * i + 2] - p[3 * j + 2];
-        const float d = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        const float d = j0 < 0 ? INFINITY : sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
         float a, s, w;
         if (!ext[i]) { a = 1.f; s = 0.04f; w = w_push; }
         else if (pull_mode == PULL_ALL || d < euclthres) { a = 0.005f; s = 0.005f; w = w_pull; }
@@ -313,9 +313,9 @@ contact_loss_chunk_kernel(const float* __restrict__ points, const int* __restric
 
     float push = 0.f, pull = 0.f, n_push = 0.f, n_pull = 0.f;
     for (int i = blockIdx.x * CL_THREADS + threadIdx.x; i < n; i += gridDim.x * CL_THREADS) {
-        const int j = argmin[(size_t)b * N + i];
+        const int j0 = argmin[(size_t)b * N + i], j = j0 < 0 ? i : j0;   // -1: nothing within the query's limit
         const float dx = p[3 * i] - p[3 * j], dy = p[3 * i + 1] - p[3 * j + 1], dz = p[3 * i + 2] - p[3 * j + 2];
-        const float d = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        const float d = j0 < 0 ? INFINITY : sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
         float a, s, t;
         if (!exterior[(size_t)b * N + i]) {
             a = 1.f; s = 0.04f; t = tanhf(d / 0.04f);

@@ -374,9 +374,10 @@ class Topology:
             raise TuchError('verts live on %s but the topology on %s' % (v.device, self.device))
         return v
 
-    def contact_query(self, verts, use_segments=True, want_nearest=True, want_winding=True):
+    def contact_query(self, verts, use_segments=True, want_nearest=True, want_winding=True, within=None):
         """Fused losses.py:76-93 for the whole batch -> dict(argmin int32[B,V], min_sq[B,V],
-        winding[B,V], exterior bool[B,V])."""
+        winding[B,V], exterior bool[B,V]).  within=r (metres): the nearest vertex only where losses.py:96-103
+        consumes it -- interior vertices and vertices with an allowed vertex within r; (-1, inf) elsewhere."""
         v = self._verts(verts)
         B = v.shape[0]
         out = {}
@@ -388,8 +389,14 @@ class Topology:
             w = torch.empty(B, self.V, device=v.device, dtype=torch.float32)
             ext = torch.empty(B, self.V, device=v.device, dtype=torch.uint8)
         with torch.cuda.device(v.device):
-            check(lib().tuch_contact_query(self._h, _ptr(v), B, int(bool(use_segments)), _ptr(am), _ptr(mn),
-                                           _ptr(w), _ptr(ext), _stream()), 'tuch_contact_query')
+            if within is not None:
+                if not (want_nearest and want_winding):
+                    raise TuchError('contact_query(within=...) needs the nearest-vertex and the winding outputs')
+                check(lib().tuch_contact_query_within(self._h, _ptr(v), B, int(bool(use_segments)), float(within), _ptr(am),
+                                                      _ptr(mn), _ptr(w), _ptr(ext), _stream()), 'tuch_contact_query_within')
+            else:
+                check(lib().tuch_contact_query(self._h, _ptr(v), B, int(bool(use_segments)), _ptr(am), _ptr(mn),
+                                               _ptr(w), _ptr(ext), _stream()), 'tuch_contact_query')
         out.update(argmin=am, min_sq=mn, winding=w, exterior=None if ext is None else ext.bool())
         return out
 
