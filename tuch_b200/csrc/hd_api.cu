@@ -79,8 +79,14 @@ TUCH_EXPORT int tuch_regressor_contact_loss(const tuch_topology* t, const float*
     uint8_t* ex = sc.get<uint8_t>(h_ex);
 
     // loss.py:251-270 -- exterior flags (winding + segment whitelist) and the masked nearest vertex
+    // With HD points the vertices' nearest vertex only decides which of them are "in contact" (min_sq < euclthres^2,
+    // hd_select): the search is limited to that radius; without, every exterior vertex is pulled (PULL_ALL below)
+    // and the search is unlimited.
     PackedClusters packed;
-    if (int rc = contact_query_impl(t, verts, B, 1, am, mn, nullptr, ex, nullptr, st, &packed)) return rc;
+    QueryStreams qs;
+    qs.nn = st;
+    if (use_hd && t->has_maskP && euclthres >= 0.f) qs.nn_limit = euclthres;
+    if (int rc = contact_query_impl(t, verts, B, 1, am, mn, nullptr, ex, nullptr, st, &packed, &qs)) return rc;
 
     if (!use_hd) {                                                    // loss.py:303-315
         return launch_contact_loss(verts, am, ex, valid, nullptr, B, V, 0.f, PULL_ALL, REDUCE_SUM, weight, g_loss,

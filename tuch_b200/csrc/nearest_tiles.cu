@@ -273,6 +273,47 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
     // true squared distance (<= 3.6e-7 (|v|^2 + |q|^2)).
     // thr: the running minimum with the query's share of the slack folded in, refreshed after every visit
     float thr = fmaf(st.best, 1.00001f, 4e-6f * q.w);
+    if (MIXED && !__any_sync(0xffffffffu, seeded)) {
+        // Every query of the warp is limited (most warps: interior vertices are a few per cent and clustered).  All
+        // candidates then lie within limit of this tile's own sphere, so the groups, and the tiles of a reachable
+        // group, are tested sphere against sphere with ONE LANE PER GROUP / TILE instead of one loop trip each
+        // (29 + ~35 trips of dependent loads, 75 % of this kernel's time before); the few survivors get the
+        // per-query test of the general loop below.
+        const float4 own = __ldg(ib + 2 * qt);
+        const float reach_r = own.w + 1.01f * limit + 1e-6f;
+        for (int g0 = 0; g0 < NG; g0 += 32) {
+            bool gcand = false;
+            if (g0 + lane < NG) {
+                const float4 gs = __ldg(ib + 2 * (T + g0 + lane));
+                const float gx = own.x - gs.x, gy = own.y - gs.y, gz = own.z - gs.z;
+                gcand = fmaf(sqrtf(fmaf(gz, gz, fmaf(gy, gy, gx * gx))), 0.9999f, -gs.w) <= reach_r;
+            }
+            for (unsigned gm = __ballot_sync(0xffffffffu, gcand); gm != 0u; gm &= gm - 1u) {
+                const int g = g0 + __ffs(gm) - 1;
+                const int t0 = __ldg(vgroup_off + g), t1 = __ldg(vgroup_off + g + 1);
+                for (int tb = t0; tb < t1; tb += 32) {
+                    bool tcand = false;
+                    if (tb + lane < t1) {
+                        const float4 s = __ldg(ib + 2 * (tb + lane));
+                        const float dx = own.x - s.x, dy = own.y - s.y, dz = own.z - s.z;
+                        tcand = fmaf(sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w) <= reach_r;
+                    }
+                    for (unsigned tm = __ballot_sync(0xffffffffu, tcand); tm != 0u; tm &= tm - 1u) {
+                        const int t = tb + __ffs(tm) - 1;
+                        const float4 s = __ldg(ib + 2 * t), s2 = __ldg(ib + 2 * t + 1);
+                        const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
+                        const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
+                        const bool reach = live && (lo <= 0.f || lo * lo <= fmaf(4e-6f, s2.x, thr));
+                        if (!__any_sync(0xffffffffu, reach)) continue;
+                        const uint32_t m = mcol[(size_t)t * mstride];
+                        if (!__any_sync(0xffffffffu, reach && m != 0u)) continue;
+                        nearest_visit_tile(vb, vtile, mcol, mstride, t, m, pad, q, st);
+                        thr = fmaf(st.best, 1.00001f, 4e-6f * q.w);
+                    }
+                }
+            }
+        }
+    } else
     for (int g = 0; g < NG; ++g) {
         const float4 gs = __ldg(ib + 2 * (T + g)), gs2 = __ldg(ib + 2 * (T + g) + 1);
         const float gx = q.x - gs.x, gy = q.y - gs.y, gz = q.z - gs.z;
