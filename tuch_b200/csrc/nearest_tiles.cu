@@ -325,20 +325,14 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
         const uint32_t* mp = mcol + (size_t)t0 * mstride;
         const float4* sp = ib + 2 * t0;
         for (int t = t0; t < t1; ++t, mp += mstride, sp += 2) {
-            uint32_t m = 0u;
-            if (!MIXED) m = *mp;
+            // requested up front: its L2 round trip overlaps the sphere test.  (Tried for the mixed kernel, whose few
+            // warps here run at low occupancy: a group's eight mask words requested together -- 70 registers,
+            // 447 against 363 us.)
+            const uint32_t m = *mp;
             const float4 s = __ldg(sp), s2 = __ldg(sp + 1);
             const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
             const float lo = fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w);
-            const bool reach = lo <= 0.f || lo * lo <= fmaf(4e-6f, s2.x, thr);
-            if (MIXED) {
-                // limited queries reach next to no tile: test the sphere first and only then wait for the mask
-                // word (an L2 round trip per tile; for unlimited queries, whose spheres mostly pass, the word is
-                // better requested up front)
-                if (!__any_sync(0xffffffffu, live && reach)) continue;
-                m = *mp;
-            }
-            const bool need = m != 0u && reach && (!MIXED || live);
+            const bool need = m != 0u && (!MIXED || live) && (lo <= 0.f || lo * lo <= fmaf(4e-6f, s2.x, thr));
             if (!__any_sync(0xffffffffu, need)) continue;
             if (__any_sync(0xffffffffu, tstar == t)) continue;          // evaluated for the whole warp above
             nearest_visit_tile(vb, vtile, mcol, mstride, t, m, pad, q, st);
