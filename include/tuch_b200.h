@@ -120,10 +120,10 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
 /* Winding-number evaluation inside tuch_contact_query.  Callers of the reference only consume the
  * flag `winding_numbers(...) <= 0.99` (losses.py:82, loss.py:262), so the default mode evaluates the
  * sum hierarchically: the faces are clustered once per topology (leaves of <= 16 faces, mid groups of
- * <= 8 leaves, top groups of <= 64 leaves); per body, nodes farther than 1.6 (leaves) / 2 (groups) radii
+ * <= 8 leaves, top groups of <= 64 leaves); per body, nodes farther than 1.4 (leaves) / 2 (groups) radii
  * from a query contribute through a
  * second-order multipole expansion of the solid-angle integrand (max abs error measured 1.05e-2 on the winding
- * number), nearer leaves are summed exactly, and every query whose value falls within 0.06 of the 0.99
+ * number), nearer leaves are summed exactly, and every query whose value falls within 0.10 of the 0.99
  * threshold is re-evaluated exactly over all faces -- the exterior flags are those of the exact sum.
  * TUCH_WINDING_EXACT sums all F solid angles for every query (values within 2e-5 of the reference).
  * The hierarchy is built from the template given to tuch_topology_set_template (HOST [V,3]) or, when
@@ -132,7 +132,7 @@ int tuch_topology_set_segments(tuch_topology* topo, int n_segments,
  * at hand (SMPL.v_template): the lazily built hierarchy depends on which body arrives first, and with it the
  * far-field rounding of the returned `winding` values (never the flags: every value within the band around the
  * threshold is re-evaluated over all faces).  In TUCH_WINDING_FAST mode `winding` is the hierarchical value:
- * within 1.5e-2 of the all-faces sum away from the threshold band, exact (2e-5) inside it. */
+ * within 2.5e-2 of the all-faces sum away from the threshold band, exact (2e-5) inside it. */
 #define TUCH_WINDING_EXACT 0
 #define TUCH_WINDING_FAST 1
 int tuch_topology_set_template(tuch_topology* topo, const float* verts_host);

@@ -47,7 +47,7 @@ def test_tree_disconnected_and_tiny():
     assert len(t['leaf_face']) == 1 and len(t['vtile']) == 1                       # small components share a leaf
 
 
-WC_BETA, WC_MARGIN = 1.6, 0.06          # tuch_b200/csrc/clusters.h
+WC_BETA, WC_MARGIN = 1.4, 0.10          # tuch_b200/csrc/clusters.h
 
 
 def test_far_field_expansion_matches_exact_solid_angles():

@@ -9,7 +9,7 @@ from conftest import golden
 pytestmark = pytest.mark.gpu
 # hierarchical winding numbers (tuch_b200/csrc/clusters.h): values within the re-evaluation margin of the 0.99
 # threshold are exact; elsewhere the far-field error must stay below a quarter of that margin
-WC_MARGIN = 0.06
+WC_MARGIN = 0.10
 FAR_FIELD_TOL = 0.25 * WC_MARGIN
 
 

@@ -300,6 +300,9 @@ int build_cluster_tree(const int* faces, int F, int V, const float* verts, Clust
     {   // faces: neighbours share an edge
         TreeBuilder tb;
         tb.N = F; tb.leaf = WC_LEAF; tb.mid_leaves = WC_MID_LEAVES; tb.top_leaves = WC_TOP_LEAVES;
+        // development knobs for the fan-out sweeps (scripts/proto/winding_work_model.py); the constants ship
+        if (const char* e = getenv("TUCH_WC_MID")) tb.mid_leaves = std::max(2, atoi(e));
+        if (const char* e = getenv("TUCH_WC_TOP")) tb.top_leaves = std::max(tb.mid_leaves, atoi(e));
         tb.leaf_items = &out.leaf_face; tb.mid_off = &out.mid_off; tb.top_off = &out.top_off;
         tb.cen.resize((size_t)F * 3);
         for (int t = 0; t < F; ++t)
@@ -1066,8 +1069,9 @@ int launch_cluster_finish(const ClusterJob& j, cudaStream_t st) {
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
     {
         dim3 grid(cdiv(Q, 256), j.B);
+        static const float env_margin = getenv("TUCH_WC_MARGIN") ? (float)atof(getenv("TUCH_WC_MARGIN")) : 0.f;   // dev knob
         cluster_finalize_kernel<<<grid, 256, 0, st>>>(j.partial, Q, j.S, j.winding, j.refine_list, j.q_counts, j.body_active,
-                                                      j.margin);
+                                                      env_margin > 0.f && j.points == nullptr ? env_margin : j.margin);
         TUCH_LAUNCH_CHECK(); count_launch();
     }
     {

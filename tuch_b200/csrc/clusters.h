@@ -16,17 +16,20 @@ constexpr int WC_WARPS = 8;          // warps per CTA of the winding kernel; one
 // folded-arm poses; time = pack + winding + exact re-evaluation, error = max |w_fast - w_all_faces|):
 //   (2.0, 2.5) 3.03 ms 3.9e-3 | (2.0, 2.0) 2.67 ms 7.7e-3 | (1.8, 2.0) 2.40 ms 9.2e-3 | (1.6, 2.0) 2.19 ms 1.05e-2
 //   (1.4, 2.0) 2.00 ms 1.76e-2;   exterior flags identical to the all-faces sum in every row.
+// Again with the refined leaves and the whole iteration as the clock (ms per stage-2 iteration at 256 bodies, leaf
+// radius / margin / max error): 1.6 / 0.06: 2.76, 1.07e-2 | 1.5 / 0.08: 2.70, 1.47e-2 | 1.4 / 0.10: 2.64, 1.93e-2 |
+// 1.3 / 0.13: 2.58, 2.69e-2 | 1.2 / 0.16: 2.57, 4.18e-2.
 // The flags only need |error| < WC_MARGIN (everything nearer the threshold is re-evaluated over all faces), so the
 // radii are chosen for time with the margin at >= 5x the measured error; tests/test_clusters_cpu.py bounds the
 // leaf-level error WITHOUT cancellation by half the margin.
-constexpr float WC_BETA = 1.6f;
+constexpr float WC_BETA = 1.4f;
 constexpr float WC_BETA_GROUP = 2.0f;
 // off-surface point queries (the 1 mm offset HD points of loss.py:295-297): interior points sit at 1.0, only 0.01
 // above the 0.99 threshold, so the far field opens later (3 / 3.5 radii) and every value within 0.02 of the
 // threshold -- 4x the largest far-field error measured for the looser on-surface radii -- is re-evaluated exactly
 constexpr float WC_BETA_POINTS = 3.0f, WC_BETA_GROUP_POINTS = 3.5f, WC_MARGIN_POINTS = 0.02f;
-constexpr float WC_MARGIN = 0.06f;   // |w - 0.99| below this is re-evaluated exactly (5.7 x the worst far-field
-                                     // error measured at these opening parameters: 1.05e-2)
+constexpr float WC_MARGIN = 0.10f;   // |w - 0.99| below this is re-evaluated exactly (5.2 x the worst far-field
+                                     // error measured at these opening parameters: 1.93e-2)
 
 // Host-side hierarchy of one mesh topology, built from the faces and ONE set of vertex positions
 // (the template, or the first body seen).
