@@ -708,6 +708,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, nullptr, vert4, st)) return rc;
 
     const bool nn_after_flags = nn_tiles && qs != nullptr && qs->nn_limit >= 0.f && exterior != nullptr && want_w;
+    bool nn_launched = false;
     int* am_nn = want_nn ? (argmin ? argmin : sc.get<int>(h_am)) : nullptr;
     float* mn_nn = want_nn ? (min_sq ? min_sq : sc.get<float>(h_mn)) : nullptr;
     if (nn_after_flags)                                   // tile / group spheres: independent of the inside test
@@ -728,7 +729,22 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                 if (int rc = launch_cluster_traverse(j, 0, j.B, qs->trav)) return rc;
                 TUCH_CUDA(cudaEventRecord(qs->after_trav, qs->trav));
                 TUCH_CUDA(cudaStreamWaitEvent(st, qs->after_trav, 0));
-                if (int rc = launch_cluster_finish(j, st)) return rc;
+                const bool nn_early = nn_after_flags && st_nn != st;
+                if (int rc = launch_cluster_finalize(j, nn_early ? exterior : nullptr, st)) return rc;
+                if (nn_early) {
+                    // The nearest vertex starts on the flags as the finalize pass knows them -- final outside the
+                    // band, "interior" (= searched without a limit, the safe side) for the few queries the exact
+                    // re-evaluation still has to decide -- instead of waiting for that re-evaluation and the flag
+                    // pass (~60 us of the chain behind the winding kernel).  It reads the flags while the kernels
+                    // below rewrite them (same value, or interior -> exterior): either value is fine.
+                    TUCH_CUDA(cudaEventRecord(qs->after_ext, st));
+                    TUCH_CUDA(cudaStreamWaitEvent(st_nn, qs->after_ext, 0));
+                    if (int rc = launch_nearest_tiles_query(t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, 0, B, V, T,
+                                                            t->NG, vert4, sc.get<float4>(h_tinfo), qs->nn_limit, exterior,
+                                                            am_nn, mn_nn, st_nn)) return rc;
+                    nn_launched = true;
+                }
+                if (int rc = launch_cluster_refine(j, st)) return rc;
             } else {
                 if (int rc = launch_winding_clusters(j, st)) return rc;
             }
@@ -745,7 +761,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
             uint8_t* any = segs ? sc.get<uint8_t>(h_any) : nullptr;
             if (any) TUCH_CUDA(cudaMemsetAsync(any, 0, (size_t)B, st));
             if (int rc = launch_exterior_init(w, B, V, exterior, any, st)) return rc;
-            if (nn_after_flags) {
+            if (nn_after_flags && !nn_launched) {
                 // the nearest vertex once the flags exist: interior vertices without a limit, exterior ones within
                 // nn_limit.  It reads the flags while the segment pass below may still turn some of them to
                 // "exterior": either value is fine, a vertex read as interior merely gets the unlimited answer

@@ -939,14 +939,19 @@ winding_cluster_kernel(const float* __restrict__ points, const int* __restrict__
 
 // sums the split partials in a fixed order, scales by 1 / (2 pi) and lists the queries whose value is
 // within WC_MARGIN of the 0.99 threshold of losses.py:82 for exact re-evaluation
+// early_ext (optional, [B][V]): the exterior flags as far as they are known before the exact re-evaluation -- final
+// for every query outside the band, 0 ("interior") for the listed ones, which is the safe side for the consumer that
+// starts on them early (the mixed nearest-vertex query searches interior vertices without a limit)
 __global__ void cluster_finalize_kernel(const float* __restrict__ partial, int V, int S, float* __restrict__ winding,
                                         int* __restrict__ refine_list, const int* __restrict__ q_counts,
-                                        const uint8_t* __restrict__ body_active, float margin) {
+                                        const uint8_t* __restrict__ body_active, float margin,
+                                        uint8_t* __restrict__ early_ext) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= V) return;
     if ((body_active != nullptr && !body_active[b]) || (q_counts != nullptr && q >= q_counts[b])) {
         winding[(size_t)b * V + q] = 0.f;
+        if (early_ext != nullptr) early_ext[(size_t)b * V + q] = 1;
         return;
     }
     const float* p = partial + (size_t)b * S * V + q;
@@ -954,10 +959,12 @@ __global__ void cluster_finalize_kernel(const float* __restrict__ partial, int V
     for (int s = 0; s < S; ++s) acc += p[(size_t)s * V];
     const float w = acc * 0.159154943091895336f;
     winding[(size_t)b * V + q] = w;
-    if (fabsf(w - 0.99f) < margin) {
+    const bool listed = fabsf(w - 0.99f) < margin;
+    if (listed) {
         const int k = atomicAdd(refine_list, 1);
         refine_list[1 + k] = b * V + q;
     }
+    if (early_ext != nullptr) early_ext[(size_t)b * V + q] = (!listed && w <= 0.99f) ? 1 : 0;
 }
 
 // exact winding number (all face slots, one lane per slot) of every listed query; one CTA per entry, its
@@ -1062,24 +1069,31 @@ int launch_cluster_traverse(const ClusterJob& j, int b0, int nb, cudaStream_t st
     return 0;
 }
 
-// split sum + list of the queries near the threshold, then their exact re-evaluation; whole job
-int launch_cluster_finish(const ClusterJob& j, cudaStream_t st) {
-    const float* points = j.points != nullptr ? j.points : j.verts;
+// split sum + list of the queries near the threshold ...
+int launch_cluster_finalize(const ClusterJob& j, uint8_t* early_ext, cudaStream_t st) {
     const int Q = j.points != nullptr ? j.Q : j.V;
     TUCH_CUDA(cudaMemsetAsync(j.refine_list, 0, sizeof(int), st));
-    {
-        dim3 grid(cdiv(Q, 256), j.B);
-        static const float env_margin = getenv("TUCH_WC_MARGIN") ? (float)atof(getenv("TUCH_WC_MARGIN")) : 0.f;   // dev knob
-        cluster_finalize_kernel<<<grid, 256, 0, st>>>(j.partial, Q, j.S, j.winding, j.refine_list, j.q_counts, j.body_active,
-                                                      env_margin > 0.f && j.points == nullptr ? env_margin : j.margin);
-        TUCH_LAUNCH_CHECK(); count_launch();
-    }
-    {
-        KernelTimer timer("winding_refine_kernel", st);
-        cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(points, j.ctri, Q, j.K, j.refine_list, j.winding, j.stats);
-    }
+    dim3 grid(cdiv(Q, 256), j.B);
+    static const float env_margin = getenv("TUCH_WC_MARGIN") ? (float)atof(getenv("TUCH_WC_MARGIN")) : 0.f;   // dev knob
+    cluster_finalize_kernel<<<grid, 256, 0, st>>>(j.partial, Q, j.S, j.winding, j.refine_list, j.q_counts, j.body_active,
+                                                  env_margin > 0.f && j.points == nullptr ? env_margin : j.margin, early_ext);
     TUCH_LAUNCH_CHECK(); count_launch();
     return 0;
+}
+
+// ... then their exact re-evaluation
+int launch_cluster_refine(const ClusterJob& j, cudaStream_t st) {
+    const float* points = j.points != nullptr ? j.points : j.verts;
+    const int Q = j.points != nullptr ? j.Q : j.V;
+    KernelTimer timer("winding_refine_kernel", st);
+    cluster_refine_kernel<<<sm_count() * 4, 256, 0, st>>>(points, j.ctri, Q, j.K, j.refine_list, j.winding, j.stats);
+    TUCH_LAUNCH_CHECK(); count_launch();
+    return 0;
+}
+
+int launch_cluster_finish(const ClusterJob& j, cudaStream_t st) {
+    if (int rc = launch_cluster_finalize(j, nullptr, st)) return rc;
+    return launch_cluster_refine(j, st);
 }
 
 // queries against the packed hierarchy of launch_cluster_pack

@@ -94,6 +94,8 @@ int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
 void cluster_pack_betas(const ClusterJob& job, float* beta_leaf, float* beta_group);   // the radii it bakes in
 int launch_cluster_traverse(const ClusterJob& job, int b0, int nb, cudaStream_t st);   // the winding kernel alone
+int launch_cluster_finalize(const ClusterJob& job, uint8_t* early_ext, cudaStream_t st);   // split sum + refine list
+int launch_cluster_refine(const ClusterJob& job, cudaStream_t st);    // exact re-evaluation of the listed queries
 int launch_cluster_finish(const ClusterJob& job, cudaStream_t st);    // finalize + exact refine
 int launch_cluster_query(const ClusterJob& job, cudaStream_t st);     // winding kernel + finalize + exact refine
 int launch_winding_clusters(const ClusterJob& job, cudaStream_t st);  // both
