@@ -265,26 +265,36 @@ class ContactFit:
         optimiser state, like a fresh begin_contact_fit()."""
         dev = self.body_pose.device
         to = lambda t: t.to(dev, non_blocking=True)
+
+        def put(dst, src):
+            # straight into the tensor the iteration reads when no conversion is needed (one op instead of two:
+            # this method is host-bound, ~25 small launches between two iterations of the end-to-end loop)
+            if src.dtype == dst.dtype and src.is_contiguous() and src.shape == dst.shape:
+                dst.copy_(src, non_blocking=True)
+            else:
+                dst.copy_(to(src))
         with torch.no_grad():
             pose = to(init_pose)
             self.global_orient.copy_(pose[:, :3])
             self.body_pose.copy_(pose[:, 3:])
-            self.betas.copy_(to(init_betas))
-            self.args['camera_t'].copy_(to(init_cam_t))
-            self.args['camera_center'].copy_(to(camera_center))
+            put(self.betas, init_betas)
+            put(self.args['camera_t'], init_cam_t)
+            put(self.args['camera_center'], camera_center)
             kp = to(keypoints_2d)
             self.args['joints_2d'].copy_(kp[:, :, :2])
             self.args['joints_conf'].copy_(kp[:, :, 2])
-            self.args['joints_conf'][:, self.owner.ign_joints] = 0.0
+            if getattr(self, '_ign_index', None) is None:
+                self._ign_index = torch.as_tensor(list(self.owner.ign_joints), device=dev, dtype=torch.long)
+            self.args['joints_conf'].index_fill_(1, self._ign_index, 0.0)
             if gt_contact_l3 is not None:
-                self.args['gt_contact'][0].copy_(to(gt_contact_l3))
+                put(self.args['gt_contact'][0], gt_contact_l3)
             if ignore_idxs is not None:
-                self.args['ignore_idxs'].copy_(to(ignore_idxs))
+                put(self.args['ignore_idxs'], ignore_idxs)
             if has_discrete_contact is not None:
-                self.args['has_discrete_contact'].copy_(to(has_discrete_contact))
-            for st in self.opt.state:
-                for t in st:
-                    t.zero_()
+                put(self.args['has_discrete_contact'], has_discrete_contact)
+            states = [t for st in self.opt.state for t in st]
+            if states:
+                torch._foreach_zero_(states)
             if self.native:
                 self._refresh_masks()
         return self
