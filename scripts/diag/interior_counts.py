@@ -36,3 +36,7 @@ for it in (1, 20, 60, 100):
         t_int = (inter[:, vt.clamp(min=0)] & ~pad).any(-1)
         print('iteration %d, %s: interior vertices %.2f %%, tiles with an interior vertex %.1f %%, in contact (< 2 cm) %.2f %%'
               % (it, name, 100 * inter.float().mean(), 100 * t_int.float().mean(), 100 * (q['min_sq'] < 4e-4).float().mean()))
+q = fit.topo.contact_query(fit.vertices, use_segments=True)
+inter = ~q['exterior']
+for r in (0.02, 0.04, 0.06, 0.08, 0.10, 0.15, 0.20):
+    print('interior vertices with an allowed vertex within %.2f m: %.1f %%' % (r, 100 * (q['min_sq'][inter] < r * r).float().mean()))

@@ -333,7 +333,7 @@ TUCH_EXPORT void tuch_topology_destroy(tuch_topology* t) {
     if (!t) return;
     free_dev(t->d_faces); free_dev(t->d_maskT); free_dev(t->d_strip_vid); free_dev(t->d_strip_fid);
     free_dev(t->d_leaf_face); free_dev(t->d_mid_off); free_dev(t->d_top_off); free_dev(t->d_vtile); free_dev(t->d_vgroup_off);
-    free_dev(t->d_maskP); free_dev(t->d_maskG); free_dev(t->d_stats);
+    free_dev(t->d_maskP); free_dev(t->d_maskG); free_dev(t->d_tile_any); free_dev(t->d_stats);
     free_dev(t->d_hd_row_off); free_dev(t->d_hd_cols); free_dev(t->d_hd_face); free_dev(t->d_hd_vals);
     free_regions(t); free_segments(t);
     delete t;
@@ -373,6 +373,10 @@ static int refresh_permuted_mask(tuch_topology* t, cudaStream_t st) {
     t->d_maskG = nullptr;
     TUCH_CUDA(cudaMalloc((void**)&t->d_maskG, sizeof(uint32_t) * (size_t)cdiv(t->NG, 32) * T * 32));
     if (int rc = launch_group_mask(t->d_maskP, t->d_vgroup_off, T, t->NG, t->d_maskG, st)) return rc;
+    free_dev(t->d_tile_any);
+    t->d_tile_any = nullptr;
+    TUCH_CUDA(cudaMalloc((void**)&t->d_tile_any, sizeof(uint32_t) * (size_t)T * cdiv(T, 32)));
+    if (int rc = launch_tile_any_mask(t->d_maskP, T, t->d_tile_any, st)) return rc;
     t->has_maskP = true;
     return 0;
 }
@@ -700,6 +704,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     const size_t h_mn = sc.plan((want_nn && !min_sq) ? sizeof(float) * (size_t)B * V : 0);
     const size_t h_apex = sc.plan(segs ? sizeof(float) * 3 * (size_t)B * (t->n_bands > 0 ? t->n_bands : 1) : 0);
     const size_t h_wl = sc.plan(segs ? sizeof(int) * ((size_t)B * t->n_sv + 1) : 0);
+    const size_t h_todo = sc.plan(qs != nullptr && qs->nn_limit >= 0.f ? sizeof(int) * ((size_t)B * V + 1) : 0);
     if (int rc = sc.commit(st)) return rc;
 
     float4* strip4 = want_w ? sc.get<float4>(h_tri) : nullptr;
@@ -739,9 +744,9 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                     // below rewrite them (same value, or interior -> exterior): either value is fine.
                     TUCH_CUDA(cudaEventRecord(qs->after_ext, st));
                     TUCH_CUDA(cudaStreamWaitEvent(st_nn, qs->after_ext, 0));
-                    if (int rc = launch_nearest_tiles_query(t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, 0, B, V, T,
+                    if (int rc = launch_nearest_tiles_query(t->d_maskP, t->d_maskG, t->d_tile_any, t->d_vtile, t->d_vgroup_off, 0, B, V, T,
                                                             t->NG, vert4, sc.get<float4>(h_tinfo), qs->nn_limit, exterior,
-                                                            am_nn, mn_nn, st_nn)) return rc;
+                                                            sc.get<int>(h_todo), am_nn, mn_nn, st_nn)) return rc;
                     nn_launched = true;
                 }
                 if (int rc = launch_cluster_refine(j, st)) return rc;
@@ -770,9 +775,9 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
                     TUCH_CUDA(cudaEventRecord(qs->after_ext, st));
                     TUCH_CUDA(cudaStreamWaitEvent(st_nn, qs->after_ext, 0));
                 }
-                if (int rc = launch_nearest_tiles_query(t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, 0, B, V, T, t->NG,
-                                                        vert4, sc.get<float4>(h_tinfo), qs->nn_limit, exterior, am_nn, mn_nn,
-                                                        st_nn)) return rc;
+                if (int rc = launch_nearest_tiles_query(t->d_maskP, t->d_maskG, t->d_tile_any, t->d_vtile, t->d_vgroup_off, 0, B, V, T, t->NG,
+                                                        vert4, sc.get<float4>(h_tinfo), qs->nn_limit, exterior, sc.get<int>(h_todo),
+                                                        am_nn, mn_nn, st_nn)) return rc;
             }
             if (segs) {
                 float* apex = sc.get<float>(h_apex);
@@ -787,7 +792,7 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
         int* am = am_nn;
         float* mn = mn_nn;
         if (nn_tiles) {
-            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_maskG, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4,
+            if (int rc = launch_nearest_tiles(verts, t->d_maskP, t->d_maskG, t->d_tile_any, t->d_vtile, t->d_vgroup_off, B, V, T, t->NG, vert4,
                                               sc.get<float4>(h_tinfo), am, mn, st_nn)) return rc;
         } else {
             if (int rc = launch_nearest(vert4, t->d_maskT, B, V, Vp, t->Vq, am, mn, st)) return rc;

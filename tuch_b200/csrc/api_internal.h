@@ -20,6 +20,7 @@ struct tuch_topology {
     std::atomic<bool> has_clusters{false};   // published last (release) by install_clusters; the lazy build of the
                                              // first query may run while other threads read it (acquire)
     uint32_t* d_maskG = nullptr;       // per-group summary of d_maskP (any unmasked row in the tile group)
+    uint32_t* d_tile_any = nullptr;    // per (query tile, candidate tile) summary: any unmasked pair at all
     uint32_t* d_maskP = nullptr;       // geodesic mask in cluster order (nearest_tiles.cu); valid when both
     bool has_maskP = false;            // the mask and the hierarchy exist
     int winding_mode = 1;              // TUCH_WINDING_FAST

@@ -80,15 +80,17 @@ struct ClusterJob {
 int launch_permute_mask(const uint32_t* maskT, int Vq, const int* vtile, int T, uint32_t* maskP, cudaStream_t st);
 // tinfo: [B][T + NG][2] float4 -- tile spheres, then group spheres
 int launch_group_mask(const uint32_t* maskP, const int* vgroup_off, int T, int NG, uint32_t* maskG, cudaStream_t st);
-int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32_t* maskG, const int* vtile,
+// tile_any [T][ceil(T / 32)]: bit (t & 31) of tile_any[qt][t >> 5] = some query of tile qt has an unmasked row in tile t
+int launch_tile_any_mask(const uint32_t* maskP, int T, uint32_t* tile_any, cudaStream_t st);
+int launch_nearest_tiles(const float* verts, const uint32_t* maskP, const uint32_t* maskG, const uint32_t* tile_any, const int* vtile,
                          const int* vgroup_off, int B, int V, int T, int NG, float4* vert4p, float4* tinfo,
                          int* argmin, float* minval, cudaStream_t st);
 
 int launch_nearest_tiles_pack(const float* verts, const int* vtile, const int* vgroup_off, int B, int V, int T, int NG,
                               float4* vert4p, float4* tinfo, cudaStream_t st);
-int launch_nearest_tiles_query(const uint32_t* maskP, const uint32_t* maskG, const int* vtile, const int* vgroup_off,
+int launch_nearest_tiles_query(const uint32_t* maskP, const uint32_t* maskG, const uint32_t* tile_any, const int* vtile, const int* vgroup_off,
                                int b0, int nb, int V, int T, int NG, const float4* vert4p, const float4* tinfo,
-                               float limit, const uint8_t* exterior, int* argmin, float* minval, cudaStream_t st);
+                               float limit, const uint8_t* exterior, int* todo_list, int* argmin, float* minval, cudaStream_t st);
 
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
