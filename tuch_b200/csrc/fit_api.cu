@@ -132,7 +132,19 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
         TUCH_CUDA(cudaStreamWaitEvent(side->hi, side->begin, 0));
         st = side->hi;
     }
-    const cudaStream_t s_nn = side ? side->lo : st, s2 = side ? side->s2 : st;
+    // The contact term (launch_contact_loss below, PULL_THRESHOLD) reads the nearest allowed vertex of interior
+    // vertices and of exterior vertices closer than euclthres only: the query is limited accordingly (nn_limit),
+    // which leaves loss, gradients and parameters bit-identical (tests/test_objective_gpu.py compares with the
+    // composition over the unlimited query) at a fifth of the nearest-vertex work.
+    // (Below FIT_NN_LIMIT_FROM bodies the unlimited query hides behind the inside test anyway and a search behind
+    // the flags would only lengthen the chain: 32 bodies 0.687 against 0.716 ms.)
+    static const bool nn_full = getenv("TUCH_FIT_NN_FULL") != nullptr && atoi(getenv("TUCH_FIT_NN_FULL")) != 0;   // A/B
+    static const int nn_from = getenv("TUCH_FIT_NN_FROM") != nullptr ? atoi(getenv("TUCH_FIT_NN_FROM")) : FIT_NN_LIMIT_FROM;
+    const bool nn_limited = !nn_full && topo->has_maskP && B >= nn_from;
+    // the limited search runs behind the winding kernel, on its stream: at the chain's priority, so that it is not
+    // locked out by the segment pass, whose CTAs fill the register file (TUCH_FIT_NN_LO=1: the low-priority stream)
+    static const bool nn_lo = getenv("TUCH_FIT_NN_LO") != nullptr && atoi(getenv("TUCH_FIT_NN_LO")) != 0;
+    const cudaStream_t s_nn = side ? (nn_limited && !nn_lo ? side->mid : side->lo) : st, s2 = side ? side->s2 : st;
 
     // ---- SMPL forward (split pose; advances the Adam step counters); the output joints follow on side 2
     LbsBuffers w;
@@ -171,17 +183,9 @@ TUCH_EXPORT int tuch_contact_fit_step(const tuch_smpl* smpl, const tuch_topology
     if (side) TUCH_CUDA(cudaEventRecord(side->join2, s2));
     // ---- losses.py:73-105: inside test + allowed self-intersections (winding kernel on `mid`, the rest on the
     //      chain), masked nearest vertex (`lo`)
-    // The contact term (launch_contact_loss below, PULL_THRESHOLD) reads the nearest allowed vertex of interior
-    // vertices and of exterior vertices closer than euclthres only: the query is limited accordingly (nn_limit),
-    // which leaves loss, gradients and parameters bit-identical (tests/test_objective_gpu.py compares with the
-    // composition over the unlimited query) at a fifth of the nearest-vertex work.
     QueryStreams qs;
     qs.nn = st;
-    static const bool nn_full = getenv("TUCH_FIT_NN_FULL") != nullptr && atoi(getenv("TUCH_FIT_NN_FULL")) != 0;   // A/B
-    // (below FIT_NN_LIMIT_FROM bodies the unlimited query hides behind the inside test anyway and the second pass
-    // would only lengthen the chain: 32 bodies 0.687 against 0.716 ms)
-    static const int nn_from = getenv("TUCH_FIT_NN_FROM") != nullptr ? atoi(getenv("TUCH_FIT_NN_FROM")) : FIT_NN_LIMIT_FROM;
-    if (!nn_full && topo->has_maskP && B >= nn_from) qs.nn_limit = a->euclthres > 0.f ? a->euclthres : 0.f;
+    if (nn_limited) qs.nn_limit = a->euclthres > 0.f ? a->euclthres : 0.f;
     if (side) {
         qs.nn = s_nn; qs.trav = side->mid; qs.split_trav = true;
         qs.before_trav = side->before_trav; qs.after_trav = side->after_trav; qs.after_ext = side->after_ext;

@@ -216,13 +216,14 @@ __device__ __forceinline__ void nearest_visit_tile(const float4* __restrict__ vb
 //
 // MIXED: an exterior query only counts candidates within `limit` (metres); an interior one has no limit.
 // SMPLify-DC's contact term consumes the nearest allowed vertex of an INTERIOR vertex at any distance, but
-// of an EXTERIOR vertex only when it is closer than euclthres (losses.py:96-103, 2 cm): with the limit as the
-// initial bound of the exterior queries nearly every tile is pruned at the group level, and the seeding pass runs
-// for the interior queries only.  A limited query with an allowed vertex inside the limit gets exactly the
-// unlimited answer (same values, same tie-breaking); one without gets (-1, +inf) -- or (0, +inf), as in the
-// unlimited case, when its mask column is empty.  The limit carries the slack by which an fp32 expansion-form value
-// can exceed the true squared distance.
-// exterior (MIXED only, [B][V]): the inside test's flags; 0 = interior = unlimited query.
+// of an EXTERIOR vertex only when it is closer than euclthres (losses.py:96-103, 2 cm).  In this mode the kernel is a
+// radius search for every query (stage A below: `limit` for the exterior ones, interior_first for the interior
+// ones) and the unlimited search moves out: the interior queries without an allowed vertex inside their first
+// radius are appended to todo_list for nearest_single_kernel.  A query with an allowed vertex inside its radius gets
+// exactly the unlimited answer (same values, same tie-breaking); an exterior one without gets (-1, +inf) -- or
+// (0, +inf), as in the unlimited case, when its mask column is empty.  The radius carries the slack by which an fp32
+// expansion-form value can exceed the true squared distance.
+// exterior (MIXED only, [B][V]): the inside test's flags; 0 = interior.
 template <bool MIXED>
 __global__ void __launch_bounds__(NT_WARPS * 32)
 nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
@@ -401,14 +402,15 @@ nearest_tiles_kernel(const float4* __restrict__ vert4p, const float4* __restrict
 // the bounding phase and rows in the evaluation phase, so the dependent chain is ~30 round trips instead of the
 // ~150 of a lane of nearest_tiles_kernel.  Same values (row_value), same winner: the smallest value, the lowest
 // original row id among equal ones, (0, +inf) for an empty mask column.
-// Dynamic shared memory: T floats per warp (the tiles' lower bounds).
+// Dynamic shared memory: 2 T words per warp (the tiles' lower bounds and the query's mask words).
 __global__ void __launch_bounds__(NT_WARPS * 32)
 nearest_single_kernel(const float4* __restrict__ vert4p, const float4* __restrict__ tinfo,
                       const uint32_t* __restrict__ maskP, const int* __restrict__ vtile, int V, int T, int NG,
                       const int* __restrict__ todo_list, int* __restrict__ argmin_out, float* __restrict__ min_out) {
     extern __shared__ float s_lo[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* lo = s_lo + (size_t)warp * T;
+    float* lo = s_lo + (size_t)warp * 2 * T;
+    uint32_t* mw = (uint32_t*)(lo + T);                              // the query's mask word of every tile
     const size_t mstride = (size_t)T * 32;
     const int n = todo_list[0];
     for (int e = blockIdx.x * NT_WARPS + warp; e < n; e += gridDim.x * NT_WARPS) {
@@ -422,7 +424,9 @@ nearest_single_kernel(const float4* __restrict__ vert4p, const float4* __restric
         float vmax2 = 0.f;           // largest |v|^2 of any candidate: the slack of the pruning test below
         for (int t = lane; t < T; t += 32) {
             float v = INFINITY;
-            if (mcol[(size_t)t * mstride] != 0u) {
+            const uint32_t m = mcol[(size_t)t * mstride];
+            mw[t] = m;
+            if (m != 0u) {
                 const float4 s = __ldg(ib + 2 * t);
                 const float dx = q.x - s.x, dy = q.y - s.y, dz = q.z - s.z;
                 v = fmaxf(fmaf(sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), 0.9999f, -s.w), 0.f);
@@ -452,7 +456,7 @@ nearest_single_kernel(const float4* __restrict__ vert4p, const float4* __restric
             }
             if (mt < 0 || m == INFINITY) break;
             if (!(m * m <= fmaf(wbest, 1.00001f, slack))) break;       // nor can any other tile: m is the smallest bound
-            const uint32_t bits = mcol[(size_t)mt * mstride];
+            const uint32_t bits = mw[mt];
             const int rid = vtile[mt * 32 + lane];
             if (((bits >> lane) & 1u) && rid >= 0) {
                 const float p = row_value(__ldg(vb + mt * 32 + lane), q);
@@ -536,9 +540,9 @@ int launch_nearest_tiles_query(const uint32_t* maskP, const uint32_t* maskG, con
                                                                    first, exterior + (size_t)b0 * V, todo_list,
                                                                    argmin + (size_t)b0 * V, minval + (size_t)b0 * V);
         TUCH_LAUNCH_CHECK(); count_launch();
-        const size_t smem = sizeof(float) * (size_t)T * NT_WARPS;
+        const size_t smem = sizeof(float) * 2 * (size_t)T * NT_WARPS;
         TUCH_REQUIRE(smem <= 48 * 1024, "nearest vertex: %d vertex tiles exceed the shared memory of the single-query kernel", T);
-        nearest_single_kernel<<<sm_count() * 8, NT_WARPS * 32, smem, st>>>(v4, ti, maskP, vtile, V, T, NG, todo_list,
+        nearest_single_kernel<<<sm_count() * 32, NT_WARPS * 32, smem, st>>>(v4, ti, maskP, vtile, V, T, NG, todo_list,
                                                                             argmin + (size_t)b0 * V, minval + (size_t)b0 * V);
     } else {
         nearest_tiles_kernel<false><<<grid, NT_WARPS * 32, 0, st>>>(v4, ti, maskP, maskG, tile_any, vtile, vgroup_off, V, T, NG, -1.f,
