@@ -28,7 +28,8 @@ namespace {
 //   s2   the joint-side terms (output joints, reprojection, pose prior, region minima; the per-joint reduction of
 //        the SMPL backward)
 //   mid  the winding kernel
-//   lo   the masked nearest vertex
+//   lo   the masked nearest vertex when it is searched without a limit (small batches); the limited search of
+//        larger batches runs behind the winding kernel on `mid`
 // The caller's stream only forks into `hi` at the start and joins it at the end.  Events and waits are capturable:
 // in a CUDA graph the forks / joins become plain dependencies and the kernel nodes keep their stream's priority.
 //
@@ -36,11 +37,11 @@ namespace {
 // equal-priority kernels in launch order, so the two big kernels run one after the other and only overlap at their
 // tails, and a small kernel launched behind a big one on another stream waits until that kernel's whole grid has
 // been DISPATCHED.  The iteration is bound by the sum of its kernels' work, not by exposed latency: giving the
-// chain priority moves its kernels forward but slows the nearest-vertex kernel by as much.  Measured, ms per
-// iteration, all streams at one priority / hi = s2 = mid above lo: 8 bodies 0.388 / 0.390, 32: 0.753 / 0.733,
-// 64: 1.179 / 1.130, 128: 1.955 / 1.991, 256: 3.607 / 3.690 (more than two levels change nothing).  So below
-// FIT_PRIORITY_BELOW bodies, where no kernel fills the GPU for long and the inside test is the longer chain, the
-// nearest vertex runs at low priority; from there on everything runs at one priority.
+// chain priority moves its kernels forward but slows the nearest-vertex kernel by as much.  Measured with the
+// unlimited nearest-vertex query, ms per iteration, all streams at one priority / hi = s2 = mid above lo: 8 bodies
+// 0.388 / 0.390, 32: 0.753 / 0.733, 64: 1.179 / 1.130, 128: 1.955 / 1.991, 256: 3.607 / 3.690; with the limited
+// query: 64: 1.066 / 1.033, 128: 1.691 / 1.600, 256: 2.937 / 2.894 (more than two levels change nothing).  The
+// streams are prioritised at every batch size.
 // Also tried at 256 bodies: the nearest-vertex query in two launches, one ahead of the hierarchy pack and one behind
 // the winding kernel, so that the pack is overlapped too: 3.52 against 3.53 ms eager, no gain (the pack kernel's
 // CTAs fill the register file, nothing co-resides with them).
