@@ -413,7 +413,7 @@ def run_extras(rig, a, s, fit, iters_done, host, upload, args):
         res['betas'] = tdist.gather_bodies(betas, N4)
         res['verts'] = tdist.gather_bodies(verts, N4)
     run4()                                                                      # captures both stages
-    ms, wall = rig.timed(run4, 2)
+    ms, wall = rig.timed(run4, 3, warmup=1)
     ident = None
     if world > 1 and rank == 0:                                                 # the same job on ONE GPU: bit-identical?
         allb = {k: rig.t(a4['inp'][k]) for k in INPUT_KEYS}
