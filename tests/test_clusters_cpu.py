@@ -134,3 +134,69 @@ print(json.dumps(dict(K=len(leaf), NM=len(t['mid_off']) - 1, NT=len(t['top_off']
     for k in ('K', 'NM', 'NT', 'T', 'mid_off'):
         assert out['plain'][k] == out['refined'][k], k
     assert out['refined']['r3'] < 0.85 * out['plain']['r3'], (out['refined']['r3'], out['plain']['r3'])
+
+
+def _raw_moments(tris, p):
+    """The 23 raw sums NodeMoments::add accumulates (tuch_b200/csrc/clusters.cu), in float64, about centre p."""
+    out = np.zeros(23)
+    for t in tris:
+        a, b, g = t - p
+        n = 0.5 * np.cross(b - a, g - a)
+        h = (a + b + g) / 3
+        S = sum(np.outer(x, x) for x in (0.5 * (a + b), 0.5 * (b + g), 0.5 * (g + a))) / 3
+        out[0:3] += n
+        out[3] += n @ h
+        out[4:7] += n * h
+        out[7] += n[0] * h[1] + n[1] * h[0]
+        out[8] += n[0] * h[2] + n[2] * h[0]
+        out[9] += n[1] * h[2] + n[2] * h[1]
+        out[10:13] += 2 * S @ n + n * np.trace(S)
+        nx, ny, nz = n
+        sxx, syy, szz, sxy, sxz, syz = S[0, 0], S[1, 1], S[2, 2], S[0, 1], S[0, 2], S[1, 2]
+        out[13:16] += [nx * sxx, ny * syy, nz * szz]
+        out[16] += 2 * nx * sxy + ny * sxx
+        out[17] += 2 * nx * sxz + nz * sxx
+        out[18] += 2 * ny * sxy + nx * syy
+        out[19] += 2 * ny * syz + nz * syy
+        out[20] += 2 * nz * sxz + nx * szz
+        out[21] += 2 * nz * syz + ny * szz
+        out[22] += 2 * (nx * syz + ny * sxz + nz * sxy)
+    return out
+
+
+def _shifted(s, d):
+    """clusters.cu add_shifted: the sums of a child about its own centre re-expressed about a centre d away."""
+    dx, dy, dz = d
+    m0x, m0y, m0z, tr, qxx, qyy, qzz, qxy, qxz, qyz = s[:10]
+    dm, d2 = d @ s[:3], d @ d
+    trd = tr + dm
+    o = np.zeros(23)
+    o[0:3] = s[0:3]
+    o[3] = trd
+    o[4:7] = [qxx + m0x * dx, qyy + m0y * dy, qzz + m0z * dz]
+    o[7:10] = [qxy + m0x * dy + m0y * dx, qxz + m0x * dz + m0z * dx, qyz + m0y * dz + m0z * dy]
+    o[10] = s[10] + 2 * (2 * qxx * dx + qxy * dy + qxz * dz) + 2 * dx * trd + d2 * m0x
+    o[11] = s[11] + 2 * (qxy * dx + 2 * qyy * dy + qyz * dz) + 2 * dy * trd + d2 * m0y
+    o[12] = s[12] + 2 * (qxz * dx + qyz * dy + 2 * qzz * dz) + 2 * dz * trd + d2 * m0z
+    o[13] = s[13] + 2 * dx * qxx + dx * dx * m0x
+    o[14] = s[14] + 2 * dy * qyy + dy * dy * m0y
+    o[15] = s[15] + 2 * dz * qzz + dz * dz * m0z
+    o[16] = s[16] + 2 * (dx * qxy + dy * qxx) + dx * dx * m0y + 2 * dx * dy * m0x
+    o[17] = s[17] + 2 * (dx * qxz + dz * qxx) + dx * dx * m0z + 2 * dx * dz * m0x
+    o[18] = s[18] + 2 * (dy * qxy + dx * qyy) + dy * dy * m0x + 2 * dx * dy * m0y
+    o[19] = s[19] + 2 * (dy * qyz + dz * qyy) + dy * dy * m0z + 2 * dy * dz * m0y
+    o[20] = s[20] + 2 * (dz * qxz + dx * qzz) + dz * dz * m0x + 2 * dx * dz * m0z
+    o[21] = s[21] + 2 * (dz * qyz + dy * qzz) + dz * dz * m0y + 2 * dy * dz * m0z
+    o[22] = s[22] + 2 * (dx * qyz + dy * qxz + dz * qxy) + 2 * (dx * dy * m0z + dx * dz * m0y + dy * dz * m0x)
+    return o
+
+
+def test_child_moments_shift_to_the_parent_centre_exactly():
+    """The pack kernel forms group nodes from their children's moments (add_shifted).  The identities are exact:
+    in float64 the shifted sums of two child clusters add up to the sums taken straight about the parent's centre."""
+    rng = np.random.default_rng(5)
+    tris_a, tris_b = rng.normal(size=(7, 3, 3)), rng.normal(size=(5, 3, 3)) + 2.0
+    pa, pb, p = tris_a.mean((0, 1)), tris_b.mean((0, 1)), rng.normal(size=3)
+    direct = _raw_moments(np.concatenate([tris_a, tris_b]), p)
+    combined = _shifted(_raw_moments(tris_a, pa), pa - p) + _shifted(_raw_moments(tris_b, pb), pb - p)
+    assert np.abs(direct - combined).max() < 1e-11 * np.abs(direct).max()
