@@ -176,7 +176,8 @@ int tuch_contact_query(const tuch_topology* topo, const float* verts, int B, int
 /* The same query with the nearest vertex restricted to what SMPLify-DC's contact term consumes (losses.py:96-103:
  * the nearest allowed vertex of every INTERIOR vertex, and of an exterior vertex only when it is closer than
  * euclthres): argmin / min_sq are exactly tuch_contact_query's for every interior vertex (before the segment
- * whitelist) and for every vertex with an allowed vertex within `radius` metres, and (-1, +inf) for the others
+ * whitelist) and for every vertex with an allowed vertex within `radius` metres, and (-1, +inf) -- or, on meshes of
+ * more than 49,152 vertices, still tuch_contact_query's answer -- for the others
  * ((0, +inf), as above, for a vertex whose mask column is empty).  tuch_contact_loss reads -1 as "infinitely far".
  * About a fifth of the unlimited query's work at radius = 0.02.  exterior and one of argmin / min_sq are required. */
 int tuch_contact_query_within(const tuch_topology* topo, const float* verts, int B, int use_segments, float radius,

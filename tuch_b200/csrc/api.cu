@@ -712,7 +712,8 @@ int contact_query_impl(const tuch_topology* t, const float* verts, int B, int us
     if (vert4 != nullptr && !nn_tiles)
         if (int rc = launch_pack_mesh(verts, t->d_faces, B, V, t->F, Fp, Vp, nullptr, vert4, st)) return rc;
 
-    const bool nn_after_flags = nn_tiles && qs != nullptr && qs->nn_limit >= 0.f && exterior != nullptr && want_w;
+    const bool nn_after_flags = nn_tiles && qs != nullptr && qs->nn_limit >= 0.f && exterior != nullptr && want_w &&
+                                nearest_limited_supported(T);      // else: the unlimited query, which answers every vertex
     bool nn_launched = false;
     int* am_nn = want_nn ? (argmin ? argmin : sc.get<int>(h_am)) : nullptr;
     float* mn_nn = want_nn ? (min_sq ? min_sq : sc.get<float>(h_mn)) : nullptr;

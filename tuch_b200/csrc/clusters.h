@@ -92,6 +92,9 @@ int launch_nearest_tiles_query(const uint32_t* maskP, const uint32_t* maskG, con
                                int b0, int nb, int V, int T, int NG, const float4* vert4p, const float4* tinfo,
                                float limit, const uint8_t* exterior, int* todo_list, int* argmin, float* minval, cudaStream_t st);
 
+// the radius-limited query needs 2 T words of shared memory per warp of its single-query kernel (48 KB per CTA)
+inline bool nearest_limited_supported(int T) { return (size_t)T * 2 * 4 * sizeof(float) <= 48 * 1024; }
+
 int cluster_splits(int B, int T, int NT, int sm_count);
 int launch_cluster_pack(const ClusterJob& job, cudaStream_t st);      // node records + packed leaf triangles
 void cluster_pack_betas(const ClusterJob& job, float* beta_leaf, float* beta_group);   // the radii it bakes in
